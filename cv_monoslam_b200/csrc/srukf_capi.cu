@@ -1,0 +1,436 @@
+// srukf_capi.cu -- C ABI (include/srukf.h) over the CUDA kernels.  No CPU fallback: every entry
+// point needs a CUDA device and fails with SRUKF_ENODEV / SRUKF_ECUDA otherwise.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "srukf_device.cuh"
+
+namespace srukf {
+struct StepPtrs {
+  double* x; double* S; const double* u; const double* z; const uint8_t* matched;
+  double* hbar; double* si; uint8_t* visible; double* cshift; double* pxyr; double* rsig;
+  double* dZ; double* U; double* G; uint32_t* flags; int chunk0;
+};
+cudaError_t configure_kernels(const DevParams& p);
+size_t predict_smem_bytes(const DevParams& p);
+void launch_predict(const DevParams& p, const StepPtrs& q, int nblocks, bool motion, bool meas, bool save_rsig,
+                    cudaStream_t st);
+void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st);
+void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, cudaStream_t st);
+void launch_pack(int B, int n, int ntri, const double* dense, double* packed, cudaStream_t st);
+void launch_unpack(int B, int n, int ntri, const double* packed, double* dense, cudaStream_t st);
+void launch_cov_block(int B, int n, int ntri, const double* S, int r0, int nr, double* out, cudaStream_t st);
+void launch_stats(int B, int n, int ntri, const double* x, const double* S, const double* truth, double* perf,
+                  const uint32_t* flags, double* out, cudaStream_t st);
+}  // namespace srukf
+
+using namespace srukf;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  g_err = what;
+  if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+  return code;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? SRUKF_ENOMEM : SRUKF_ECUDA, #x, e_); } while (0)
+
+struct srukf_handle {
+  int device = 0;
+  DevParams p{};
+  SrukfParams prm{};
+  cudaStream_t stream = nullptr;
+  // state
+  double *x = nullptr, *S = nullptr;
+  // per-step inputs (device copies for the host-pointer API)
+  double *u = nullptr, *z = nullptr; uint8_t* matched = nullptr;
+  // prediction outputs
+  double *hbar = nullptr, *si = nullptr, *cshift = nullptr, *pxyr = nullptr; uint8_t* visible = nullptr;
+  uint32_t* flags = nullptr;
+  // scratch
+  int chunk = 0;           // filters per pipeline pass of srukf_step
+  double *dZ = nullptr, *U = nullptr, *G = nullptr;
+  // split-API persistent intermediates (allocated on first use)
+  double *rsig = nullptr, *dZ_all = nullptr, *U_all = nullptr, *G_all = nullptr;
+  int phase = 0;           // 0 idle, 1 motion done, 2 measurement done
+  double *perf = nullptr, *stats_out = nullptr, *truth = nullptr;
+  uint64_t launches = 0;
+};
+
+extern "C" {
+
+void srukf_default_params(SrukfParams* p) {
+  // CSLAM::initializeParameters, SLAM.cpp:158-343
+  p->cam_dx = 0.0028; p->cam_dy = 0.0028; p->cam_cx = 310.1129; p->cam_cy = 236.7526;
+  p->cam_k1 = 0.0001; p->cam_k2 = 0.0; p->cam_f = 2.1735;
+  p->image_width = 640; p->image_height = 480;
+  p->a1 = 8; p->a2 = 8; p->a3 = 8; p->a4 = 8;
+  p->sigma_measure = 3.0;
+  p->weight_type = 0; p->alpha = 1e-3; p->beta = 2;
+  p->epsilon = 1e-13;
+  p->newton_iters = 100;
+  p->downdate_mode = 0;
+}
+
+const char* srukf_last_error(void) { return g_err.c_str(); }
+const char* srukf_version(void) { return "srukf-b200 0.1 (sm_100a, fp64)"; }
+
+static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
+  d.B = B; d.L = L; d.n = 6 * L + 4; d.nf = 6 * L; d.Na = d.n + 5; d.P = 2 * d.Na + 1;
+  d.ntri = d.n * (d.n + 1) / 2;
+  d.cam_dx = s.cam_dx; d.cam_dy = s.cam_dy; d.cam_cx = s.cam_cx; d.cam_cy = s.cam_cy;
+  d.cam_k1 = s.cam_k1; d.cam_k2 = s.cam_k2;
+  d.f1 = s.cam_f / s.cam_dx; d.f2 = s.cam_f / s.cam_dy;  // SLAM.cpp:336-337
+  d.img_w = s.image_width; d.img_h = s.image_height;
+  d.a1 = s.a1; d.a2 = s.a2; d.a3 = s.a3; d.a4 = s.a4; d.sigma_measure = s.sigma_measure;
+  d.epsilon = s.epsilon; d.newton_iters = s.newton_iters;
+  // calculateSampleParameter, SLAM.cpp:1050-1103 (operation order kept)
+  const int Na = d.Na;
+  double wm0, wc0, wi, wi_sr, gamma;
+  if (s.weight_type == 0) {
+    wm0 = 1.0 - Na / 3.0; wc0 = 1.0 - Na / 3.0;
+    wi = (1.0 - wc0) / (2 * Na); wi_sr = std::sqrt(wi);
+    gamma = std::sqrt(Na / (1.0 - wm0));
+  } else if (s.weight_type == 1) {
+    double kappa = 0;
+    double lambda = std::pow(s.alpha, 2) * (Na + kappa) - Na;
+    gamma = std::sqrt(Na + lambda);
+    wm0 = lambda / (Na + lambda);
+    wc0 = wm0 + (1 - std::pow(s.alpha, 2) + s.beta);
+    wi = 1.0 / (2 * (Na + lambda)); wi_sr = std::sqrt(std::fabs(wi));
+  } else {
+    gamma = std::sqrt(3.0 * Na / 2.0);
+    wm0 = 1.0 / 3.0; wc0 = 1.0 / 3.0;
+    wi = 1.0 / (3.0 * Na); wi_sr = std::sqrt(wi);
+  }
+  d.gamma = gamma; d.wm0 = wm0; d.wc0 = wc0; d.wi = wi; d.wi_sr = wi_sr;
+  d.Wsum = wm0 + 2.0 * Na * wi;
+  d.cpair = std::sqrt(2.0) * wi_sr * gamma;
+}
+
+int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** out) {
+  if (!out || B <= 0 || L <= 0) return fail(SRUKF_EINVAL, "srukf_create: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SRUKF_ENODEV, "srukf_create: no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(SRUKF_EINVAL, "srukf_create: bad device index");
+  SrukfParams prm;
+  if (params) prm = *params; else srukf_default_params(&prm);
+  if (prm.weight_type < 0 || prm.weight_type > 2) return fail(SRUKF_EINVAL, "srukf_create: weight_type must be 0..2");
+  srukf_handle* h = new (std::nothrow) srukf_handle();
+  if (!h) return fail(SRUKF_ENOMEM, "srukf_create: host allocation failed");
+  h->device = device; h->prm = prm;
+  fill_dev_params(h->p, prm, B, L);
+  const DevParams& p = h->p;
+  if (std::fabs(p.cpair - 1.0) > 1e-12) { delete h; return fail(SRUKF_EINVAL, "srukf_create: sqrt(2)*wi_sr*gamma != 1"); }
+  if (predict_smem_bytes(p) > 227 * 1024) { delete h; return fail(SRUKF_EINVAL, "srukf_create: L too large for one CTA"); }
+  cudaError_t e;
+#define CUH(x) do { e = (x); if (e != cudaSuccess) { int c_ = fail(e == cudaErrorMemoryAllocation ? SRUKF_ENOMEM : SRUKF_ECUDA, #x, e); srukf_destroy(h); return c_; } } while (0)
+  CUH(cudaSetDevice(device));
+  CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUH(configure_kernels(p));
+  const size_t n = p.n, L2 = 2 * (size_t)L;
+  CUH(cudaMalloc(&h->x, sizeof(double) * B * n));
+  CUH(cudaMalloc(&h->S, sizeof(double) * (size_t)B * p.ntri));
+  CUH(cudaMalloc(&h->u, sizeof(double) * B * 3));
+  CUH(cudaMalloc(&h->z, sizeof(double) * B * L2));
+  CUH(cudaMalloc(&h->matched, (size_t)B * L));
+  CUH(cudaMalloc(&h->hbar, sizeof(double) * B * L2));
+  CUH(cudaMalloc(&h->si, sizeof(double) * B * 4 * L));
+  CUH(cudaMalloc(&h->cshift, sizeof(double) * B * L2));
+  CUH(cudaMalloc(&h->pxyr, sizeof(double) * B * 4 * L2));
+  CUH(cudaMalloc(&h->visible, (size_t)B * L));
+  CUH(cudaMalloc(&h->flags, sizeof(uint32_t) * B));
+  CUH(cudaMalloc(&h->perf, sizeof(double) * B * 4));
+  CUH(cudaMalloc(&h->stats_out, sizeof(double) * 8));
+  CUH(cudaMalloc(&h->truth, sizeof(double) * B * 3));
+  CUH(cudaMemsetAsync(h->flags, 0, sizeof(uint32_t) * B, h->stream));
+  CUH(cudaMemsetAsync(h->x, 0, sizeof(double) * B * n, h->stream));
+  CUH(cudaMemsetAsync(h->S, 0, sizeof(double) * (size_t)B * p.ntri, h->stream));
+  CUH(cudaMemsetAsync(h->visible, 0, (size_t)B * L, h->stream));
+  // scratch: chunk sized so the pipeline scratch stays <= 2 GiB
+  size_t per = sizeof(double) * ((size_t)p.nf * L2 + n * L2 + (size_t)p.ntri);
+  size_t budget = (size_t)2 << 30;
+  long chunk = (long)(budget / per);
+  if (chunk < 1) chunk = 1;
+  if (chunk > B) chunk = B;
+  if (chunk >= 296) chunk -= chunk % 148;  // whole waves of one CTA per SM
+  h->chunk = (int)chunk;
+  CUH(cudaMalloc(&h->dZ, sizeof(double) * (size_t)chunk * p.nf * L2));
+  CUH(cudaMalloc(&h->U, sizeof(double) * (size_t)chunk * n * L2));
+  CUH(cudaMalloc(&h->G, sizeof(double) * (size_t)chunk * p.ntri));
+  CUH(cudaStreamSynchronize(h->stream));
+#undef CUH
+  *out = h;
+  return SRUKF_OK;
+}
+
+int srukf_destroy(srukf_t* h) {
+  if (!h) return SRUKF_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  void* ptrs[] = {h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+                  h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return SRUKF_OK;
+}
+
+static StepPtrs base_ptrs(srukf_t* h) {
+  StepPtrs q{};
+  q.x = h->x; q.S = h->S; q.u = h->u; q.z = h->z; q.matched = h->matched;
+  q.hbar = h->hbar; q.si = h->si; q.visible = h->visible; q.cshift = h->cshift; q.pxyr = h->pxyr;
+  q.rsig = h->rsig; q.dZ = h->dZ; q.U = h->U; q.G = h->G; q.flags = h->flags; q.chunk0 = 0;
+  return q;
+}
+
+int srukf_set_state(srukf_t* h, const double* x, const double* S_packed) {
+  if (!h || !x || !S_packed) return fail(SRUKF_EINVAL, "srukf_set_state: null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->x, x, sizeof(double) * (size_t)h->p.B * h->p.n, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->S, S_packed, sizeof(double) * (size_t)h->p.B * h->p.ntri, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->phase = 0;
+  return SRUKF_OK;
+}
+
+int srukf_get_state(srukf_t* h, double* x, double* S_packed) {
+  if (!h) return fail(SRUKF_EINVAL, "srukf_get_state: null handle");
+  CU(cudaSetDevice(h->device));
+  if (x) CU(cudaMemcpyAsync(x, h->x, sizeof(double) * (size_t)h->p.B * h->p.n, cudaMemcpyDeviceToHost, h->stream));
+  if (S_packed)
+    CU(cudaMemcpyAsync(S_packed, h->S, sizeof(double) * (size_t)h->p.B * h->p.ntri, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return SRUKF_OK;
+}
+
+int srukf_set_state_dense(srukf_t* h, const double* x, const double* S_dense) {
+  if (!h || !x || !S_dense) return fail(SRUKF_EINVAL, "srukf_set_state_dense: null argument");
+  CU(cudaSetDevice(h->device));
+  const size_t n = h->p.n;
+  // stage through a temporary in slices of <= 256 MiB
+  size_t per = sizeof(double) * n * n;
+  int slice = (int)(((size_t)256 << 20) / per);
+  if (slice < 1) slice = 1;
+  if (slice > h->p.B) slice = h->p.B;
+  double* tmp = nullptr;
+  CU(cudaMalloc(&tmp, per * slice));
+  for (int b0 = 0; b0 < h->p.B; b0 += slice) {
+    int nb = h->p.B - b0 < slice ? h->p.B - b0 : slice;
+    cudaError_t e = cudaMemcpyAsync(tmp, S_dense + (size_t)b0 * n * n, per * nb, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+      launch_pack(nb, (int)n, h->p.ntri, tmp, h->S + (size_t)b0 * h->p.ntri, h->stream);
+      h->launches++;
+      e = cudaStreamSynchronize(h->stream);
+    }
+    if (e != cudaSuccess) { cudaFree(tmp); return fail(SRUKF_ECUDA, "srukf_set_state_dense", e); }
+  }
+  cudaFree(tmp);
+  CU(cudaMemcpyAsync(h->x, x, sizeof(double) * (size_t)h->p.B * n, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->phase = 0;
+  return SRUKF_OK;
+}
+
+int srukf_get_state_dense(srukf_t* h, double* x, double* S_dense) {
+  if (!h) return fail(SRUKF_EINVAL, "srukf_get_state_dense: null handle");
+  CU(cudaSetDevice(h->device));
+  const size_t n = h->p.n;
+  if (S_dense) {
+    size_t per = sizeof(double) * n * n;
+    int slice = (int)(((size_t)256 << 20) / per);
+    if (slice < 1) slice = 1;
+    if (slice > h->p.B) slice = h->p.B;
+    double* tmp = nullptr;
+    CU(cudaMalloc(&tmp, per * slice));
+    for (int b0 = 0; b0 < h->p.B; b0 += slice) {
+      int nb = h->p.B - b0 < slice ? h->p.B - b0 : slice;
+      launch_unpack(nb, (int)n, h->p.ntri, h->S + (size_t)b0 * h->p.ntri, tmp, h->stream);
+      h->launches++;
+      cudaError_t e = cudaMemcpyAsync(S_dense + (size_t)b0 * n * n, tmp, per * nb, cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { cudaFree(tmp); return fail(SRUKF_ECUDA, "srukf_get_state_dense", e); }
+    }
+    cudaFree(tmp);
+  }
+  if (x) CU(cudaMemcpyAsync(x, h->x, sizeof(double) * (size_t)h->p.B * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return SRUKF_OK;
+}
+
+static int ensure_split_buffers(srukf_t* h) {
+  const DevParams& p = h->p;
+  const size_t L2 = 2 * (size_t)p.L;
+  if (!h->rsig) CU(cudaMalloc(&h->rsig, sizeof(double) * (size_t)p.B * p.P * 4));
+  if (h->chunk >= p.B) return SRUKF_OK;  // the step scratch already covers the whole batch
+  if (!h->dZ_all) CU(cudaMalloc(&h->dZ_all, sizeof(double) * (size_t)p.B * p.nf * L2));
+  return SRUKF_OK;
+}
+
+int srukf_predict_motion(srukf_t* h, const double* u) {
+  if (!h || !u) return fail(SRUKF_EINVAL, "srukf_predict_motion: null argument");
+  CU(cudaSetDevice(h->device));
+  int rc = ensure_split_buffers(h);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->u, u, sizeof(double) * (size_t)h->p.B * 3, cudaMemcpyHostToDevice, h->stream));
+  StepPtrs q = base_ptrs(h);
+  launch_predict(h->p, q, h->p.B, true, false, true, h->stream);
+  h->launches++;
+  CU(cudaGetLastError());
+  h->phase = 1;
+  return SRUKF_OK;
+}
+
+int srukf_predict_measurement(srukf_t* h) {
+  if (!h) return fail(SRUKF_EINVAL, "srukf_predict_measurement: null handle");
+  if (h->phase != 1) return fail(SRUKF_ESTATE, "srukf_predict_measurement: call srukf_predict_motion first");
+  CU(cudaSetDevice(h->device));
+  StepPtrs q = base_ptrs(h);
+  if (h->dZ_all) q.dZ = h->dZ_all;
+  launch_predict(h->p, q, h->p.B, false, true, false, h->stream);
+  h->launches++;
+  CU(cudaGetLastError());
+  h->phase = 2;
+  return SRUKF_OK;
+}
+
+int srukf_get_prediction(srukf_t* h, double* hbar, double* si, uint8_t* visible) {
+  if (!h) return fail(SRUKF_EINVAL, "srukf_get_prediction: null handle");
+  if (h->phase < 2) return fail(SRUKF_ESTATE, "srukf_get_prediction: no prediction available");
+  CU(cudaSetDevice(h->device));
+  const size_t B = h->p.B, L = h->p.L;
+  if (hbar) CU(cudaMemcpyAsync(hbar, h->hbar, sizeof(double) * B * 2 * L, cudaMemcpyDeviceToHost, h->stream));
+  if (si) CU(cudaMemcpyAsync(si, h->si, sizeof(double) * B * 4 * L, cudaMemcpyDeviceToHost, h->stream));
+  if (visible) CU(cudaMemcpyAsync(visible, h->visible, B * L, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return SRUKF_OK;
+}
+
+// gain + downdate over [b0, b0+nb) with scratch indexed from 0
+static void run_update(srukf_t* h, StepPtrs q, int b0, int nb) {
+  q.chunk0 = b0;
+  launch_gain(h->p, q, nb, h->stream);
+  launch_downdate(h->p, q, nb, h->prm.downdate_mode, h->stream);
+  h->launches += 2;
+}
+
+int srukf_kalman_update(srukf_t* h, const double* z, const uint8_t* matched) {
+  if (!h || !z || !matched) return fail(SRUKF_EINVAL, "srukf_kalman_update: null argument");
+  if (h->phase != 2) return fail(SRUKF_ESTATE, "srukf_kalman_update: call srukf_predict_measurement first");
+  CU(cudaSetDevice(h->device));
+  const DevParams& p = h->p;
+  CU(cudaMemcpyAsync(h->z, z, sizeof(double) * (size_t)p.B * 2 * p.L, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->matched, matched, (size_t)p.B * p.L, cudaMemcpyHostToDevice, h->stream));
+  StepPtrs q = base_ptrs(h);
+  const size_t L2 = 2 * (size_t)p.L;
+  for (int b0 = 0; b0 < p.B; b0 += h->chunk) {
+    int nb = p.B - b0 < h->chunk ? p.B - b0 : h->chunk;
+    StepPtrs qq = q;
+    if (h->dZ_all) qq.dZ = h->dZ_all + (size_t)b0 * p.nf * L2;
+    run_update(h, qq, b0, nb);
+  }
+  CU(cudaGetLastError());
+  h->phase = 0;
+  return SRUKF_OK;
+}
+
+int srukf_step_dev(srukf_t* h, const double* d_u, const double* d_z, const uint8_t* d_matched) {
+  if (!h || !d_u || !d_z || !d_matched) return fail(SRUKF_EINVAL, "srukf_step_dev: null argument");
+  CU(cudaSetDevice(h->device));
+  const DevParams& p = h->p;
+  StepPtrs q = base_ptrs(h);
+  q.u = d_u; q.z = d_z; q.matched = d_matched;
+  for (int b0 = 0; b0 < p.B; b0 += h->chunk) {
+    int nb = p.B - b0 < h->chunk ? p.B - b0 : h->chunk;
+    q.chunk0 = b0;
+    launch_predict(p, q, nb, true, true, false, h->stream);
+    h->launches++;
+    run_update(h, q, b0, nb);
+  }
+  CU(cudaGetLastError());
+  h->phase = 0;
+  return SRUKF_OK;
+}
+
+int srukf_step(srukf_t* h, const double* u, const double* z, const uint8_t* matched) {
+  if (!h || !u || !z || !matched) return fail(SRUKF_EINVAL, "srukf_step: null argument");
+  CU(cudaSetDevice(h->device));
+  const DevParams& p = h->p;
+  CU(cudaMemcpyAsync(h->u, u, sizeof(double) * (size_t)p.B * 3, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->z, z, sizeof(double) * (size_t)p.B * 2 * p.L, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->matched, matched, (size_t)p.B * p.L, cudaMemcpyHostToDevice, h->stream));
+  return srukf_step_dev(h, h->u, h->z, h->matched);
+}
+
+int srukf_state_dev(srukf_t* h, double** d_x, double** d_S_packed) {
+  if (!h) return fail(SRUKF_EINVAL, "srukf_state_dev: null handle");
+  if (d_x) *d_x = h->x;
+  if (d_S_packed) *d_S_packed = h->S;
+  return SRUKF_OK;
+}
+
+int srukf_get_cov_block(srukf_t* h, int r0, int nr, double* out) {
+  if (!h || !out || r0 < 0 || nr <= 0 || r0 + nr > h->p.n) return fail(SRUKF_EINVAL, "srukf_get_cov_block: bad arguments");
+  CU(cudaSetDevice(h->device));
+  double* tmp = nullptr;
+  size_t bytes = sizeof(double) * (size_t)h->p.B * nr * nr;
+  CU(cudaMalloc(&tmp, bytes));
+  launch_cov_block(h->p.B, h->p.n, h->p.ntri, h->S, r0, nr, tmp, h->stream);
+  h->launches++;
+  cudaError_t e = cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(SRUKF_ECUDA, "srukf_get_cov_block", e);
+  return SRUKF_OK;
+}
+
+int srukf_get_flags(srukf_t* h, uint32_t* flags) {
+  if (!h || !flags) return fail(SRUKF_EINVAL, "srukf_get_flags: null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(flags, h->flags, sizeof(uint32_t) * h->p.B, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return SRUKF_OK;
+}
+
+int srukf_clear_flags(srukf_t* h) {
+  if (!h) return fail(SRUKF_EINVAL, "srukf_clear_flags: null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemsetAsync(h->flags, 0, sizeof(uint32_t) * h->p.B, h->stream));
+  return SRUKF_OK;
+}
+
+int srukf_stats(srukf_t* h, const double* truth, double* out8) {
+  if (!h || !truth || !out8) return fail(SRUKF_EINVAL, "srukf_stats: null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->truth, truth, sizeof(double) * (size_t)h->p.B * 3, cudaMemcpyHostToDevice, h->stream));
+  launch_stats(h->p.B, h->p.n, h->p.ntri, h->x, h->S, h->truth, h->perf, h->flags, h->stats_out, h->stream);
+  h->launches += 2;
+  CU(cudaMemcpyAsync(out8, h->stats_out, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return SRUKF_OK;
+}
+
+int srukf_sync(srukf_t* h) {
+  if (!h) return fail(SRUKF_EINVAL, "srukf_sync: null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return SRUKF_OK;
+}
+
+int srukf_stream(srukf_t* h, uint64_t* stream) {
+  if (!h || !stream) return fail(SRUKF_EINVAL, "srukf_stream: null argument");
+  *stream = (uint64_t)(uintptr_t)h->stream;
+  return SRUKF_OK;
+}
+
+int srukf_launch_count(srukf_t* h, uint64_t* count) {
+  if (!h || !count) return fail(SRUKF_EINVAL, "srukf_launch_count: null argument");
+  *count = h->launches;
+  return SRUKF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// srukf_device.cuh -- device-side building blocks of the batched SRUKF (sm_100a, FP64).
+//
+// Everything here follows the arithmetic of MonoSLAM/SLAM.cpp (cited per function) but never
+// materialises the reference's Na x (2Na+1) sigma matrix: sigma point i is x +- gamma * row_i of
+// blockdiag(S, Mt, Qt) (SLAM.cpp:1148-1162,1461-1463) and is generated on the fly from packed S.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/srukf.h"
+
+namespace srukf {
+
+// Per-handle constants, passed by value to every kernel.
+struct DevParams {
+  int B, L, n, nf, Na, P, ntri;
+  // camera (SLAM.cpp:329-337)
+  double cam_dx, cam_dy, cam_cx, cam_cy, cam_k1, cam_k2, f1, f2;
+  double img_w, img_h;
+  // noise (SLAM.cpp:195-198, 238)
+  double a1, a2, a3, a4, sigma_measure;
+  // sample parameters for Na (SLAM.cpp:1050-1103)
+  double gamma, wm0, wc0, wi, wi_sr;
+  double Wsum;   // wm0 + 2 Na wi  (== 1 analytically)
+  double cpair;  // sqrt(2) * wi_sr * gamma (== 1 analytically for all three weight types)
+  double epsilon;
+  int newton_iters;
+};
+
+// packed upper-triangular row-major: row i holds columns i..n-1
+__host__ __device__ __forceinline__ int tri_off(int i, int n) { return i * n - (i * (i - 1)) / 2; }
+
+__device__ __forceinline__ double S_at(const double* __restrict__ S, int n, int i, int c) {
+  return (c >= i) ? S[tri_off(i, n) + (c - i)] : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// distortOnePointRW, SLAM.cpp:3177-3213.  The Newton loop (fixed 100 iterations in the reference)
+// exits once the step no longer changes rd; the fixed point is the same to < 1 ulp.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void distort_point(const DevParams& p, double ux, double uy, double& ox, double& oy,
+                                              uint32_t& flags) {
+  const double k1 = p.cam_k1, k2 = p.cam_k2;
+  double xu = (ux - p.cam_cx) * p.cam_dx;
+  double yu = (uy - p.cam_cy) * p.cam_dy;
+  double ru = sqrt(xu * xu + yu * yu);
+  double ru2 = ru * ru;
+  double rd = ru / (1 + k1 * ru2 + k2 * (ru2 * ru2));
+  for (int it = 0; it < p.newton_iters; ++it) {
+    double rd2 = rd * rd;
+    double f = rd + k1 * (rd2 * rd) + k2 * (rd2 * rd2 * rd) - ru;
+    double ff = 1.0 + 3.0 * k1 * rd2 + 5.0 * k2 * (rd2 * rd2);
+    double nrd = rd - f / ff;
+    bool done = (nrd == rd);
+    rd = nrd;
+    if (done) break;
+  }
+  double rd2 = rd * rd;
+  double d = 1 + k1 * rd2 + k2 * (rd2 * rd2);
+  if (d == 0) d = p.epsilon;
+  double xd = xu / d;
+  double yd = yu / d;
+  ox = p.cam_cx + xd / p.cam_dx;
+  oy = p.cam_cy + yd / p.cam_dy;
+  bool vis = (ox >= 0) && (ox <= p.img_w) && (oy >= 0) && (oy <= p.img_h);
+  if (!vis) {
+    ox = 0;
+    oy = 0;
+    flags |= SRUKF_FLAG_OUT_OF_VIEW;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One sigma-point projection of one feature:
+//   coordinatesState2World :3250-3276, World2Camera :3289-3292 with Rcw = Rwc.inv() (:1642-1643,
+//   OpenCV closed-form 3x3 inverse = adj/det), Camera2Image :3324-3347 (x/y swap kept), distortion.
+// (cth, sth) = cos/sin of the robot heading of this sigma point; (e0, e1) its pixel-noise components.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void project_feature(const DevParams& p, double xi, double yi, double zi, double theta,
+                                                double phi, double rho, double rx, double ry, double rz, double cth,
+                                                double sth, double e0, double e1, double& ox, double& oy,
+                                                uint32_t& flags) {
+  double sphi, cphi, sthe, cthe;
+  sincos(phi, &sphi, &cphi);
+  sincos(theta, &sthe, &cthe);
+  double ir = 1 / rho;
+  double hx = xi + ir * cphi * sthe - rx;
+  double hy = yi - ir * sphi - ry;
+  double hz = zi + ir * cphi * cthe - rz;
+  double det = cth * cth + sth * sth;
+  double dinv = 1.0 / det;
+  double rxx = (cth * dinv) * hx + (sth * dinv) * hy;
+  double ryy = (-sth * dinv) * hx + (cth * dinv) * hy;
+  double rzz = (det * dinv) * hz;
+  double ux, uy;
+  if (rzz == 0) {
+    ux = 0;
+    uy = 0;
+  } else {
+    uy = p.cam_cx + p.f1 * rxx / rzz + e0;
+    ux = p.cam_cy + p.f2 * ryy / rzz + e1;
+    if (ux < 10 || ux > p.img_w - 10 || uy < 10 || uy > p.img_h - 10) {
+      ux = 0;
+      uy = 0;
+      flags |= SRUKF_FLAG_OUT_OF_VIEW;
+    }
+  }
+  distort_point(p, ux, uy, ox, oy, flags);
+}
+
+// deterministic block reductions (fixed tree order => run-to-run and 1-vs-N-GPU bit identical)
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  int tid = threadIdx.x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (tid < 32) {
+    r = (tid < NT / 32) ? red[tid] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    if (tid == 0) red[32] = r;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+template <int NT>
+__device__ __forceinline__ double block_max(double v, double* red) {
+  int tid = threadIdx.x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  if (tid < 32) {
+    double r = (tid < NT / 32) ? red[tid] : -1.0e300;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_down_sync(0xffffffffu, r, o));
+    if (tid == 0) red[32] = r;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+}  // namespace srukf

@@ -1,0 +1,656 @@
+// srukf_kernels.cu -- batched SRUKF predict/update kernels (sm_100a, FP64), one CTA per filter.
+//
+// Pipeline per filter-step (reference: MonoSLAM/SLAM.cpp, cited per kernel):
+//   k_predict  : sigma points from packed S (never materialised), odometry motion model, robot mean,
+//                structured square-root update of S (only the 4 robot columns change), ceiling-camera
+//                projections of every sigma point, predicted pixels, per-feature 2x2 factors, robot-row
+//                cross covariances, and dZ = z(+) - z(-) per sigma pair.
+//   k_gain     : U0 = S_ff^T (wi*gamma*dZ*si^-1), robot rows, sequential-in-feature state update.
+//   k_downdate : G = S^T S - U U^T and the Gill-Murray-Wright modified Cholesky -> S.
+#include "srukf_device.cuh"
+
+namespace srukf {
+
+constexpr int NT = 256;  // threads per CTA for all kernels in this file
+
+struct StepPtrs {
+  double* x;              // [B][n]
+  double* S;              // [B][ntri]
+  const double* u;        // [B][3]
+  const double* z;        // [B][L][2]
+  const uint8_t* matched; // [B][L]
+  double* hbar;           // [B][2L]
+  double* si;             // [B][L][4]
+  uint8_t* visible;       // [B][L]
+  double* cshift;         // [B][2L]   sum_i w_i (z_i - hbar) (zero analytically when wc0 == wm0)
+  double* pxyr;           // [B][4][2L] robot rows of Pxy
+  double* rsig;           // [B][P][4] propagated robot pose per sigma point (split API only)
+  double* dZ;             // [chunk][nf][2L]   z(+) - z(-), later V
+  double* U;              // [chunk][n][2L]
+  double* G;              // [chunk][ntri]
+  uint32_t* flags;        // [B]
+  int chunk0;             // first filter of this chunk (scratch arrays are chunk-relative)
+};
+
+// -------------------------------------------------------------------------------------------------
+// Householder QR (GSL convention: beta = -sign(alpha) * norm, SLAM.cpp:2339) of the rows x 4 matrix
+// T (row-major, shared memory) by the whole CTA.  R (4x4 upper) is left in T[0..3][*].
+// -------------------------------------------------------------------------------------------------
+__device__ void householder4(double* T, int rows, double* red) {
+  const int tid = threadIdx.x;
+  for (int c = 0; c < 4; ++c) {
+    double ss = 0.0;
+    for (int r = c + 1 + tid; r < rows; r += NT) ss += T[r * 4 + c] * T[r * 4 + c];
+    ss = block_sum<NT>(ss, red);
+    double xnorm = sqrt(ss);
+    if (xnorm == 0.0) continue;  // tau = 0 (gsl_linalg_householder_transform)
+    double alpha = T[c * 4 + c];
+    double beta = -(alpha >= 0.0 ? 1.0 : -1.0) * hypot(alpha, xnorm);
+    double tau = (beta - alpha) / beta;
+    double sc = 1.0 / (alpha - beta);
+    __syncthreads();
+    for (int r = c + 1 + tid; r < rows; r += NT) T[r * 4 + c] *= sc;
+    __syncthreads();
+    for (int j = c + 1; j < 4; ++j) {
+      double w = 0.0;
+      for (int r = c + 1 + tid; r < rows; r += NT) w += T[r * 4 + j] * T[r * 4 + c];
+      w = block_sum<NT>(w, red) + T[c * 4 + j];
+      __syncthreads();
+      if (tid == 0) T[c * 4 + j] -= tau * w;
+      for (int r = c + 1 + tid; r < rows; r += NT) T[r * 4 + j] -= tau * T[r * 4 + c] * w;
+      __syncthreads();
+    }
+    if (tid == 0) T[c * 4 + c] = beta;
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_predict
+//   MOTION: predictMotion, motion part (SLAM.cpp:1430-1465): generateSigmaPoints :1148-1162,
+//           passSigmaThroughMotionFunction :1476-1532, QrAndCholeskyForMotion :1539-1556.
+//           The QR matrix rows are wi_sr*(sigma_i - sigma_0).  Pairs (+-) are combined by the
+//           orthogonal map (a+ - a-)/sqrt2, (a+ + a-)/sqrt2, which leaves A^T A unchanged: the first
+//           family is [S_ff | E] (S_ff untouched, already triangular), the second is zero in every
+//           feature column.  R = [[S_ff, E_f], [0, R_rr]] with R_rr from a (n+10) x 4 Householder QR.
+//   MEAS  : predictMeasurement (SLAM.cpp:1604-1608): passSigmaThroughMesaurementFunction :1615-1682,
+//           QrAndCholeskyForMeasurement :1700-1748 / calculateOneFeatureCovariance :1759-1775, and the
+//           robot rows of calculateOneFeatureCrossCovariance :2020-2038.
+// -------------------------------------------------------------------------------------------------
+template <bool MOTION, bool MEAS>
+__global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int save_rsig) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  const int b = q.chunk0 + blockIdx.x;
+  const int n = p.n, nf = p.nf, Na = p.Na, P = p.P, L = p.L;
+  double* xs = sm;                 // n
+  double* rs = xs + n;             // P x 6 : rx ry rz rtheta cos sin
+  double* z0 = rs + (size_t)P * 6; // 2L
+  double* red = z0 + 2 * L;        // 40
+  double* work = red + 40;         // max((n+10)*4, slots*13)
+  double* xg = q.x + (size_t)b * n;
+  double* Sg = q.S + (size_t)b * p.ntri;
+  uint32_t flags = 0;
+
+  for (int i = tid; i < n; i += NT) xs[i] = xg[i];
+  __syncthreads();
+
+  if (MOTION) {
+    const double* ug = q.u + (size_t)b * 3;
+    const double u0 = ug[0], u1 = ug[1], u2 = ug[2];
+    // Mt, SLAM.cpp:1456-1458 (inserted as a square-root block, :1461)
+    const double Mt0 = p.a1 * u0 * u0 + p.a2 * u1 * u1;
+    const double Mt1 = p.a3 * u1 * u1 + p.a4 * u0 * u0 + p.a4 * u2 * u2;
+    const double Mt2 = p.a1 * u2 * u2 + p.a2 * u1 * u1;
+    for (int i = tid; i < P; i += NT) {
+      int k = -1;
+      double sg = 0.0;
+      if (i >= 1 && i <= Na) { k = i - 1; sg = p.gamma; }
+      else if (i > Na) { k = i - 1 - Na; sg = -p.gamma; }
+      double bx = xs[n - 4], by = xs[n - 3], bz = xs[n - 2], bt = xs[n - 1];
+      double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+      if (k >= 0) {
+        if (k < n) {  // addWeighted(mu, 1, row, +-gamma, 0), :1159-1160
+          bx = bx * 1 + S_at(Sg, n, k, n - 4) * sg;
+          by = by * 1 + S_at(Sg, n, k, n - 3) * sg;
+          bz = bz * 1 + S_at(Sg, n, k, n - 2) * sg;
+          bt = bt * 1 + S_at(Sg, n, k, n - 1) * sg;
+        } else if (k == n) n0 = Mt0 * sg;
+        else if (k == n + 1) n1 = Mt1 * sg;
+        else if (k == n + 2) n2 = Mt2 * sg;
+      }
+      // :1492-1494, :1518-1523
+      double rot1 = u0 - n0, trans = u1 - n1, rot2 = u2 - n2;
+      double sn, cs;
+      sincos(bt + rot1, &sn, &cs);
+      double rx = bx + trans * cs;
+      double ry = by + trans * sn;
+      double rz = bz + 0;
+      double rt = bt + (rot1 + rot2);
+      double* r = rs + (size_t)i * 6;
+      r[0] = rx; r[1] = ry; r[2] = rz; r[3] = rt;
+      sincos(rt, &sn, &cs);
+      r[4] = cs; r[5] = sn;
+    }
+    __syncthreads();
+    // robot mean, :1526-1531: wm0*r0 + wi*sum r_i == Wsum*r0 + wi*sum (r_i - r0)
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int i = 1 + tid; i < P; i += NT) {
+      const double* r = rs + (size_t)i * 6;
+      a0 += r[0] - rs[0]; a1 += r[1] - rs[1]; a2 += r[2] - rs[2]; a3 += r[3] - rs[3];
+    }
+    a0 = block_sum<NT>(a0, red); a1 = block_sum<NT>(a1, red);
+    a2 = block_sum<NT>(a2, red); a3 = block_sum<NT>(a3, red);
+    __syncthreads();
+    if (tid == 0) {
+      xs[n - 4] = p.Wsum * rs[0] + p.wi * a0;
+      xs[n - 3] = p.Wsum * rs[1] + p.wi * a1;
+      xs[n - 2] = p.Wsum * rs[2] + p.wi * a2;
+      xs[n - 1] = p.Wsum * rs[3] + p.wi * a3;
+      xg[n - 4] = xs[n - 4]; xg[n - 3] = xs[n - 3]; xg[n - 2] = xs[n - 2]; xg[n - 1] = xs[n - 1];
+    }
+    // square-root factor: E rows and the stacked robot-only rows
+    double* T = work;  // (n + 10) x 4
+    const double hs = p.wi_sr * 0.70710678118654752440;  // wi_sr / sqrt(2)
+    for (int k = tid; k < n; k += NT) {
+      const double* rp = rs + (size_t)(k + 1) * 6;
+      const double* rm = rs + (size_t)(Na + k + 1) * 6;
+      double e[4], s[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double ap = rp[c] - rs[c], am = rm[c] - rs[c];
+        e[c] = hs * (ap - am);
+        s[c] = hs * (ap + am);
+      }
+      if (k < nf) {
+        double* row = Sg + tri_off(k, n) + (nf - k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) row[c] = e[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) T[(k - nf) * 4 + c] = e[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) T[(4 + k) * 4 + c] = s[c];
+    }
+    if (tid < 6) {  // control-noise pairs n..n+2 (pixel-noise pairs have zero robot deviation)
+      int k = n + tid / 2;
+      const double* r = rs + (size_t)((tid & 1) ? (Na + k + 1) : (k + 1)) * 6;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) T[(4 + n + tid) * 4 + c] = p.wi_sr * (r[c] - rs[c]);
+    }
+    __syncthreads();
+    householder4(T, n + 10, red);
+    if (tid < 4) {
+      double* row = Sg + tri_off(nf + tid, n);
+      for (int c = tid; c < 4; ++c) row[c - tid] = T[tid * 4 + c];
+    }
+    if (save_rsig) {
+      double* rg = q.rsig + (size_t)b * P * 4;
+      for (int i = tid; i < P * 4; i += NT) rg[i] = rs[(size_t)(i >> 2) * 6 + (i & 3)];
+    }
+    __syncthreads();
+  } else {
+    const double* rg = q.rsig + (size_t)b * P * 4;
+    for (int i = tid; i < P; i += NT) {
+      double* r = rs + (size_t)i * 6;
+      r[0] = rg[i * 4 + 0]; r[1] = rg[i * 4 + 1]; r[2] = rg[i * 4 + 2]; r[3] = rg[i * 4 + 3];
+      double sn, cs;
+      sincos(r[3], &sn, &cs);
+      r[4] = cs; r[5] = sn;
+    }
+    __syncthreads();
+  }
+
+  if (MEAS) {
+    const double gsm = p.gamma * p.sigma_measure;  // Qt = I2*sigma_measure enters as a sqrt block (:1462)
+    // sigma point 0
+    for (int j = tid; j < L; j += NT) {
+      const double* f = xs + 6 * j;
+      double ox, oy;
+      project_feature(p, f[0], f[1], f[2], f[3], f[4], f[5], rs[0], rs[1], rs[2], rs[4], rs[5], 0.0, 0.0, ox, oy,
+                      flags);
+      z0[2 * j] = ox;
+      z0[2 * j + 1] = oy;
+    }
+    __syncthreads();
+    const int G = (L <= NT) ? NT / L : 1;
+    double* acc = work;  // [G*L][13]
+    double* dZ = q.dZ + (size_t)blockIdx.x * nf * 2 * L;
+    for (int slot = tid; slot < G * L; slot += NT) {
+      const int g = slot / L, j = slot - g * L;
+      const double* f = xs + 6 * j;
+      const double zx0 = z0[2 * j], zy0 = z0[2 * j + 1];
+      double sb0 = 0, sb1 = 0, s00 = 0, s01 = 0, s11 = 0;
+      double sa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int k = g; k < Na; k += G) {
+        double s[6] = {0, 0, 0, 0, 0, 0};
+        if (k < nf && k <= 6 * j + 5) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) s[c] = S_at(Sg, n, k, 6 * j + c);
+        }
+        double e0 = (k == n + 3) ? gsm : 0.0, e1 = (k == n + 4) ? gsm : 0.0;
+        const double* rp = rs + (size_t)(k + 1) * 6;
+        const double* rm = rs + (size_t)(Na + k + 1) * 6;
+        double px, py, mx, my;
+        project_feature(p, f[0] * 1 + s[0] * p.gamma, f[1] * 1 + s[1] * p.gamma, f[2] * 1 + s[2] * p.gamma,
+                        f[3] * 1 + s[3] * p.gamma, f[4] * 1 + s[4] * p.gamma, f[5] * 1 + s[5] * p.gamma, rp[0], rp[1],
+                        rp[2], rp[4], rp[5], e0, e1, px, py, flags);
+        project_feature(p, f[0] * 1 - s[0] * p.gamma, f[1] * 1 - s[1] * p.gamma, f[2] * 1 - s[2] * p.gamma,
+                        f[3] * 1 - s[3] * p.gamma, f[4] * 1 - s[4] * p.gamma, f[5] * 1 - s[5] * p.gamma, rm[0], rm[1],
+                        rm[2], rm[4], rm[5], -e0, -e1, mx, my, flags);
+        if (k < nf) {
+          dZ[(size_t)k * 2 * L + 2 * j] = px - mx;
+          dZ[(size_t)k * 2 * L + 2 * j + 1] = py - my;
+        }
+        double bpx = px - zx0, bpy = py - zy0, bmx = mx - zx0, bmy = my - zy0;
+        sb0 += bpx + bmx;
+        sb1 += bpy + bmy;
+        s00 += bpx * bpx + bmx * bmx;
+        s01 += bpx * bpy + bmx * bmy;
+        s11 += bpy * bpy + bmy * bmy;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double ap = rp[c] - rs[c], am = rm[c] - rs[c];
+          sa[2 * c] += ap * bpx + am * bmx;
+          sa[2 * c + 1] += ap * bpy + am * bmy;
+        }
+      }
+      double* a = acc + (size_t)slot * 13;
+      a[0] = sb0; a[1] = sb1; a[2] = s00; a[3] = s01; a[4] = s11;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[5 + c] = sa[c];
+    }
+    __syncthreads();
+    // reduce over g in fixed order; per-feature outputs
+    const double W1 = 2.0 * Na * p.wi;
+    const double cab = W1 + p.wc0 - 2.0;  // coefficient of abar*bbar^T (== -1 when wc0 == wm0)
+    double* hb = q.hbar + (size_t)b * 2 * L;
+    double* sig = q.si + (size_t)b * 4 * L;
+    double* csh = q.cshift + (size_t)b * 2 * L;
+    double* pr = q.pxyr + (size_t)b * 8 * L;
+    uint8_t* vis = q.visible + (size_t)b * L;
+    for (int j = tid; j < L; j += NT) {
+      double t[13];
+#pragma unroll
+      for (int c = 0; c < 13; ++c) t[c] = 0.0;
+      for (int g = 0; g < G; ++g) {
+        const double* a = acc + (size_t)(g * L + j) * 13;
+#pragma unroll
+        for (int c = 0; c < 13; ++c) t[c] += a[c];
+      }
+      const double zx0 = z0[2 * j], zy0 = z0[2 * j + 1];
+      const double bb0 = p.wi * t[0], bb1 = p.wi * t[1];
+      const double hx = p.Wsum * zx0 + bb0, hy = p.Wsum * zy0 + bb1;
+      hb[2 * j] = hx;
+      hb[2 * j + 1] = hy;
+      const bool v = (hx != 0.0) && (hy != 0.0);  // :1727
+      vis[j] = v ? 1 : 0;
+      if (!v) flags |= SRUKF_FLAG_INVISIBLE;
+      // si = R of the 2Na x 2 QR (:1771-1775) == Cholesky factor of wi * sum b b^T
+      double g00 = p.wi * t[2], g01 = p.wi * t[3], g11 = p.wi * t[4];
+      double r00 = sqrt(g00);
+      double r01 = (r00 > 0.0) ? g01 / r00 : 0.0;
+      double r11 = sqrt(fmax(g11 - r01 * r01, 0.0));
+      sig[4 * j + 0] = r00; sig[4 * j + 1] = r01; sig[4 * j + 2] = 0.0; sig[4 * j + 3] = r11;
+      // sum_i w_i (z_i - hbar): multiplies the accumulated state shift in :2030
+      csh[2 * j] = (p.wc0 - p.wm0) * (zx0 - hx) + (1.0 - p.Wsum) * hx;
+      csh[2 * j + 1] = (p.wc0 - p.wm0) * (zy0 - hy) + (1.0 - p.Wsum) * hy;
+      // robot rows of Pxy (:2028-2037) about the predicted means
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double abar = xs[n - 4 + c] - rs[c];  // = wi * sum a_i (+ (Wsum-1) r0, zero analytically)
+        pr[(size_t)c * 2 * L + 2 * j] = p.wi * t[5 + 2 * c] + cab * abar * bb0;
+        pr[(size_t)c * 2 * L + 2 * j + 1] = p.wi * t[6 + 2 * c] + cab * abar * bb1;
+      }
+    }
+  }
+  // flags
+  flags = __reduce_or_sync(0xffffffffu, flags);
+  if ((tid & 31) == 0 && flags) atomicOr(q.flags + b, flags);
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_gain -- KalmanUpdate gain part (SLAM.cpp:2066-2080) for all matched features at once.
+//   U0_f = S_ff^T V with V = wi*gamma*dZ*blockdiag(si^-1)   (calculateOneFeatureCrossCovariance :2020-2038
+//          restricted to the feature rows, where sigma_i - x = +-gamma*S[i,:]; U = Ki*si^T = Pxy*si^-1)
+//   U0_r = Pxy_r si^-1 for the 4 robot rows
+//   then feature by feature (:2079): U_j = U0_j - dx (c_j^T si_j^-1);  dx += U_j (si_j^-T (z_j - hbar_j))
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_gain(DevParams p, StepPtrs q) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  const int b = q.chunk0 + blockIdx.x;
+  const int n = p.n, nf = p.nf, L = p.L, L2 = 2 * p.L;
+  double* sii = sm;            // L x 4
+  double* gv = sii + 4 * L;    // L x 2  si^-T (z - hbar)
+  double* ct = gv + 2 * L;     // L x 2  c^T si^-1
+  int* act = (int*)(ct + 2 * L);  // L
+  int* nact = act + L;
+  const double* Sg = q.S + (size_t)b * p.ntri;
+  double* dZ = q.dZ + (size_t)blockIdx.x * nf * L2;
+  double* U = q.U + (size_t)blockIdx.x * n * L2;
+  if (tid == 0) *nact = 0;
+  __syncthreads();
+  for (int j = tid; j < L; j += NT) {
+    const double* s = q.si + ((size_t)b * L + j) * 4;
+    const bool a = q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j];
+    // si.inv(), :2077 (2x2 closed form)
+    double det = s[0] * s[3] - s[1] * s[2];
+    double i00 = 0, i01 = 0, i10 = 0, i11 = 0;
+    bool ok = a && (det != 0.0);
+    if (ok) {
+      double d = 1.0 / det;
+      i00 = s[3] * d; i01 = -s[1] * d; i10 = -s[2] * d; i11 = s[0] * d;
+    }
+    sii[4 * j] = i00; sii[4 * j + 1] = i01; sii[4 * j + 2] = i10; sii[4 * j + 3] = i11;
+    double in0 = 0, in1 = 0;
+    if (ok) {
+      in0 = q.z[((size_t)b * L + j) * 2] - q.hbar[(size_t)b * L2 + 2 * j];
+      in1 = q.z[((size_t)b * L + j) * 2 + 1] - q.hbar[(size_t)b * L2 + 2 * j + 1];
+    }
+    gv[2 * j] = i00 * in0 + i10 * in1;
+    gv[2 * j + 1] = i01 * in0 + i11 * in1;
+    double c0 = q.cshift[(size_t)b * L2 + 2 * j], c1 = q.cshift[(size_t)b * L2 + 2 * j + 1];
+    ct[2 * j] = c0 * i00 + c1 * i10;
+    ct[2 * j + 1] = c0 * i01 + c1 * i11;
+    act[j] = ok ? 1 : 0;
+    if (ok) atomicAdd(nact, 1);
+  }
+  __syncthreads();
+  if (*nact == 0) {  // KalmanUpdate returns early, :2050
+    for (int i = tid; i < n * L2; i += NT) U[i] = 0.0;
+    return;
+  }
+  // V = wi*gamma * dZ * blockdiag(sii) in place
+  const double wg = p.wi * p.gamma;
+  for (int i = tid; i < nf * L; i += NT) {
+    int k = i / L, j = i - k * L;
+    double* d = dZ + (size_t)k * L2 + 2 * j;
+    double d0 = d[0], d1 = d[1];
+    d[0] = wg * (d0 * sii[4 * j] + d1 * sii[4 * j + 2]);
+    d[1] = wg * (d0 * sii[4 * j + 1] + d1 * sii[4 * j + 3]);
+  }
+  __syncthreads();
+  // U0_f = S_ff^T V
+  for (int i = tid; i < nf * L2; i += NT) {
+    int f = i / L2, c = i - f * L2;
+    double acc = 0.0;
+    for (int k = 0; k <= f; ++k) acc += Sg[tri_off(k, n) + (f - k)] * dZ[(size_t)k * L2 + c];
+    U[(size_t)f * L2 + c] = acc;
+  }
+  // U0_r = Pxy_r sii
+  for (int i = tid; i < 4 * L; i += NT) {
+    int r = i / L, j = i - r * L;
+    const double* pr = q.pxyr + (size_t)b * 8 * L + (size_t)r * L2 + 2 * j;
+    double* u = U + (size_t)(nf + r) * L2 + 2 * j;
+    u[0] = pr[0] * sii[4 * j] + pr[1] * sii[4 * j + 2];
+    u[1] = pr[0] * sii[4 * j + 1] + pr[1] * sii[4 * j + 3];
+  }
+  __syncthreads();
+  // feature-sequential state update, one state row per thread
+  double* xg = q.x + (size_t)b * n;
+  uint32_t flags = 0;
+  for (int r = tid; r < n; r += NT) {
+    double dx = 0.0;
+    double* u = U + (size_t)r * L2;
+    for (int j = 0; j < L; ++j) {
+      if (!act[j]) { u[2 * j] = 0.0; u[2 * j + 1] = 0.0; continue; }
+      double u0 = u[2 * j] - dx * ct[2 * j];
+      double u1 = u[2 * j + 1] - dx * ct[2 * j + 1];
+      u[2 * j] = u0;
+      u[2 * j + 1] = u1;
+      dx += u0 * gv[2 * j] + u1 * gv[2 * j + 1];
+    }
+    double xn = xg[r] + dx;
+    xg[r] = xn;
+    if (!isfinite(xn)) flags |= SRUKF_FLAG_NAN;
+  }
+  flags = __reduce_or_sync(0xffffffffu, flags);
+  if ((tid & 31) == 0 && flags) atomicOr(q.flags + b, flags);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Gill-Murray-Wright modified Cholesky (SLAM.cpp:2197-2327) of the packed symmetric G (column j of the
+// lower triangle == row j of the packed upper layout), right-looking, in place; S receives sqrt(D) L^T.
+// -------------------------------------------------------------------------------------------------
+__device__ void mchol_inplace(const DevParams& p, double* G, double* S, double* wcol, double* red, uint32_t& flags) {
+  const int tid = threadIdx.x, n = p.n;
+  // :2204-2211
+  double gmax = -1.0e300, zmax = 0.0;
+  for (int j = 0; j < n; ++j) {
+    const double* col = G + tri_off(j, n);
+    if (tid == 0) gmax = fmax(gmax, col[0]);
+    for (int i = 1 + tid; i < n - j; i += NT) zmax = fmax(zmax, col[i]);
+  }
+  gmax = block_max<NT>(gmax, red);
+  zmax = block_max<NT>(zmax, red);
+  double nu = sqrt((double)n * n - 1.0);
+  if (nu < 1.0) nu = 1.0;
+  const double beta2 = fmax(fmax(gmax, zmax / nu), 1e-15);
+  for (int j = 0; j < n; ++j) {
+    double* col = G + tri_off(j, n);
+    const int len = n - j;
+    double th = 0.0;
+    for (int i = 1 + tid; i < len; i += NT) th = fmax(th, fabs(col[i]));
+    th = block_max<NT>(th, red);  // :2264-2276
+    const double cjj = col[0];
+    const double d = fmax(fmax(p.epsilon, fabs(cjj)), th * th / beta2);  // :2279-2285
+    if (d != cjj) flags |= (d > 16.0 * p.epsilon) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
+    const double sd = sqrt(d);
+    double* srow = S + tri_off(j, n);
+    for (int i = tid; i < len; i += NT) {
+      double c = col[i];
+      wcol[i] = c;
+      srow[i] = (i == 0) ? sd : sd * (c / d);  // :2232, :2321
+    }
+    __syncthreads();
+    // trailing update: C(i,k) -= (C(k,j)/d) * C(i,j), j < k <= i   (:2253, :2291-2295)
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int k = 1 + warp; k < len; k += NT / 32) {
+      double* ck = G + tri_off(j + k, n);
+      const double lk = wcol[k] / d;
+      for (int i = k + lane; i < len; i += 32) ck[i - k] -= lk * wcol[i];
+    }
+    __syncthreads();
+  }
+}
+
+// G = S^T S - sum_c U(:,c) U(:,c)^T over columns [c0, c1), packed
+__device__ void form_G(const DevParams& p, const double* __restrict__ S, const double* __restrict__ U, int c0, int c1,
+                       double* G) {
+  const int n = p.n, L2 = 2 * p.L;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < n; j += NT / 32) {
+    double* col = G + tri_off(j, n);
+    for (int i = j + lane; i < n; i += 32) {
+      double acc = 0.0;
+      for (int k = 0; k <= j; ++k) acc += S[tri_off(k, n) + (j - k)] * S[tri_off(k, n) + (i - k)];
+      double sub = 0.0;
+      for (int c = c0; c < c1; ++c) sub += U[(size_t)j * L2 + c] * U[(size_t)i * L2 + c];
+      col[i - j] = acc - sub;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_downdate -- GSLCholeskyUpdate, DOWNDATING / NEEDNOT_REORDER (SLAM.cpp:2106-2121,2139-2153).
+//   mode 0: one GMW factorisation of S^T S - U U^T (all matched features at once)
+//   mode 1: the reference's sequence: for every matched feature, for each of its 2 U columns,
+//           re-form S^T S, subtract u u^T, re-factorise.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mode) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  const int b = q.chunk0 + blockIdx.x;
+  const int n = p.n, L = p.L, L2 = 2 * p.L;
+  double* wcol = sm;       // n
+  double* red = wcol + n;  // 40
+  double* Sg = q.S + (size_t)b * p.ntri;
+  const double* U = q.U + (size_t)blockIdx.x * n * L2;
+  double* G = q.G + (size_t)blockIdx.x * p.ntri;
+  uint32_t flags = 0;
+  int nact = 0;
+  for (int j = 0; j < L; ++j) nact += (q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j]) ? 1 : 0;
+  if (nact == 0) return;  // :2050
+  if (mode == 0) {
+    form_G(p, Sg, U, 0, L2, G);
+    __syncthreads();
+    mchol_inplace(p, G, Sg, wcol, red, flags);
+  } else {
+    for (int j = 0; j < L; ++j) {
+      if (!(q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j])) continue;
+      for (int c = 0; c < 2; ++c) {
+        form_G(p, Sg, U, 2 * j + c, 2 * j + c + 1, G);
+        __syncthreads();
+        mchol_inplace(p, G, Sg, wcol, red, flags);
+        __syncthreads();
+      }
+    }
+  }
+  for (int i = tid; i < n; i += NT)
+    if (!isfinite(Sg[tri_off(i, n)])) flags |= SRUKF_FLAG_NAN;
+  flags = __reduce_or_sync(0xffffffffu, flags);
+  if ((tid & 31) == 0 && flags) atomicOr(q.flags + b, flags);
+}
+
+// -------------------------------------------------------------------------------------------------
+// auxiliary kernels
+// -------------------------------------------------------------------------------------------------
+// dense [B][n][n] <-> packed
+__global__ void k_pack(int n, int ntri, const double* __restrict__ dense, double* __restrict__ packed, int to_packed,
+                       double* dense_out) {
+  const int b = blockIdx.x;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    int i = idx / n, c = idx - i * n;
+    if (to_packed) {
+      if (c >= i) packed[(size_t)b * ntri + tri_off(i, n) + (c - i)] = dense[(size_t)b * n * n + idx];
+    } else {
+      dense_out[(size_t)b * n * n + idx] = (c >= i) ? packed[(size_t)b * ntri + tri_off(i, n) + (c - i)] : 0.0;
+    }
+  }
+}
+
+// P[r0:r0+nr, r0:r0+nr] of S^T S (m_P_k, SLAM.cpp:2404)
+__global__ void k_cov_block(int n, int ntri, const double* __restrict__ S, int r0, int nr, double* out) {
+  const int b = blockIdx.x;
+  const double* Sg = S + (size_t)b * ntri;
+  for (int idx = threadIdx.x; idx < nr * nr; idx += blockDim.x) {
+    int a = r0 + idx / nr, c = r0 + idx % nr;
+    int m = a < c ? a : c;
+    double acc = 0.0;
+    for (int k = 0; k <= m; ++k) acc += Sg[tri_off(k, n) + (a - k)] * Sg[tri_off(k, n) + (c - k)];
+    out[(size_t)b * nr * nr + idx] = acc;
+  }
+}
+
+// per-filter squared errors and NEES of (rx, ry, rtheta) -> perf[b][4]
+__global__ void __launch_bounds__(128) k_stats(int n, int ntri, const double* __restrict__ x,
+                                               const double* __restrict__ S, const double* __restrict__ truth,
+                                               double* perf) {
+  __shared__ double red[40];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* Sg = S + (size_t)b * ntri;
+  const int ia[3] = {n - 4, n - 3, n - 1};
+  double acc[6] = {0, 0, 0, 0, 0, 0};  // P00 P01 P02 P11 P12 P22
+  for (int k = tid; k < n; k += 128) {
+    double v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (ia[c] >= k) ? Sg[tri_off(k, n) + (ia[c] - k)] : 0.0;
+    acc[0] += v[0] * v[0]; acc[1] += v[0] * v[1]; acc[2] += v[0] * v[2];
+    acc[3] += v[1] * v[1]; acc[4] += v[1] * v[2]; acc[5] += v[2] * v[2];
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) acc[c] = block_sum<128>(acc[c], red);
+  if (tid == 0) {
+    double e0 = x[(size_t)b * n + n - 4] - truth[b * 3 + 0];
+    double e1 = x[(size_t)b * n + n - 3] - truth[b * 3 + 1];
+    double e2 = x[(size_t)b * n + n - 1] - truth[b * 3 + 2];
+    // solve P y = e (3x3 symmetric, cofactors)
+    double a = acc[0], bb = acc[1], c = acc[2], d = acc[3], e = acc[4], f = acc[5];
+    double det = a * (d * f - e * e) - bb * (bb * f - e * c) + c * (bb * e - d * c);
+    double y0 = ((d * f - e * e) * e0 + (c * e - bb * f) * e1 + (bb * e - c * d) * e2) / det;
+    double y1 = ((c * e - bb * f) * e0 + (a * f - c * c) * e1 + (bb * c - a * e) * e2) / det;
+    double y2 = ((bb * e - c * d) * e0 + (bb * c - a * e) * e1 + (a * d - bb * bb) * e2) / det;
+    perf[(size_t)b * 4 + 0] = e0 * e0;
+    perf[(size_t)b * 4 + 1] = e1 * e1;
+    perf[(size_t)b * 4 + 2] = e2 * e2;
+    perf[(size_t)b * 4 + 3] = e0 * y0 + e1 * y1 + e2 * y2;
+  }
+}
+
+// deterministic single-CTA reduction of perf[B][4] and the flag words -> out[8]
+__global__ void __launch_bounds__(256) k_stats_reduce(int B, const double* __restrict__ perf,
+                                                      const uint32_t* __restrict__ flags, double* out) {
+  __shared__ double red[40];
+  double s[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < B; b += 256) {
+    s[0] += perf[(size_t)b * 4 + 0]; s[1] += perf[(size_t)b * 4 + 1];
+    s[2] += perf[(size_t)b * 4 + 2]; s[3] += perf[(size_t)b * 4 + 3];
+    s[4] += 1.0;
+    s[5] += (flags[b] & SRUKF_FLAG_NAN) ? 1.0 : 0.0;
+    s[6] += (flags[b] & SRUKF_FLAG_GMW_MODIFIED) ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int c = 0; c < 7; ++c) s[c] = block_sum<256>(s[c], red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int c = 0; c < 7; ++c) out[c] = s[c];
+    out[7] = 0.0;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-side launchers (called from srukf_capi.cu)
+// -------------------------------------------------------------------------------------------------
+size_t predict_smem_bytes(const DevParams& p) {
+  size_t slots = (p.L <= NT) ? (size_t)(NT / p.L) * p.L : (size_t)p.L;
+  size_t work = slots * 13;
+  size_t t4 = (size_t)(p.n + 10) * 4;
+  if (t4 > work) work = t4;
+  return sizeof(double) * ((size_t)p.n + (size_t)p.P * 6 + 2 * (size_t)p.L + 40 + work);
+}
+size_t gain_smem_bytes(const DevParams& p) { return sizeof(double) * (8 * (size_t)p.L) + sizeof(int) * (p.L + 4); }
+size_t downdate_smem_bytes(const DevParams& p) { return sizeof(double) * ((size_t)p.n + 40); }
+
+cudaError_t configure_kernels(const DevParams& p) {
+  cudaError_t e;
+  int smem = (int)predict_smem_bytes(p);
+  if ((e = cudaFuncSetAttribute(k_predict<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+  if ((e = cudaFuncSetAttribute(k_predict<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+  if ((e = cudaFuncSetAttribute(k_predict<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+  if ((e = cudaFuncSetAttribute(k_gain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gain_smem_bytes(p)))) return e;
+  if ((e = cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)downdate_smem_bytes(p))))
+    return e;
+  return cudaSuccess;
+}
+
+void launch_predict(const DevParams& p, const StepPtrs& q, int nblocks, bool motion, bool meas, bool save_rsig,
+                    cudaStream_t st) {
+  size_t smem = predict_smem_bytes(p);
+  if (motion && meas) k_predict<true, true><<<nblocks, NT, smem, st>>>(p, q, save_rsig ? 1 : 0);
+  else if (motion) k_predict<true, false><<<nblocks, NT, smem, st>>>(p, q, 1);
+  else k_predict<false, true><<<nblocks, NT, smem, st>>>(p, q, 0);
+}
+void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
+  k_gain<<<nblocks, NT, gain_smem_bytes(p), st>>>(p, q);
+}
+void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, cudaStream_t st) {
+  k_downdate<<<nblocks, NT, downdate_smem_bytes(p), st>>>(p, q, mode);
+}
+void launch_pack(int B, int n, int ntri, const double* dense, double* packed, cudaStream_t st) {
+  k_pack<<<B, 256, 0, st>>>(n, ntri, dense, packed, 1, nullptr);
+}
+void launch_unpack(int B, int n, int ntri, const double* packed, double* dense, cudaStream_t st) {
+  k_pack<<<B, 256, 0, st>>>(n, ntri, nullptr, const_cast<double*>(packed), 0, dense);
+}
+void launch_cov_block(int B, int n, int ntri, const double* S, int r0, int nr, double* out, cudaStream_t st) {
+  k_cov_block<<<B, 128, 0, st>>>(n, ntri, S, r0, nr, out);
+}
+void launch_stats(int B, int n, int ntri, const double* x, const double* S, const double* truth, double* perf,
+                  const uint32_t* flags, double* out, cudaStream_t st) {
+  k_stats<<<B, 128, 0, st>>>(n, ntri, x, S, truth, perf);
+  k_stats_reduce<<<1, 256, 0, st>>>(B, perf, flags, out);
+}
+
+}  // namespace srukf

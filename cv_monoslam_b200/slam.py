@@ -1,0 +1,153 @@
+"""Host-side mirror of the reference's CSLAM interface for the SRUKF path, batched over B filters.
+
+Method names follow MonoSLAM/SLAM.h:359-360,372 (`predictMotion`, `predictMeasurement`,
+`KalmanUpdate`, `SLAM`); the data members the reference exchanges through (`m_X_k`, `m_S_k`,
+`m_P_k`, `Ut`, `m_allPredictSet`, map_p->Si / isVisible / matchLocation / isMatching) become
+explicit arguments and getters.  All arithmetic happens in libsrukf_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+def tri_pack(S: np.ndarray) -> np.ndarray:
+    """[B,n,n] upper-triangular -> packed row-major [B, n(n+1)/2] (layout of include/srukf.h)."""
+    n = S.shape[-1]
+    iu = np.triu_indices(n)
+    return np.ascontiguousarray(S[..., iu[0], iu[1]])
+
+
+def tri_unpack(Sp: np.ndarray, n: int) -> np.ndarray:
+    iu = np.triu_indices(n)
+    out = np.zeros(Sp.shape[:-1] + (n, n))
+    out[..., iu[0], iu[1]] = Sp
+    return out
+
+
+class CSLAMBatch:
+    """B independent CSLAM filters (SLAM.h:118) with L landmarks each on one CUDA device."""
+
+    def __init__(self, B: int, L: int, params: capi.SrukfParams | None = None, device: int = 0):
+        self._lib = capi.load_library()
+        self.B, self.L, self.n = int(B), int(L), 6 * int(L) + 4
+        self.ntri = self.n * (self.n + 1) // 2
+        self.params = params or capi.default_params()
+        h = C.c_void_p()
+        capi.check(self._lib.srukf_create(device, self.B, self.L, C.byref(self.params), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.srukf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- m_X_k / m_S_k ------------------------------------------------------------------------
+    def set_state(self, x: np.ndarray, S: np.ndarray):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(self.B, self.n)
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        if S.shape == (self.B, self.ntri):
+            capi.check(self._lib.srukf_set_state(self._h, capi.ptr(x), capi.ptr(S)))
+        else:
+            S = S.reshape(self.B, self.n, self.n)
+            capi.check(self._lib.srukf_set_state_dense(self._h, capi.ptr(x), capi.ptr(S)))
+
+    def get_state(self, dense: bool = True):
+        x = np.empty((self.B, self.n))
+        if dense:
+            S = np.empty((self.B, self.n, self.n))
+            capi.check(self._lib.srukf_get_state_dense(self._h, capi.ptr(x), capi.ptr(S)))
+        else:
+            S = np.empty((self.B, self.ntri))
+            capi.check(self._lib.srukf_get_state(self._h, capi.ptr(x), capi.ptr(S)))
+        return x, S
+
+    @property
+    def m_X_k(self) -> np.ndarray:
+        return self.get_state()[0]
+
+    @property
+    def m_S_k(self) -> np.ndarray:
+        return self.get_state()[1]
+
+    def m_P_k(self, r0: int = None, nr: int = None) -> np.ndarray:
+        """Block of m_P_k = S^T S (SLAM.cpp:2404); default: the 4x4 robot block."""
+        if r0 is None:
+            r0, nr = self.n - 4, 4
+        out = np.empty((self.B, nr, nr))
+        capi.check(self._lib.srukf_get_cov_block(self._h, r0, nr, capi.ptr(out)))
+        return out
+
+    # ---- the path -----------------------------------------------------------------------------
+    def predictMotion(self, Ut: np.ndarray):
+        Ut = np.ascontiguousarray(Ut, dtype=np.float64).reshape(self.B, 3)
+        capi.check(self._lib.srukf_predict_motion(self._h, capi.ptr(Ut)))
+
+    def predictMeasurement(self):
+        capi.check(self._lib.srukf_predict_measurement(self._h))
+
+    def prediction(self):
+        """(m_allPredictSet [B,L,2], Si [B,L,2,2], isVisible [B,L])"""
+        hbar = np.empty((self.B, self.L, 2))
+        si = np.empty((self.B, self.L, 2, 2))
+        vis = np.empty((self.B, self.L), dtype=np.uint8)
+        capi.check(self._lib.srukf_get_prediction(self._h, capi.ptr(hbar), capi.ptr(si), capi.ptr(vis)))
+        return hbar, si, vis
+
+    def KalmanUpdate(self, matchLocation: np.ndarray, isMatching: np.ndarray):
+        z = np.ascontiguousarray(matchLocation, dtype=np.float64).reshape(self.B, self.L, 2)
+        m = np.ascontiguousarray(isMatching, dtype=np.uint8).reshape(self.B, self.L)
+        capi.check(self._lib.srukf_kalman_update(self._h, capi.ptr(z), capi.ptr(m)))
+
+    def SLAM(self, Ut, matchLocation, isMatching):
+        """One frame of the hot path: predictMotion + predictMeasurement + KalmanUpdate (SLAM.cpp:91-99)."""
+        u = np.ascontiguousarray(Ut, dtype=np.float64).reshape(self.B, 3)
+        z = np.ascontiguousarray(matchLocation, dtype=np.float64).reshape(self.B, self.L, 2)
+        m = np.ascontiguousarray(isMatching, dtype=np.uint8).reshape(self.B, self.L)
+        capi.check(self._lib.srukf_step(self._h, capi.ptr(u), capi.ptr(z), capi.ptr(m)))
+
+    def SLAM_dev(self, d_u: int, d_z: int, d_matched: int):
+        """Same, inputs already in HBM (integer device addresses); asynchronous."""
+        capi.check(self._lib.srukf_step_dev(self._h, d_u, d_z, d_matched))
+
+    # ---- diagnostics --------------------------------------------------------------------------
+    def flags(self) -> np.ndarray:
+        f = np.empty(self.B, dtype=np.uint32)
+        capi.check(self._lib.srukf_get_flags(self._h, capi.ptr(f)))
+        return f
+
+    def clear_flags(self):
+        capi.check(self._lib.srukf_clear_flags(self._h))
+
+    def stats(self, truth: np.ndarray) -> np.ndarray:
+        truth = np.ascontiguousarray(truth, dtype=np.float64).reshape(self.B, 3)
+        out = np.empty(8)
+        capi.check(self._lib.srukf_stats(self._h, capi.ptr(truth), capi.ptr(out)))
+        return out
+
+    def sync(self):
+        capi.check(self._lib.srukf_sync(self._h))
+
+    def stream(self) -> int:
+        s = C.c_uint64()
+        capi.check(self._lib.srukf_stream(self._h, C.byref(s)))
+        return s.value
+
+    def launch_count(self) -> int:
+        c = C.c_uint64()
+        capi.check(self._lib.srukf_launch_count(self._h, C.byref(c)))
+        return c.value
+
+    def state_dev(self):
+        dx, dS = C.c_void_p(), C.c_void_p()
+        capi.check(self._lib.srukf_state_dev(self._h, C.byref(dx), C.byref(dS)))
+        return dx.value, dS.value

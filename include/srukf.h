@@ -1,0 +1,111 @@
+/*
+ * srukf.h -- C ABI of the B200-native batched SRUKF predict/update (libsrukf_b200.so).
+ *
+ * The reference (junliu111/CV-MonoSLAM) has no plugin/FFI layer: its boundary for this path is the
+ * C++ class CSLAM (MonoSLAM/SLAM.h:118-398) whose methods communicate through public members.
+ * Each entry point below names the CSLAM method / member it replaces.  A reference maintainer binds
+ * them as shown in INTEGRATION.md (include/SLAM.h is the ready-made C++ facade).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all host arrays are caller-owned, C-contiguous doubles
+ *   - B independent filters, L landmarks each, n = 6L+4, state order
+ *       x = [f_0(6) .. f_{L-1}(6) | rx ry rz rtheta]            (SLAM.cpp:1659,2427-2432,1492-1523)
+ *   - S is the upper-triangular factor with P = S^T S (SLAM.cpp:2118), exchanged PACKED row-major:
+ *       row i holds columns i..n-1 at offset i*n - i*(i-1)/2 ; ntri = n(n+1)/2 doubles per filter
+ *   - every function returns 0 on success or a negative SRUKF_E* code; nothing aborts or prints
+ *   - a handle is bound to one device and one stream; calls on a handle are ordered
+ *   - *_dev variants take DEVICE pointers (same layouts) and enqueue without host copies
+ */
+#ifndef SRUKF_B200_H
+#define SRUKF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRUKF_OK 0
+#define SRUKF_EINVAL (-1)   /* bad argument */
+#define SRUKF_ECUDA (-2)    /* CUDA runtime error (srukf_last_error gives the string) */
+#define SRUKF_ENOMEM (-3)   /* device allocation failed */
+#define SRUKF_ESTATE (-4)   /* call order violated (e.g. update before predict_measurement) */
+#define SRUKF_ENODEV (-5)   /* no CUDA device: there is no CPU fallback */
+
+/* per-filter flag bits (srukf_get_flags) */
+#define SRUKF_FLAG_NAN 1u            /* non-finite value seen in x or S */
+#define SRUKF_FLAG_GMW_FLOOR 2u      /* GMW pivot raised to the EPSILON floor (expected, rank-deficient prior) */
+#define SRUKF_FLAG_GMW_MODIFIED 4u   /* GMW pivot modified beyond the floor: one-shot downdate not proven equal */
+#define SRUKF_FLAG_OUT_OF_VIEW 8u    /* some sigma-point projection left the image and was zeroed (SLAM.cpp:3341-3345) */
+#define SRUKF_FLAG_INVISIBLE 16u     /* some feature had a zero predicted pixel (SLAM.cpp:1727) */
+
+/* Replaces the scalar members CSLAM::cam_*, a1..a4, m_sigmaMeasure, m_weightType, m_sample.Alpha/Beta,
+ * EPSILON, imageWidth/imageHeight (SLAM.h:148,203-204,206,240,261,293-301; defaults SLAM.cpp:164-343). */
+typedef struct SrukfParams {
+  double cam_dx, cam_dy, cam_cx, cam_cy, cam_k1, cam_k2, cam_f;
+  int32_t image_width, image_height;
+  double a1, a2, a3, a4;
+  double sigma_measure;  /* Qt = I2 * sigma_measure (SLAM.cpp:238) */
+  int32_t weight_type;   /* 0,1,2 = FLAG_4_WEIGHT1..3 (SLAM.cpp:1062-1102) */
+  double alpha, beta;    /* m_sample.Alpha / Beta (SLAM.cpp:263-264), weight type 1 only */
+  double epsilon;        /* EPSILON (SLAM.cpp:52) */
+  int32_t newton_iters;  /* cap of the distortion Newton loop (SLAM.cpp:3186: 100); exits early once converged */
+  int32_t downdate_mode; /* 0 = one-shot GMW of S^T S - U U^T with device-side guard (default);
+                            1 = sequential per-column GMW exactly as SLAM.cpp:2116-2153 */
+} SrukfParams;
+
+typedef struct srukf_handle srukf_t;
+
+/* defaults of CSLAM::initializeParameters (SLAM.cpp:158-343) */
+void srukf_default_params(SrukfParams *p);
+
+/* CSLAM::CSLAM / ~CSLAM (SLAM.cpp:21-78) for B filters on CUDA device `device`. */
+int srukf_create(int device, int B, int L, const SrukfParams *params, srukf_t **out);
+int srukf_destroy(srukf_t *h);
+
+/* m_X_k, m_S_k (SLAM.h:271-272).  x: [B][n]; S_packed: [B][n(n+1)/2]. */
+int srukf_set_state(srukf_t *h, const double *x, const double *S_packed);
+int srukf_get_state(srukf_t *h, double *x, double *S_packed);
+/* dense helpers: S as [B][n][n] row-major (lower part ignored on input, zero on output) */
+int srukf_set_state_dense(srukf_t *h, const double *x, const double *S_dense);
+int srukf_get_state_dense(srukf_t *h, double *x, double *S_dense);
+
+/* CSLAM::predictMotion, motion part (SLAM.cpp:1430-1465): u is [B][3] = Ut (rot1, trans, rot2). */
+int srukf_predict_motion(srukf_t *h, const double *u);
+/* CSLAM::predictMeasurement (SLAM.cpp:1604-1608). */
+int srukf_predict_measurement(srukf_t *h);
+/* m_allPredictSet / map_p->predictLocation, map_p->Si, map_p->isVisible (SLAM.cpp:1724-1738):
+ * hbar [B][L][2], si [B][L][4] (2x2 row-major upper triangular), visible [B][L]; any may be NULL. */
+int srukf_get_prediction(srukf_t *h, double *hbar, double *si, uint8_t *visible);
+/* CSLAM::KalmanUpdate (SLAM.cpp:2048-2096): z [B][L][2] = matchLocation (x,y); matched [B][L] = isMatching. */
+int srukf_kalman_update(srukf_t *h, const double *z, const uint8_t *matched);
+/* predictMotion + predictMeasurement + KalmanUpdate of one CSLAM::SLAM() frame (SLAM.cpp:91,93,99). */
+int srukf_step(srukf_t *h, const double *u, const double *z, const uint8_t *matched);
+
+/* device-pointer variants (inputs already resident in HBM; asynchronous on the handle's stream) */
+int srukf_step_dev(srukf_t *h, const double *d_u, const double *d_z, const uint8_t *d_matched);
+int srukf_state_dev(srukf_t *h, double **d_x, double **d_S_packed);
+
+/* m_P_k block (SLAM.cpp:2404): P[r0:r0+nr, r0:r0+nr] of S^T S per filter, out [B][nr][nr]. */
+int srukf_get_cov_block(srukf_t *h, int r0, int nr, double *out);
+int srukf_get_flags(srukf_t *h, uint32_t *flags /* [B] */);
+int srukf_clear_flags(srukf_t *h);
+
+/* Monte-Carlo statistics (no reference equivalent): truth [B][3] = true (rx, ry, rtheta).
+ * out[8] = { sum ex^2, sum ey^2, sum etheta^2, sum NEES(x,y,theta), count, #flag NAN, #flag GMW_MODIFIED, 0 }
+ * These partial sums are what the multi-GPU driver all-reduces. */
+int srukf_stats(srukf_t *h, const double *truth, double *out8);
+
+int srukf_sync(srukf_t *h);
+/* cudaStream_t of the handle as an integer (for event timing on the launching stream) */
+int srukf_stream(srukf_t *h, uint64_t *stream);
+/* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
+int srukf_launch_count(srukf_t *h, uint64_t *count);
+const char *srukf_last_error(void);
+const char *srukf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRUKF_B200_H */
