@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- SRUKF filter-steps/s (predictMotion + predictMeasurement + KalmanUpdate, FP64).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+One "step" = one frame of the hot path for every filter of the batch.  Workload at N GPUs: BASELINE.json
+configs[2] per GPU (65,536 filters x 50 landmarks, n = 304, 619 sigma points), i.e. weak scaling towards
+configs[4] (524,288 filters at N = 8).  Synthetic inputs: cv_monoslam_b200/synth.py.
+
+Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the library's stream with inputs
+resident in HBM; `e2e` goes through the host-pointer C ABI (pinned host buffers, H2D of the step's inputs
+and D2H of m_X_k inside the timed region).  The roofline entry is for the dominant kernel (k_downdate),
+timed live with CUDA events by the library (srukf_set_profiling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP64_PEAK_TFLOPS = 37.2   # measured DMMA peak on this pool's B200 (profiles/r01_fp64_peak.json) == nominal
+
+
+# ------------------------------------------------------------------------------------------------------
+# work model (DESIGN.md "Work per filter-step"): flops of the formulation that is actually executed
+# ------------------------------------------------------------------------------------------------------
+def flops_downdate(n: int, L: int) -> float:
+    """k_downdate, one-shot mode: G = S^T S - U U^T on the packed triangle, then right-looking GMW."""
+    form = sum((n - j) * ((j + 1) + 2 * L) * 2.0 for j in range(n))
+    mchol = sum((n - j - 1) * (n - j) / 2.0 * 2.0 + 3.0 * (n - j) for j in range(n))
+    return form + mchol
+
+
+def flops_gain(n: int, L: int) -> float:
+    nf = n - 4
+    return nf * (nf + 1) / 2.0 * 2 * L * 2.0 + 12.0 * n * L + 8.0 * nf * L
+
+
+def flops_predict(n: int, L: int) -> float:
+    Na = n + 5
+    P = 2 * Na + 1
+    return 100.0 * P * L + 40.0 * P + 26.0 * 2 * Na * L   # projections (~100 flop each incl. sincos) + sums
+
+
+def algorithmic_bytes(n: int, L: int) -> float:
+    return 8.0 * (n * (n + 1) + 2 * n + 3 + 2 * L)          # packed S in+out, x in+out, u, z
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1])); pw.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(L: int, filters: int, steps: int, warmup: int, threads: int, seed_first: int = 0):
+    """Times the oracle port of the reference algorithm (literal mode: materialised sigma matrices, Householder
+    QR of the 2Na x n matrix, one dense S^T S + modified Cholesky per U column) on host cores.
+    Returns (seconds per step list, filters)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O  # the one place bench.py executes oracle/: as the measured CPU baseline
+    from cv_monoslam_b200 import synth
+    O.build()
+    sc = synth.make_scenario(L, filters, warmup + steps, unique=min(filters, 4), first_filter=seed_first)
+    p = O.default_params(downdate_mode=2)
+    x, S = sc.x0.copy(), sc.S0.copy()
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.batch_step(p, x, S, sc.u[s:s + 1], sc.z[s:s + 1], sc.matched[s:s + 1], threads)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    assert np.isfinite(x).all()
+    return times
+
+
+def run_reference(args, ctx):
+    """--impl reference: the reference's CPU algorithm (oracle port; oracle/_ref is unbuildable: MFC + OpenCV 2.4.3
+    + GSL 1.8) with all host threads, each step a bounded sample of the workload."""
+    if ctx.rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    L = args.landmarks
+    filters = cores
+    times = cpu_reference_run(L, filters, args.steps, args.warmup, cores)
+    tot = float(sum(times))
+    value = filters * len(times) / tot
+    n = 6 * L + 4
+    line = {
+        "impl": "reference", "metric": "srukf_filter_steps_per_sec", "value": value, "unit": "filter-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"batched SRUKF, {args.filters} filters x {L} landmarks per GPU (n={n}), FP64",
+                   "filters_per_gpu": args.filters, "landmarks": L, "state_dim": n, "sigma_points": 2 * (n + 5) + 1},
+        "cpu_baseline": {"value": value, "unit": "filter-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{filters} filters (one per host thread) x {len(times)} steps of the same workload, "
+                                   "oracle literal mode, gcc -O2"},
+        "e2e": {"value": value, "unit": "filter-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--filters", type=int, default=65536, help="filters per GPU (BASELINE config 3)")
+    ap.add_argument("--landmarks", type=int, default=50)
+    ap.add_argument("--unique", type=int, default=8, help="distinct synthetic worlds (priors) replicated over the batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--downdate-mode", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    from cv_monoslam_b200 import dist
+    if args.impl == "reference":
+        ctx = dist.Ctx(int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), 0, None)
+        run_reference(args, ctx)
+        return
+
+    import torch
+    ctx = dist.init()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    dev = ctx.local_rank
+    torch.cuda.set_device(dev)
+    from cv_monoslam_b200 import CSLAMBatch, capi, synth
+    from cv_monoslam_b200.slam import tri_pack
+
+    B, L = args.filters, args.landmarks
+    n = 6 * L + 4
+    ntri = n * (n + 1) // 2
+    W, K = args.warmup, args.steps
+    T = 2 * (W + K)                       # device-resident pass, then the end-to-end pass continues the run
+    first = ctx.rank * B                  # weak scaling: global filter ids of this rank
+    sc = synth.make_scenario(L, B, T, unique=args.unique, first_filter=first, dense_state=False)
+
+    g = CSLAMBatch(B, L, capi.default_params(downdate_mode=args.downdate_mode), device=dev)
+    # priors: upload the distinct worlds, replicate on the device
+    xw = torch.from_numpy(sc.x0).cuda()
+    Sw = torch.from_numpy(tri_pack(sc.S0)).cuda()
+    wof = torch.from_numpy(sc.meta["world_of"]).cuda()
+    slab = 4096
+    for b0 in range(0, B, slab):
+        nb = min(slab, B - b0)
+        idx = wof[b0:b0 + nb]
+        xs, Ss = xw[idx].contiguous(), Sw[idx].contiguous()
+        g.set_state_dev(b0, nb, xs.data_ptr(), Ss.data_ptr())
+    del xs, Ss
+    stream = torch.cuda.ExternalStream(g.stream(), device=dev)
+
+    # ---- pass 1: inputs resident in HBM ----------------------------------------------------------------
+    half = W + K
+    d_u = torch.from_numpy(sc.u[:half]).cuda()
+    d_z = torch.from_numpy(sc.z[:half]).cuda()
+    d_m = torch.from_numpy(sc.matched[:half]).cuda()
+    torch.cuda.synchronize()
+    for s in range(W):
+        g.SLAM_dev(d_u[s].data_ptr(), d_z[s].data_ptr(), d_m[s].data_ptr())
+    g.sync()
+    g.set_profiling(True)
+    launches0 = g.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier(ctx)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev)
+    e0.record(stream)
+    for s in range(W, W + K):
+        g.SLAM_dev(d_u[s].data_ptr(), d_z[s].data_ptr(), d_m[s].data_ptr())
+    e1.record(stream)
+    g.sync()
+    torch.cuda.synchronize()
+    dist.barrier(ctx)
+    clocks = sampler.stop()
+    ms_total = dist.max_over_ranks(ctx, e0.elapsed_time(e1))
+    launches = g.launch_count() - launches0
+    kms, kcnt = g.kernel_times()
+    g.set_profiling(False)
+    del d_u, d_z, d_m
+
+    # ---- pass 2: end to end through the host-pointer C ABI ---------------------------------------------
+    hu = torch.from_numpy(sc.u[half:]).pin_memory()
+    hz = torch.from_numpy(sc.z[half:]).pin_memory()
+    hm = torch.from_numpy(sc.matched[half:]).pin_memory()
+    hx = torch.empty((B, n), dtype=torch.float64).pin_memory()
+    hx_np = hx.numpy()
+    lib, hnd = g._lib, g._h
+    def e2e_step(s):
+        capi.check(lib.srukf_step(hnd, hu[s].data_ptr(), hz[s].data_ptr(), hm[s].data_ptr()))
+        capi.check(lib.srukf_get_state(hnd, hx.data_ptr(), None))
+    for s in range(W):
+        e2e_step(s)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier(ctx)
+    torch.cuda.synchronize()
+    f0.record(stream)
+    for s in range(W, W + K):
+        e2e_step(s)
+    f1.record(stream)
+    g.sync()
+    torch.cuda.synchronize()
+    dist.barrier(ctx)
+    ms_e2e = dist.max_over_ranks(ctx, f0.elapsed_time(f1))
+    h2d = B * (3 * 8 + 2 * L * 8 + L)
+    d2h = B * n * 8
+
+    # ---- statistics: the system's only collective (NCCL all-reduce of 8 doubles) --------------------------
+    part = g.stats(sc.truth[T - 1])
+    tot = dist.allreduce_stats(ctx, part)
+    stats = dist.summarise(tot)
+    stats["finite_state"] = bool(np.isfinite(hx_np).all())
+    flags = g.flags()
+    stats["flag_or"] = int(np.bitwise_or.reduce(flags))
+
+    # ---- CPU baseline (rank 0, N == 1 only) ---------------------------------------------------------------
+    cpu = None
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        times = cpu_reference_run(L, cores, 2, 0, cores)
+        cpu = {"value": cores * len(times) / sum(times), "unit": "filter-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{cores} filters (one per host thread) x {len(times)} steps at L={L}, oracle literal mode "
+                         f"(dense S^T S + GMW per U column), gcc -O2, {sum(times):.1f} s"}
+
+    if ctx.rank == 0:
+        total_steps = float(B) * ctx.world * K
+        value = total_steps / (ms_total * 1e-3)
+        wd = flops_downdate(n, L)
+        per_launch_filters = B * K / max(int(kcnt[2]), 1)
+        t_dd = kms[2] / max(int(kcnt[2]), 1) * 1e-3
+        achieved = wd * per_launch_filters / t_dd / 1e12 if t_dd > 0 else 0.0
+        w_total = wd + flops_gain(n, L) + flops_predict(n, L)
+        line = {
+            "metric": "srukf_filter_steps_per_sec", "value": value, "unit": "filter-steps/s",
+            "n_gpus": ctx.world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"batched SRUKF predict+update, {B} filters x {L} landmarks per GPU "
+                                   f"(n={n}, {2 * (n + 5) + 1} sigma points), FP64 (BASELINE configs[2])",
+                       "filters_per_gpu": B, "landmarks": L, "state_dim": n, "sigma_points": 2 * (n + 5) + 1,
+                       "distinct_worlds": int(sc.meta["unique"]), "parallelism": f"filters sharded over {ctx.world} GPU(s)",
+                       "l2": f"inputs larger than L2: {B * ntri * 8 / 2**30:.1f} GiB of packed S per GPU streamed per step",
+                       "downdate_mode": args.downdate_mode},
+            "clocks": clocks,
+            "e2e": {"value": total_steps / (ms_e2e * 1e-3), "unit": "filter-steps/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe)", "kernel": "k_downdate",
+                         "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                         "peak_source": "measured: tools/fp64_peak.cu DMMA m8n8k4 (profiles/r01_fp64_peak.json); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "flops_per_filter_step_kernel": wd, "flops_per_filter_step_all": w_total,
+                         "whole_step_frac": value / ctx.world * w_total / (FP64_PEAK_TFLOPS * 1e12),
+                         "kernel_ms": {"k_predict": float(kms[0]), "k_gain": float(kms[1]), "k_downdate": float(kms[2])},
+                         "kernel_launches": [int(c) for c in kcnt],
+                         "algorithmic_bytes_per_filter_step": algorithmic_bytes(n, L),
+                         "hbm_frac_of_measured_6454GBs": value / ctx.world * algorithmic_bytes(n, L) / 6454e9},
+            "cpu_baseline": cpu,
+            "stats": stats,
+        }
+        print(json.dumps(line), flush=True)
+    g.close()
+    dist.finalize(ctx)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,7 @@ SYMBOLS = {
     "srukf_step": (C.c_int, [_VP, _VP, _VP, _VP]),
     "srukf_step_dev": (C.c_int, [_VP, _VP, _VP, _VP]),
     "srukf_state_dev": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
+    "srukf_set_state_dev": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP]),
     "srukf_get_cov_block": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "srukf_get_flags": (C.c_int, [_VP, _VP]),
     "srukf_clear_flags": (C.c_int, [_VP]),
@@ -59,6 +60,8 @@ SYMBOLS = {
     "srukf_sync": (C.c_int, [_VP]),
     "srukf_stream": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "srukf_launch_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
+    "srukf_set_profiling": (C.c_int, [_VP, C.c_int]),
+    "srukf_get_kernel_times": (C.c_int, [_VP, _VP, _VP]),
     "srukf_last_error": (C.c_char_p, []),
     "srukf_version": (C.c_char_p, []),
 }

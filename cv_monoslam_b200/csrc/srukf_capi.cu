@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "srukf_device.cuh"
 
@@ -57,7 +58,41 @@ struct srukf_handle {
   int phase = 0;           // 0 idle, 1 motion done, 2 measurement done
   double *perf = nullptr, *stats_out = nullptr, *truth = nullptr;
   uint64_t launches = 0;
+  // optional per-kernel event timing
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;   // triples of (start, stop, kind) are stored as pairs + kinds
+  std::vector<int> ev_kind;
+  size_t ev_used = 0;
+  double prof_ms[3] = {0, 0, 0};
+  uint64_t prof_n[3] = {0, 0, 0};
 };
+
+static void prof_begin(srukf_handle* h, int kind) {
+  if (!h->profiling) return;
+  if (h->ev_used + 2 > h->ev.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    h->ev.push_back(a); h->ev.push_back(b);
+  }
+  h->ev_kind.push_back(kind);
+  cudaEventRecord(h->ev[h->ev_used], h->stream);
+}
+static void prof_end(srukf_handle* h) {
+  if (!h->profiling) return;
+  cudaEventRecord(h->ev[h->ev_used + 1], h->stream);
+  h->ev_used += 2;
+}
+static void prof_collect(srukf_handle* h) {
+  for (size_t i = 0; i + 1 < h->ev_used + 1 && i / 2 < h->ev_kind.size(); i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) {
+      h->prof_ms[h->ev_kind[i / 2]] += ms;
+      h->prof_n[h->ev_kind[i / 2]]++;
+    }
+  }
+  h->ev_used = 0;
+  h->ev_kind.clear();
+}
 
 extern "C" {
 
@@ -174,6 +209,7 @@ int srukf_destroy(srukf_t* h) {
   void* ptrs[] = {h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return SRUKF_OK;
@@ -312,8 +348,12 @@ int srukf_get_prediction(srukf_t* h, double* hbar, double* si, uint8_t* visible)
 // gain + downdate over [b0, b0+nb) with scratch indexed from 0
 static void run_update(srukf_t* h, StepPtrs q, int b0, int nb) {
   q.chunk0 = b0;
+  prof_begin(h, 1);
   launch_gain(h->p, q, nb, h->stream);
+  prof_end(h);
+  prof_begin(h, 2);
   launch_downdate(h->p, q, nb, h->prm.downdate_mode, h->stream);
+  prof_end(h);
   h->launches += 2;
 }
 
@@ -346,7 +386,9 @@ int srukf_step_dev(srukf_t* h, const double* d_u, const double* d_z, const uint8
   for (int b0 = 0; b0 < p.B; b0 += h->chunk) {
     int nb = p.B - b0 < h->chunk ? p.B - b0 : h->chunk;
     q.chunk0 = b0;
+    prof_begin(h, 0);
     launch_predict(p, q, nb, true, true, false, h->stream);
+    prof_end(h);
     h->launches++;
     run_update(h, q, b0, nb);
   }
@@ -369,6 +411,20 @@ int srukf_state_dev(srukf_t* h, double** d_x, double** d_S_packed) {
   if (!h) return fail(SRUKF_EINVAL, "srukf_state_dev: null handle");
   if (d_x) *d_x = h->x;
   if (d_S_packed) *d_S_packed = h->S;
+  return SRUKF_OK;
+}
+
+int srukf_set_state_dev(srukf_t* h, int b0, int nb, const double* d_x, const double* d_S_packed) {
+  if (!h || b0 < 0 || nb <= 0 || b0 + nb > h->p.B) return fail(SRUKF_EINVAL, "srukf_set_state_dev: bad arguments");
+  CU(cudaSetDevice(h->device));
+  if (d_x)
+    CU(cudaMemcpyAsync(h->x + (size_t)b0 * h->p.n, d_x, sizeof(double) * (size_t)nb * h->p.n, cudaMemcpyDeviceToDevice,
+                       h->stream));
+  if (d_S_packed)
+    CU(cudaMemcpyAsync(h->S + (size_t)b0 * h->p.ntri, d_S_packed, sizeof(double) * (size_t)nb * h->p.ntri,
+                       cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->phase = 0;
   return SRUKF_OK;
 }
 
@@ -418,6 +474,25 @@ int srukf_sync(srukf_t* h) {
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
+  return SRUKF_OK;
+}
+
+int srukf_set_profiling(srukf_t* h, int on) {
+  if (!h) return fail(SRUKF_EINVAL, "srukf_set_profiling: null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  prof_collect(h);
+  h->profiling = on != 0;
+  for (int i = 0; i < 3; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+  return SRUKF_OK;
+}
+
+int srukf_get_kernel_times(srukf_t* h, double* ms3, uint64_t* launches3) {
+  if (!h || !ms3) return fail(SRUKF_EINVAL, "srukf_get_kernel_times: null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  prof_collect(h);
+  for (int i = 0; i < 3; ++i) { ms3[i] = h->prof_ms[i]; if (launches3) launches3[i] = h->prof_n[i]; }
   return SRUKF_OK;
 }
 

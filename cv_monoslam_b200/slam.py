@@ -147,6 +147,26 @@ class CSLAMBatch:
         capi.check(self._lib.srukf_launch_count(self._h, C.byref(c)))
         return c.value
 
+    def set_profiling(self, on: bool):
+        capi.check(self._lib.srukf_set_profiling(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """(ms[3], launches[3]) of k_predict / k_gain / k_downdate since profiling was switched on."""
+        ms = np.zeros(3)
+        cnt = np.zeros(3, dtype=np.uint64)
+        capi.check(self._lib.srukf_get_kernel_times(self._h, capi.ptr(ms), capi.ptr(cnt)))
+        return ms, cnt
+
+    def get_x(self, out: np.ndarray | None = None) -> np.ndarray:
+        """m_X_k only (the per-frame result a caller reads back)."""
+        x = out if out is not None else np.empty((self.B, self.n))
+        capi.check(self._lib.srukf_get_state(self._h, capi.ptr(x), None))
+        return x
+
+    def set_state_dev(self, b0: int, nb: int, d_x: int | None, d_S_packed: int | None):
+        """Device-to-device load of filters [b0, b0+nb) (integer device addresses)."""
+        capi.check(self._lib.srukf_set_state_dev(self._h, b0, nb, d_x, d_S_packed))
+
     def state_dev(self):
         dx, dS = C.c_void_p(), C.c_void_p()
         capi.check(self._lib.srukf_state_dev(self._h, C.byref(dx), C.byref(dS)))

@@ -258,52 +258,71 @@ class Scenario:
     meta: dict = field(default_factory=dict)
 
 
+def make_world(L: int, world_id: int, steps: int, seed0: int, cam: Camera, noise: Noise):
+    """One synthetic world: prior (x0, S0), true trajectory and noise-free measurements."""
+    rng = np.random.default_rng(seed0 + world_id)
+    theta0 = rng.uniform(-np.pi, np.pi)
+    x4 = np.array([0.0, 0.0, 0.0, theta0])
+    pose = x4 + np.asarray(noise.S4) * rng.standard_normal(4)              # true initial pose
+    r = rng.uniform(noise.kp_radius[0], noise.kp_radius[1], L)
+    a = rng.uniform(0.0, 2 * np.pi, L)
+    kp = np.stack([cam.cx + r * np.cos(a), cam.cy + r * np.sin(a)], axis=-1)
+    # true landmarks: back-project the noise-free key-points from the true pose onto the ceiling
+    kp_true = kp - noise.pix_sigma * rng.standard_normal((L, 2))
+    d = backproject_direction(cam, kp_true, pose[3])
+    t = (noise.ceiling - pose[2]) / d[:, 2]
+    Pw = pose[None, 0:3] + t[:, None] * d
+    x0, S0 = init_prior(cam, noise, x4, kp)
+    truth = np.empty((steps, 3))
+    zc = np.empty((steps, L, 2))
+    r1, tr, r2 = noise.control
+    for s in range(steps):                                                  # odometry motion model, :1518-1521
+        pose[0] += tr * np.cos(pose[3] + r1)
+        pose[1] += tr * np.sin(pose[3] + r1)
+        pose[3] += r1 + r2
+        truth[s] = (pose[0], pose[1], pose[3])
+        zc[s] = project_world(cam, Pw, pose[None, 0:3], pose[3])
+    return x0, S0, truth, zc
+
+
 def make_scenario(L: int, B: int, steps: int, unique: int | None = None, seed0: int = SEED0,
-                  cam: Camera | None = None, noise: Noise | None = None, match_prob: float = 1.0) -> Scenario:
-    """B filters, `steps` frames.  Filter b uses seed seed0+b for its noise; priors/worlds are generated
-    for min(B, unique) distinct filters and replicated (throughput runs may replicate one
-    trajectory's inputs with per-filter noise seeds)."""
+                  cam: Camera | None = None, noise: Noise | None = None, match_prob: float = 1.0,
+                  first_filter: int = 0, dense_state: bool = True) -> Scenario:
+    """B filters (global ids first_filter .. first_filter+B-1), `steps` frames.
+
+    Global filter g lives in world g % unique (priors/worlds are generated once per world and replicated:
+    SURVEY 8(d) allows throughput runs to replicate one trajectory's inputs) and draws its odometry and
+    pixel noise from seed seed0 + 1000003*(g+1), so its inputs do not depend on how the batch is sharded."""
     cam = cam or Camera()
     noise = noise or Noise()
     n = 6 * L + 4
-    U = B if unique is None else max(1, min(B, unique))
-    worlds = []
-    for w_id in range(U):
-        rng = np.random.default_rng(seed0 + w_id)
-        theta0 = rng.uniform(-np.pi, np.pi)
-        x4 = np.array([0.0, 0.0, 0.0, theta0])
-        pose = x4 + np.asarray(noise.S4) * rng.standard_normal(4)          # true initial pose
-        r = rng.uniform(noise.kp_radius[0], noise.kp_radius[1], L)
-        a = rng.uniform(0.0, 2 * np.pi, L)
-        kp = np.stack([cam.cx + r * np.cos(a), cam.cy + r * np.sin(a)], axis=-1)
-        # true landmarks: back-project the noise-free key-points from the true pose onto the ceiling
-        kp_true = kp - noise.pix_sigma * rng.standard_normal((L, 2))
-        d = backproject_direction(cam, kp_true, pose[3])
-        t = (noise.ceiling - pose[2]) / d[:, 2]
-        Pw = pose[None, 0:3] + t[:, None] * d
-        x0, S0 = init_prior(cam, noise, x4, kp)
-        worlds.append((x0, S0, pose, Pw))
-    x0 = np.empty((B, n))
-    S0 = np.empty((B, n, n))
+    U = (first_filter + B) if unique is None else max(1, unique)
+    ids = np.arange(first_filter, first_filter + B)
+    worlds = {w: make_world(L, w, steps, seed0, cam, noise) for w in sorted(set(int(g % U) for g in ids))}
+    wkeys = sorted(worlds)
+    if dense_state:
+        x0 = np.empty((B, n))
+        S0 = np.empty((B, n, n))
+    else:  # per-world priors only (x0 [U',n], S0 [U',n,n]) plus meta["world_of"]: large batches replicate on device
+        x0 = np.stack([worlds[w][0] for w in wkeys])
+        S0 = np.stack([worlds[w][1] for w in wkeys])
+    world_of = np.array([wkeys.index(int(g % U)) for g in ids], dtype=np.int64)
     u = np.empty((steps, B, 3))
     z = np.empty((steps, B, L, 2))
     truth = np.empty((steps, B, 3))
     matched = np.ones((steps, B, L), dtype=np.uint8)
     ctrl = np.asarray(noise.control)
-    for b in range(B):
-        wx0, wS0, pose0, Pw = worlds[b % U]
-        x0[b], S0[b] = wx0, wS0
-        rng = np.random.default_rng(seed0 + 1_000_003 * (b + 1))
-        pose = pose0.copy()
-        for s in range(steps):
-            r1, tr, r2 = ctrl
-            pose[0] += tr * np.cos(pose[3] + r1)
-            pose[1] += tr * np.sin(pose[3] + r1)
-            pose[3] += r1 + r2
-            u[s, b] = ctrl + np.asarray(noise.odo_sigma) * rng.standard_normal(3)
-            z[s, b] = project_world(cam, Pw, pose[None, 0:3], pose[3]) + noise.pix_sigma * rng.standard_normal((L, 2))
-            truth[s, b] = (pose[0], pose[1], pose[3])
-            if match_prob < 1.0:
-                matched[s, b] = (rng.uniform(size=L) < match_prob).astype(np.uint8)
+    odo = np.asarray(noise.odo_sigma)
+    for b, g in enumerate(ids):
+        wx0, wS0, wtruth, wz = worlds[int(g % U)]
+        truth[:, b] = wtruth
+        if dense_state:
+            x0[b], S0[b] = wx0, wS0
+        rng = np.random.default_rng(seed0 + 1_000_003 * (int(g) + 1))
+        u[:, b] = ctrl + odo * rng.standard_normal((steps, 3))
+        z[:, b] = wz + noise.pix_sigma * rng.standard_normal((steps, L, 2))
+        if match_prob < 1.0:
+            matched[:, b] = (rng.uniform(size=(steps, L)) < match_prob).astype(np.uint8)
     return Scenario(L=L, B=B, steps=steps, x0=x0, S0=S0, u=u, z=z, matched=matched, truth=truth,
-                    meta=dict(unique=U, seed0=seed0, match_prob=match_prob))
+                    meta=dict(unique=U, seed0=seed0, match_prob=match_prob, first_filter=first_filter,
+                              world_of=world_of, dense_state=dense_state))

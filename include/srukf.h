@@ -86,6 +86,8 @@ int srukf_step(srukf_t *h, const double *u, const double *z, const uint8_t *matc
 /* device-pointer variants (inputs already resident in HBM; asynchronous on the handle's stream) */
 int srukf_step_dev(srukf_t *h, const double *d_u, const double *d_z, const uint8_t *d_matched);
 int srukf_state_dev(srukf_t *h, double **d_x, double **d_S_packed);
+/* device-to-device load of filters [b0, b0+nb): d_x [nb][n], d_S_packed [nb][n(n+1)/2] (either may be NULL) */
+int srukf_set_state_dev(srukf_t *h, int b0, int nb, const double *d_x, const double *d_S_packed);
 
 /* m_P_k block (SLAM.cpp:2404): P[r0:r0+nr, r0:r0+nr] of S^T S per filter, out [B][nr][nr]. */
 int srukf_get_cov_block(srukf_t *h, int r0, int nr, double *out);
@@ -102,6 +104,11 @@ int srukf_sync(srukf_t *h);
 int srukf_stream(srukf_t *h, uint64_t *stream);
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 int srukf_launch_count(srukf_t *h, uint64_t *count);
+/* Optional per-kernel timing with CUDA events on the handle's stream (bench.py's roofline leg).
+ * ms[3] = cumulative milliseconds of {k_predict, k_gain, k_downdate} launches, launches[3] their counts,
+ * both since profiling was last switched on.  srukf_get_kernel_times synchronises the stream. */
+int srukf_set_profiling(srukf_t *h, int on);
+int srukf_get_kernel_times(srukf_t *h, double *ms3, uint64_t *launches3);
 const char *srukf_last_error(void);
 const char *srukf_version(void);
 

@@ -523,23 +523,20 @@ static void cholesky_update(OracleFilter *f, const double *U, int nc, double sig
     if (mode == 1 && c > 0) {
       /* carry-P: S^T S == G + E exactly in real arithmetic (:2288, :2321) */
       for (int i = 0; i < n; i++) Pm[(size_t)i * n + i] += E[i];
-    } else if (mode == 2) {
-      /* dense product as cv::Mat operator* does it (no triangular shortcut); timing only */
-      for (int i = 0; i < n; i++)
-        for (int j = 0; j < n; j++) {
-          double acc = 0.0;
-          for (int k = 0; k < n; k++) acc += f->S[(size_t)k * n + i] * f->S[(size_t)k * n + j];
-          Pm[(size_t)i * n + j] = acc;
-        }
     } else {
-      /* src1 = S^T S, :2118 (S is upper triangular: terms with k > min(i,j) are exact zeros) */
-      for (int i = 0; i < n; i++)
-        for (int j = i; j < n; j++) {
-          double acc = 0.0;
-          for (int k = 0; k <= i; k++) acc += f->S[(size_t)k * n + i] * f->S[(size_t)k * n + j];
-          Pm[(size_t)i * n + j] = acc;
-          Pm[(size_t)j * n + i] = acc;
+      /* src1 = S^T S, :2118, accumulated as sum_k S(k,:)^T S(k,:) with k ascending (the order of a
+       * row-by-column product).  mode 0 skips the exact zeros below the diagonal of S; mode 2 runs the
+       * full dense n^3 loop as cv::Mat operator* does (CPU-baseline timing). */
+      memset(Pm, 0, sizeof(double) * (size_t)n * n);
+      for (int k = 0; k < n; k++) {
+        const double *row = f->S + (size_t)k * n;
+        int lo = (mode == 2) ? 0 : k;
+        for (int i = lo; i < n; i++) {
+          double a = row[i];
+          double *pr = Pm + (size_t)i * n;
+          for (int j = lo; j < n; j++) pr[j] += a * row[j];
         }
+      }
     }
     /* dst = src1 -+ u u^T, :2119-2120, :2144/:2149 */
     for (int i = 0; i < n; i++) {

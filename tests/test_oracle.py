@@ -1,0 +1,296 @@
+"""CPU tests of the oracle (oracle/srukf_oracle.c) -- the checker must itself be checked.
+
+The reference has no tests or golden vectors (parity unpinned), so the oracle is pinned by
+(1) an independent numpy/LAPACK restatement (tests/ref_numpy.py, cv_monoslam_b200/synth.py),
+(2) mpmath at 50 digits on small cases, (3) known-answer properties, (4) committed fixtures.
+"""
+import glob
+import os
+
+import mpmath
+import numpy as np
+import pytest
+
+import ref_numpy
+from conftest import relmax
+from cv_monoslam_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---- calculateSampleParameter (SLAM.cpp:1050-1103) -------------------------------------------------
+def test_sample_parameters_known_values(oracle):
+    w = oracle.sample_parameters(309)  # L=50: n=304, Na=309
+    assert w["wm0"] == 1.0 - 309 / 3.0 == -102.0
+    assert w["wc0"] == w["wm0"]
+    assert w["wi"] == pytest.approx(1.0 / 6.0, rel=1e-15)
+    assert w["gamma"] == pytest.approx(np.sqrt(3.0), rel=1e-15)
+    assert w["wm0"] + 2 * 309 * w["wi"] == pytest.approx(1.0, abs=1e-13)
+    assert np.sqrt(2.0) * w["wi_sr"] * w["gamma"] == pytest.approx(1.0, rel=1e-15)
+
+
+@pytest.mark.parametrize("wt", [0, 1, 2])
+@pytest.mark.parametrize("Na", [9, 69, 129, 309])
+def test_sample_parameters_match_numpy(oracle, wt, Na):
+    w = oracle.sample_parameters(Na, oracle.default_params(weight_type=wt))
+    r = synth.sample_weights(Na, wt)
+    for k in ("gamma", "wm0", "wc0", "wi", "wi_sr"):
+        assert w[k] == pytest.approx(r[k], rel=1e-14)
+    assert w["wm0"] + 2 * Na * w["wi"] == pytest.approx(1.0, abs=1e-9 if wt == 1 else 1e-13)
+    assert 2 * w["wi"] * w["gamma"] ** 2 == pytest.approx(1.0, rel=1e-9 if wt == 1 else 1e-14)
+
+
+# ---- GSL Householder QR (SLAM.cpp:2330-2353) -------------------------------------------------------
+@pytest.mark.parametrize("m,n", [(7, 3), (40, 12), (258, 124), (5, 5)])
+def test_qr_against_lapack(oracle, m, n):
+    rng = np.random.default_rng(m * 100 + n)
+    A = rng.standard_normal((m, n))
+    R = oracle.qr_R(A)
+    assert np.allclose(np.tril(R, -1), 0)
+    assert relmax(R.T @ R, A.T @ A) < 1e-13
+    Rl = np.linalg.qr(A, mode="r")       # LAPACK dgeqrf: same Householder sign convention as GSL
+    assert relmax(R, Rl) < 1e-12
+
+
+def test_qr_sign_convention_and_degenerate_columns(oracle):
+    A = np.array([[3.0, 1.0], [4.0, 2.0], [0.0, 2.0]])
+    R = oracle.qr_R(A)
+    assert R[0, 0] == pytest.approx(-5.0)              # beta = -sign(alpha) * norm
+    A2 = A.copy()
+    A2[:, 0] *= -1
+    assert oracle.qr_R(A2)[0, 0] == pytest.approx(5.0)
+    # zero sub-column => tau = 0 and the diagonal entry is left as is
+    A3 = np.array([[2.0, 1.0], [0.0, 3.0], [0.0, 4.0]])
+    R3 = oracle.qr_R(A3)
+    assert R3[0, 0] == 2.0 and R3[0, 1] == 1.0 and abs(R3[1, 1]) == pytest.approx(5.0)
+
+
+def test_qr_against_mpmath(oracle):
+    mpmath.mp.dps = 50
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((9, 4))
+    R = oracle.qr_R(A)
+    M = mpmath.matrix(A.tolist())
+    G = M.T * M
+    Lc = mpmath.cholesky(G)                            # G = Lc Lc^T => |R| = Lc^T
+    Rref = np.array([[float(Lc[j, i]) for j in range(4)] for i in range(4)])
+    assert relmax(np.abs(R), np.abs(Rref)) < 1e-13
+
+
+# ---- Gill-Murray-Wright modified Cholesky (SLAM.cpp:2197-2327) --------------------------------------
+def test_mchol_is_cholesky_on_pd_input(oracle):
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((30, 12))
+    G = A.T @ A + 0.1 * np.eye(12)
+    S, E, nmod = oracle.mchol(G)
+    assert nmod == 0 and np.all(E == 0)
+    assert relmax(S, np.linalg.cholesky(G).T) < 1e-12
+    assert np.all(np.diag(S) > 0)
+
+
+def test_mchol_floor_on_rank_deficient_input(oracle):
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((20, 6))
+    A = np.hstack([A, A[:, :3]])                       # 3 exactly dependent columns
+    G = A.T @ A
+    S, E, nmod = oracle.mchol(G)
+    assert nmod >= 3
+    assert np.allclose(np.diag(S)[6:], np.sqrt(1e-13), rtol=1e-3)
+    assert np.abs(S.T @ S - G).max() < 2e-13           # E is at the EPSILON floor
+    S2, E2 = synth.mchol(G)
+    assert np.abs(S - S2).max() < 1e-9 and np.abs(E - E2).max() < 1e-15
+
+
+def test_mchol_indefinite_input_matches_numpy_and_definition(oracle):
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((8, 8))
+    G = A + A.T                                        # indefinite
+    S, E, nmod = oracle.mchol(G)
+    assert nmod > 0 and np.abs(E).max() > 0.1
+    assert relmax(S.T @ S, G + np.diag(E)) < 1e-12     # G + E = L D L^T  (:2288, :2321)
+    S2, E2 = synth.mchol(G)
+    assert relmax(S, S2) < 1e-12 and relmax(E, E2) < 1e-12
+    # beta^2 uses the signed max off-diagonal (minMaxLoc, :2205), not max-abs
+    G2 = np.array([[1.0, -50.0], [-50.0, 1.0]])
+    S3, E3, _ = oracle.mchol(G2)
+    beta2 = 1.0                                        # max(gamma=1, max(0,-50)/nu, 1e-15)
+    d0 = max(1e-13, 1.0, 50.0 ** 2 / beta2)
+    assert S3[0, 0] == pytest.approx(np.sqrt(d0))
+
+
+def test_mchol_against_mpmath_ldl(oracle):
+    mpmath.mp.dps = 50
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((10, 5))
+    G = A.T @ A
+    S, E, _ = oracle.mchol(G)
+    Lc = mpmath.cholesky(mpmath.matrix(G.tolist()))
+    ref = np.array([[float(Lc[j, i]) for j in range(5)] for i in range(5)])
+    assert relmax(S, ref) < 1e-13
+
+
+# ---- camera chain (SLAM.cpp:3177-3347) -------------------------------------------------------------
+def test_distortion_fixed_point_and_numpy_agreement(oracle):
+    p = oracle.default_params()
+    cam = synth.Camera()
+    rng = np.random.default_rng(6)
+    pts = np.column_stack([rng.uniform(20, 620, 200), rng.uniform(20, 460, 200)])
+    nd = synth.distort(cam, pts)
+    for (ux, uy), (nx, ny) in zip(pts, nd):
+        ox, oy = oracle.distort(p, ux, uy)
+        assert abs(ox - nx) < 1e-10 and abs(oy - ny) < 1e-10
+        bx, by = oracle.undistort(p, ox, oy)           # undistort(distort(u)) == u
+        assert abs(bx - ux) < 1e-9 and abs(by - uy) < 1e-9
+    # 100 literal Newton iterations vs an early-exit loop: same fixed point
+    p5 = oracle.default_params(newton_iters=5)
+    for ux, uy in pts[:50]:
+        a = oracle.distort(p, ux, uy)
+        b = oracle.distort(p5, ux, uy)
+        assert abs(a[0] - b[0]) < 1e-12 and abs(a[1] - b[1]) < 1e-12
+
+
+def test_out_of_view_pixels_follow_the_reference_quirk(oracle):
+    p = oracle.default_params()
+    # undistorted pixel outside [10, W-10] x [10, H-10] is zeroed (:3341-3345), then distorted (:3181-3204)
+    feat = np.array([0.0, 0.0, 0.0, 1.2, 0.0, 1.0 / 3.0])   # far off-axis
+    ox, oy = oracle.project(p, feat, np.zeros(3), 0.0)
+    zx, zy = oracle.distort(p, 0.0, 0.0)
+    assert (ox, oy) == (zx, zy)
+
+
+def test_projection_matches_numpy_and_roundtrips_initialisation(oracle):
+    p = oracle.default_params()
+    cam = synth.Camera()
+    rng = np.random.default_rng(7)
+    for _ in range(50):
+        kp = np.array([cam.cx + rng.uniform(-100, 100), cam.cy + rng.uniform(-100, 100)])
+        pos = rng.normal(0, 0.05, 3)
+        th = rng.uniform(-3, 3)
+        d = synth.backproject_direction(cam, kp, th)
+        ang = np.array([np.arctan2(d[0], d[2]), np.arctan2(-d[1], np.hypot(d[0], d[2]))])
+        feat = np.concatenate([pos, ang, [1.0 / 3.0]])
+        ox, oy = oracle.project(p, feat, pos, th)
+        assert abs(ox - kp[0]) < 1e-8 and abs(oy - kp[1]) < 1e-8    # h(init(kp)) == kp
+        n = synth.project_state(cam, feat, pos, th)
+        assert abs(ox - n[0]) < 1e-10 and abs(oy - n[1]) < 1e-10
+
+
+def test_odometry_to_control(oracle):
+    u = oracle.odometry_to_control([0.0, 0.0, 0.1], [0.3, 0.4, 0.5])
+    assert u[1] == pytest.approx(0.5)
+    assert u[0] == pytest.approx(np.arctan2(0.4, 0.3) - 0.1)
+    assert u[0] + u[2] == pytest.approx(0.4)
+
+
+# ---- feature initialisation (SLAM.cpp:818-871, 1177-1334) ------------------------------------------
+@pytest.mark.parametrize("M", [1, 4, 10])
+def test_init_features_matches_numpy(oracle, M):
+    cam, noise = synth.Camera(), synth.Noise()
+    rng = np.random.default_rng(100 + M)
+    x4 = np.array([0.0, 0.0, 0.0, rng.uniform(-3, 3)])
+    kp = np.column_stack([cam.cx + rng.uniform(-120, 120, M), cam.cy + rng.uniform(-120, 120, M)])
+    xo, So = oracle.init_features(oracle.default_params(), x4, np.diag(noise.S4), kp, noise.rho0, noise.sigma_rho)
+    xn, Sn = synth.init_prior(cam, noise, x4, kp, canonical=False)
+    assert np.allclose(np.tril(So, -1), 0)
+    assert relmax(xo, xn) < 1e-13
+    assert relmax(So.T @ So, Sn.T @ Sn) < 1e-12
+    # anchors are copies of the robot position: P is rank deficient by 3 per feature beyond the first
+    P = So.T @ So
+    rank = np.linalg.matrix_rank(P, tol=1e-12)
+    assert rank == 4 + 3 * M
+
+
+# ---- whole frame ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L", [2, 5])
+def test_step_matches_independent_numpy_restatement(oracle, L):
+    sc = synth.make_scenario(L, 1, 3)
+    f = oracle.Filter(L, oracle.default_params(downdate_mode=0))
+    f.set_state(sc.x0[0], sc.S0[0])
+    x, S = sc.x0[0], sc.S0[0]
+    for s in range(3):
+        f.step(sc.u[s, 0], sc.z[s, 0], sc.matched[s, 0])
+        x, S, _ = ref_numpy.step(x, S, sc.u[s, 0], sc.z[s, 0], sc.matched[s, 0])
+        xo, So = f.get_state()
+        assert relmax(xo, x) < 1e-12
+        assert relmax(So.T @ So, S.T @ S) < 1e-12
+
+
+def test_downdate_modes_agree(oracle):
+    L = 6
+    sc = synth.make_scenario(L, 1, 4)
+    out = []
+    for mode in (0, 1, 2):
+        f = oracle.Filter(L, oracle.default_params(downdate_mode=mode))
+        f.set_state(sc.x0[0], sc.S0[0])
+        for s in range(4):
+            f.step(sc.u[s, 0], sc.z[s, 0], sc.matched[s, 0])
+        out.append(f.get_state())
+    for x, S in out[1:]:
+        assert relmax(x, out[0][0]) < 1e-12
+        assert relmax(S.T @ S, out[0][1].T @ out[0][1]) < 1e-12
+    assert np.array_equal(out[0][1], out[2][1])        # dense vs triangular-aware product: same bits
+
+
+def test_motion_leaves_feature_block_unchanged(oracle):
+    L = 6
+    sc = synth.make_scenario(L, 1, 1)
+    f = oracle.Filter(L)
+    f.set_state(sc.x0[0], sc.S0[0])
+    P0 = sc.S0[0].T @ sc.S0[0]
+    f.predict_motion(sc.u[0, 0])
+    x, S = f.get_state()
+    P1 = S.T @ S
+    nf = 6 * L
+    assert np.abs(P1[:nf, :nf] - P0[:nf, :nf]).max() < 1e-15
+    assert np.array_equal(x[:nf], sc.x0[0][:nf])
+    assert np.abs(P1[nf:, nf:] - P0[nf:, nf:]).max() > 1e-8   # the robot block does change
+
+
+def test_unmatched_features_do_not_update(oracle):
+    L = 4
+    sc = synth.make_scenario(L, 1, 1)
+    f = oracle.Filter(L)
+    f.set_state(sc.x0[0], sc.S0[0])
+    f.predict_motion(sc.u[0, 0])
+    f.predict_measurement()
+    x1, S1 = f.get_state()
+    f.kalman_update(sc.z[0, 0], np.zeros(L, dtype=np.uint8))     # KalmanUpdate returns early (:2050)
+    x2, S2 = f.get_state()
+    assert np.array_equal(x1, x2) and np.array_equal(S1, S2)
+
+
+def test_filter_is_stable_and_consistent_on_the_benchmark_inputs(oracle):
+    L = 8
+    sc = synth.make_scenario(L, 1, 40)
+    f = oracle.Filter(L, oracle.default_params(downdate_mode=1))
+    f.set_state(sc.x0[0], sc.S0[0])
+    tr = []
+    for s in range(40):
+        f.step(sc.u[s, 0], sc.z[s, 0], sc.matched[s, 0])
+        x, S = f.get_state()
+        tr.append(np.trace(S.T @ S))
+    assert np.isfinite(tr).all() and tr[-1] < tr[0]
+    n = 6 * L + 4
+    assert np.abs(x[[n - 4, n - 3]] - sc.truth[-1, 0, :2]).max() < 0.1
+
+
+# ---- committed fixtures ------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*.npz"))))
+def test_oracle_reproduces_golden_fixtures(oracle, path):
+    g = np.load(path)
+    L, B, steps = int(g["L"]), int(g["B"]), int(g["steps"])
+    x, S = g["x0"].copy(), g["S0"].copy()
+    p = oracle.default_params(downdate_mode=0)
+    for s in range(steps):
+        oracle.batch_step(p, x, S, g["u"][s:s + 1], g["z"][s:s + 1], g["matched"][s:s + 1], 4)
+        P = np.einsum("bki,bkj->bij", S, S)
+        for b in range(B):
+            assert relmax(x[b], g["x"][s, b]) < 1e-12
+            assert relmax(P[b], g["P"][s, b]) < 1e-12
+
+
+def test_golden_inputs_are_reproducible_from_seeds():
+    g = np.load(os.path.join(GOLD, "L3_B4_s6.npz"))
+    sc = synth.make_scenario(3, 4, 6)
+    assert np.array_equal(sc.u, g["u"]) and np.array_equal(sc.z, g["z"])
+    assert relmax(sc.x0, g["x0"]) < 1e-13 and relmax(sc.S0, g["S0"]) < 1e-9
