@@ -10,7 +10,7 @@ configs[4] (524,288 filters at N = 8).  Synthetic inputs: cv_monoslam_b200/synth
 
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the library's stream with inputs
 resident in HBM; `e2e` goes through the host-pointer C ABI (pinned host buffers, H2D of the step's inputs
-and D2H of m_X_k inside the timed region).  The roofline entry is for the dominant kernel (k_downdate),
+and D2H of m_X_k inside the timed region).  The roofline entry is for the dominant kernel (k_update),
 timed live with CUDA events by the library (srukf_set_profiling).
 """
 from __future__ import annotations
@@ -35,7 +35,8 @@ FP64_PEAK_TFLOPS = 37.2   # measured DMMA peak on this pool's B200 (profiles/r01
 # work model (DESIGN.md "Work per filter-step"): flops of the formulation that is actually executed
 # ------------------------------------------------------------------------------------------------------
 def flops_downdate(n: int, L: int) -> float:
-    """k_downdate, one-shot mode: G = S^T S - U U^T on the packed triangle, then right-looking GMW."""
+    """k_update: multiply-adds of G = S^T S - U U^T on the lower triangle plus its modified Cholesky (the fused
+    left-looking kernel performs the same products in panel order; padding and masked tiles are not counted)."""
     form = sum((n - j) * ((j + 1) + 2 * L) * 2.0 for j in range(n))
     mchol = sum((n - j - 1) * (n - j) / 2.0 * 2.0 + 3.0 * (n - j) for j in range(n))
     return form + mchol
@@ -294,14 +295,14 @@ def main():
             "e2e": {"value": total_steps / (ms_e2e * 1e-3), "unit": "filter-steps/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe)", "kernel": "k_downdate",
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe)", "kernel": "k_update",
                          "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
                          "peak_source": "measured: tools/fp64_peak.cu DMMA m8n8k4 (profiles/r01_fp64_peak.json); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_filter_step_kernel": wd, "flops_per_filter_step_all": w_total,
                          "whole_step_frac": value / ctx.world * w_total / (FP64_PEAK_TFLOPS * 1e12),
-                         "kernel_ms": {"k_predict": float(kms[0]), "k_gain": float(kms[1]), "k_downdate": float(kms[2])},
+                         "kernel_ms": {"k_predict": float(kms[0]), "k_gain": float(kms[1]), "k_update": float(kms[2])},
                          "kernel_launches": [int(c) for c in kcnt],
                          "algorithmic_bytes_per_filter_step": algorithmic_bytes(n, L),
                          "hbm_frac_of_measured_6454GBs": value / ctx.world * algorithmic_bytes(n, L) / 6454e9},

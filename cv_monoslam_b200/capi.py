@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libsrukf_b200.so")
 
 SRUKF_OK, SRUKF_EINVAL, SRUKF_ECUDA, SRUKF_ENOMEM, SRUKF_ESTATE, SRUKF_ENODEV = 0, -1, -2, -3, -4, -5
-FLAG_NAN, FLAG_GMW_FLOOR, FLAG_GMW_MODIFIED, FLAG_OUT_OF_VIEW, FLAG_INVISIBLE = 1, 2, 4, 8, 16
+FLAG_NAN, FLAG_GMW_FLOOR, FLAG_GMW_MODIFIED, FLAG_OUT_OF_VIEW, FLAG_INVISIBLE, FLAG_FALLBACK = 1, 2, 4, 8, 16, 32
 
 
 class SrukfError(RuntimeError):
@@ -51,7 +51,6 @@ SYMBOLS = {
     "srukf_kalman_update": (C.c_int, [_VP, _VP, _VP]),
     "srukf_step": (C.c_int, [_VP, _VP, _VP, _VP]),
     "srukf_step_dev": (C.c_int, [_VP, _VP, _VP, _VP]),
-    "srukf_state_dev": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
     "srukf_set_state_dev": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP]),
     "srukf_get_cov_block": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "srukf_get_flags": (C.c_int, [_VP, _VP]),

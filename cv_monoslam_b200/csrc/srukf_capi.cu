@@ -14,17 +14,22 @@ struct StepPtrs {
   double* x; double* S; const double* u; const double* z; const uint8_t* matched;
   double* hbar; double* si; uint8_t* visible; double* cshift; double* pxyr; double* rsig;
   double* dZ; double* U; double* G; uint32_t* flags; int chunk0;
+  double* S2; int* worklist; int rel0;
 };
+int tile_warps(const DevParams& p);
 cudaError_t configure_kernels(const DevParams& p);
 size_t predict_smem_bytes(const DevParams& p);
+size_t gain_smem_bytes(const DevParams& p);
+size_t update_smem_bytes(const DevParams& p);
 void launch_predict(const DevParams& p, const StepPtrs& q, int nblocks, bool motion, bool meas, bool save_rsig,
                     cudaStream_t st);
 void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st);
-void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, cudaStream_t st);
-void launch_pack(int B, int n, int ntri, const double* dense, double* packed, cudaStream_t st);
-void launch_unpack(int B, int n, int ntri, const double* packed, double* dense, cudaStream_t st);
-void launch_cov_block(int B, int n, int ntri, const double* S, int r0, int nr, double* out, cudaStream_t st);
-void launch_stats(int B, int n, int ntri, const double* x, const double* S, const double* truth, double* perf,
+void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st);
+void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, int use_worklist, cudaStream_t st);
+void launch_import(const DevParams& p, int nb, int fmt, const double* ext, double* bp, cudaStream_t st);
+void launch_export(const DevParams& p, int nb, int fmt, const double* bp, double* ext, cudaStream_t st);
+void launch_cov_block(const DevParams& p, const double* S, int r0, int nr, double* out, cudaStream_t st);
+void launch_stats(const DevParams& p, const double* x, const double* S, const double* truth, double* perf,
                   const uint32_t* flags, double* out, cudaStream_t st);
 }  // namespace srukf
 
@@ -43,8 +48,8 @@ struct srukf_handle {
   DevParams p{};
   SrukfParams prm{};
   cudaStream_t stream = nullptr;
-  // state
-  double *x = nullptr, *S = nullptr;
+  // state: S lives in the internal blocked-packed layout; k_update ping-pongs between S and S2
+  double *x = nullptr, *S = nullptr, *S2 = nullptr;
   // per-step inputs (device copies for the host-pointer API)
   double *u = nullptr, *z = nullptr; uint8_t* matched = nullptr;
   // prediction outputs
@@ -53,6 +58,8 @@ struct srukf_handle {
   // scratch
   int chunk = 0;           // filters per pipeline pass of srukf_step
   double *dZ = nullptr, *U = nullptr, *G = nullptr;
+  int gslots = 0;          // CTAs (and G scratch slots) of the reference-order fallback kernel
+  int* worklist = nullptr;
   // split-API persistent intermediates (allocated on first use)
   double *rsig = nullptr, *dZ_all = nullptr, *U_all = nullptr, *G_all = nullptr;
   int phase = 0;           // 0 idle, 1 motion done, 2 measurement done
@@ -115,6 +122,9 @@ const char* srukf_version(void) { return "srukf-b200 0.1 (sm_100a, fp64)"; }
 static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
   d.B = B; d.L = L; d.n = 6 * L + 4; d.nf = 6 * L; d.Na = d.n + 5; d.P = 2 * d.Na + 1;
   d.ntri = d.n * (d.n + 1) / 2;
+  d.np = (d.n + 7) & ~7;
+  d.Lc = (2 * L + 7) & ~7;
+  d.nbp = bp_block_off(d.np / 8, d.np);
   d.cam_dx = s.cam_dx; d.cam_dy = s.cam_dy; d.cam_cx = s.cam_cx; d.cam_cy = s.cam_cy;
   d.cam_k1 = s.cam_k1; d.cam_k2 = s.cam_k2;
   d.f1 = s.cam_f / s.cam_dx; d.f2 = s.cam_f / s.cam_dy;  // SLAM.cpp:336-337
@@ -160,7 +170,12 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   fill_dev_params(h->p, prm, B, L);
   const DevParams& p = h->p;
   if (std::fabs(p.cpair - 1.0) > 1e-12) { delete h; return fail(SRUKF_EINVAL, "srukf_create: sqrt(2)*wi_sr*gamma != 1"); }
-  if (predict_smem_bytes(p) > 227 * 1024) { delete h; return fail(SRUKF_EINVAL, "srukf_create: L too large for one CTA"); }
+  if (predict_smem_bytes(p) > 227 * 1024 || tile_warps(p) == 0 || update_smem_bytes(p) > 227 * 1024 ||
+      gain_smem_bytes(p) > 227 * 1024) {
+    delete h;
+    return fail(SRUKF_EINVAL, "srukf_create: L too large for one CTA (supported: L <= 106)");
+  }
+  if (prm.downdate_mode < 0 || prm.downdate_mode > 2) { delete h; return fail(SRUKF_EINVAL, "srukf_create: downdate_mode must be 0..2"); }
   cudaError_t e;
 #define CUH(x) do { e = (x); if (e != cudaSuccess) { int c_ = fail(e == cudaErrorMemoryAllocation ? SRUKF_ENOMEM : SRUKF_ECUDA, #x, e); srukf_destroy(h); return c_; } } while (0)
   CUH(cudaSetDevice(device));
@@ -168,7 +183,8 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   CUH(configure_kernels(p));
   const size_t n = p.n, L2 = 2 * (size_t)L;
   CUH(cudaMalloc(&h->x, sizeof(double) * B * n));
-  CUH(cudaMalloc(&h->S, sizeof(double) * (size_t)B * p.ntri));
+  CUH(cudaMalloc(&h->S, sizeof(double) * (size_t)B * p.nbp));
+  if (prm.downdate_mode == 0) CUH(cudaMalloc(&h->S2, sizeof(double) * (size_t)B * p.nbp));
   CUH(cudaMalloc(&h->u, sizeof(double) * B * 3));
   CUH(cudaMalloc(&h->z, sizeof(double) * B * L2));
   CUH(cudaMalloc(&h->matched, (size_t)B * L));
@@ -183,19 +199,24 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   CUH(cudaMalloc(&h->truth, sizeof(double) * B * 3));
   CUH(cudaMemsetAsync(h->flags, 0, sizeof(uint32_t) * B, h->stream));
   CUH(cudaMemsetAsync(h->x, 0, sizeof(double) * B * n, h->stream));
-  CUH(cudaMemsetAsync(h->S, 0, sizeof(double) * (size_t)B * p.ntri, h->stream));
+  CUH(cudaMemsetAsync(h->S, 0, sizeof(double) * (size_t)B * p.nbp, h->stream));
   CUH(cudaMemsetAsync(h->visible, 0, (size_t)B * L, h->stream));
-  // scratch: chunk sized so the pipeline scratch stays <= 2 GiB
-  size_t per = sizeof(double) * ((size_t)p.nf * L2 + n * L2 + (size_t)p.ntri);
+  // scratch: chunk sized so the pipeline scratch (V and Ut per filter) stays <= 2 GiB
+  size_t per = sizeof(double) * 2 * (size_t)p.np * p.Lc;
   size_t budget = (size_t)2 << 30;
   long chunk = (long)(budget / per);
   if (chunk < 1) chunk = 1;
   if (chunk > B) chunk = B;
-  if (chunk >= 296) chunk -= chunk % 148;  // whole waves of one CTA per SM
+  if (chunk >= 592) chunk -= chunk % 296;  // whole waves of two CTAs per SM
   h->chunk = (int)chunk;
-  CUH(cudaMalloc(&h->dZ, sizeof(double) * (size_t)chunk * p.nf * L2));
-  CUH(cudaMalloc(&h->U, sizeof(double) * (size_t)chunk * n * L2));
-  CUH(cudaMalloc(&h->G, sizeof(double) * (size_t)chunk * p.ntri));
+  h->gslots = (int)(chunk < 148 ? chunk : 148);
+  CUH(cudaMalloc(&h->dZ, sizeof(double) * (size_t)chunk * p.np * p.Lc));
+  CUH(cudaMalloc(&h->U, sizeof(double) * (size_t)chunk * p.Lc * p.np));
+  CUH(cudaMalloc(&h->G, sizeof(double) * (size_t)h->gslots * p.ntri));
+  CUH(cudaMalloc(&h->worklist, sizeof(int) * ((size_t)chunk + 1)));
+  CUH(cudaMemsetAsync(h->dZ, 0, sizeof(double) * (size_t)chunk * p.np * p.Lc, h->stream));
+  CUH(cudaMemsetAsync(h->U, 0, sizeof(double) * (size_t)chunk * p.Lc * p.np, h->stream));
+  CUH(cudaMemsetAsync(h->worklist, 0, sizeof(int) * ((size_t)chunk + 1), h->stream));
   CUH(cudaStreamSynchronize(h->stream));
 #undef CUH
   *out = h;
@@ -206,7 +227,7 @@ int srukf_destroy(srukf_t* h) {
   if (!h) return SRUKF_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+  void* ptrs[] = {h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -220,89 +241,82 @@ static StepPtrs base_ptrs(srukf_t* h) {
   q.x = h->x; q.S = h->S; q.u = h->u; q.z = h->z; q.matched = h->matched;
   q.hbar = h->hbar; q.si = h->si; q.visible = h->visible; q.cshift = h->cshift; q.pxyr = h->pxyr;
   q.rsig = h->rsig; q.dZ = h->dZ; q.U = h->U; q.G = h->G; q.flags = h->flags; q.chunk0 = 0;
+  q.S2 = h->S2; q.worklist = h->worklist; q.rel0 = 0;
   return q;
 }
 
-int srukf_set_state(srukf_t* h, const double* x, const double* S_packed) {
-  if (!h || !x || !S_packed) return fail(SRUKF_EINVAL, "srukf_set_state: null argument");
-  CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(h->x, x, sizeof(double) * (size_t)h->p.B * h->p.n, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->S, S_packed, sizeof(double) * (size_t)h->p.B * h->p.ntri, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  h->phase = 0;
-  return SRUKF_OK;
-}
-
-int srukf_get_state(srukf_t* h, double* x, double* S_packed) {
-  if (!h) return fail(SRUKF_EINVAL, "srukf_get_state: null handle");
-  CU(cudaSetDevice(h->device));
-  if (x) CU(cudaMemcpyAsync(x, h->x, sizeof(double) * (size_t)h->p.B * h->p.n, cudaMemcpyDeviceToHost, h->stream));
-  if (S_packed)
-    CU(cudaMemcpyAsync(S_packed, h->S, sizeof(double) * (size_t)h->p.B * h->p.ntri, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return SRUKF_OK;
-}
-
-int srukf_set_state_dense(srukf_t* h, const double* x, const double* S_dense) {
-  if (!h || !x || !S_dense) return fail(SRUKF_EINVAL, "srukf_set_state_dense: null argument");
-  CU(cudaSetDevice(h->device));
-  const size_t n = h->p.n;
-  // stage through a temporary in slices of <= 256 MiB
-  size_t per = sizeof(double) * n * n;
-  int slice = (int)(((size_t)256 << 20) / per);
-  if (slice < 1) slice = 1;
-  if (slice > h->p.B) slice = h->p.B;
+// external S (fmt 0 dense [B][n][n], fmt 1 upper-packed [B][ntri]) <-> internal layout, staged in slabs <= 256 MiB
+static int transfer_S(srukf_t* h, int fmt, const double* src_host, double* dst_host) {
+  const DevParams& p = h->p;
+  const size_t per = sizeof(double) * (fmt ? (size_t)p.ntri : (size_t)p.n * p.n);
+  int slab = (int)(((size_t)256 << 20) / per);
+  if (slab < 1) slab = 1;
+  if (slab > p.B) slab = p.B;
   double* tmp = nullptr;
-  CU(cudaMalloc(&tmp, per * slice));
-  for (int b0 = 0; b0 < h->p.B; b0 += slice) {
-    int nb = h->p.B - b0 < slice ? h->p.B - b0 : slice;
-    cudaError_t e = cudaMemcpyAsync(tmp, S_dense + (size_t)b0 * n * n, per * nb, cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) {
-      launch_pack(nb, (int)n, h->p.ntri, tmp, h->S + (size_t)b0 * h->p.ntri, h->stream);
-      h->launches++;
-      e = cudaStreamSynchronize(h->stream);
+  CU(cudaMalloc(&tmp, per * slab));
+  for (int b0 = 0; b0 < p.B; b0 += slab) {
+    const int nb = p.B - b0 < slab ? p.B - b0 : slab;
+    cudaError_t e = cudaSuccess;
+    if (src_host) {
+      e = cudaMemcpyAsync(tmp, (const char*)src_host + per * b0, per * nb, cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) launch_import(p, nb, fmt, tmp, h->S + (size_t)b0 * p.nbp, h->stream);
+    } else {
+      launch_export(p, nb, fmt, h->S + (size_t)b0 * p.nbp, tmp, h->stream);
+      e = cudaMemcpyAsync((char*)dst_host + per * b0, tmp, per * nb, cudaMemcpyDeviceToHost, h->stream);
     }
-    if (e != cudaSuccess) { cudaFree(tmp); return fail(SRUKF_ECUDA, "srukf_set_state_dense", e); }
+    h->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(tmp); return fail(SRUKF_ECUDA, "srukf state transfer", e); }
   }
   cudaFree(tmp);
-  CU(cudaMemcpyAsync(h->x, x, sizeof(double) * (size_t)h->p.B * n, cudaMemcpyHostToDevice, h->stream));
+  return SRUKF_OK;
+}
+
+static int set_state_any(srukf_t* h, const double* x, const double* S, int fmt, const char* who) {
+  if (!h || !x || !S) return fail(SRUKF_EINVAL, who);
+  CU(cudaSetDevice(h->device));
+  int rc = transfer_S(h, fmt, S, nullptr);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->x, x, sizeof(double) * (size_t)h->p.B * h->p.n, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   h->phase = 0;
   return SRUKF_OK;
 }
 
-int srukf_get_state_dense(srukf_t* h, double* x, double* S_dense) {
-  if (!h) return fail(SRUKF_EINVAL, "srukf_get_state_dense: null handle");
+static int get_state_any(srukf_t* h, double* x, double* S, int fmt, const char* who) {
+  if (!h) return fail(SRUKF_EINVAL, who);
   CU(cudaSetDevice(h->device));
-  const size_t n = h->p.n;
-  if (S_dense) {
-    size_t per = sizeof(double) * n * n;
-    int slice = (int)(((size_t)256 << 20) / per);
-    if (slice < 1) slice = 1;
-    if (slice > h->p.B) slice = h->p.B;
-    double* tmp = nullptr;
-    CU(cudaMalloc(&tmp, per * slice));
-    for (int b0 = 0; b0 < h->p.B; b0 += slice) {
-      int nb = h->p.B - b0 < slice ? h->p.B - b0 : slice;
-      launch_unpack(nb, (int)n, h->p.ntri, h->S + (size_t)b0 * h->p.ntri, tmp, h->stream);
-      h->launches++;
-      cudaError_t e = cudaMemcpyAsync(S_dense + (size_t)b0 * n * n, tmp, per * nb, cudaMemcpyDeviceToHost, h->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-      if (e != cudaSuccess) { cudaFree(tmp); return fail(SRUKF_ECUDA, "srukf_get_state_dense", e); }
-    }
-    cudaFree(tmp);
+  if (S) {
+    int rc = transfer_S(h, fmt, nullptr, S);
+    if (rc) return rc;
   }
-  if (x) CU(cudaMemcpyAsync(x, h->x, sizeof(double) * (size_t)h->p.B * n, cudaMemcpyDeviceToHost, h->stream));
+  if (x) CU(cudaMemcpyAsync(x, h->x, sizeof(double) * (size_t)h->p.B * h->p.n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return SRUKF_OK;
+}
+
+int srukf_set_state(srukf_t* h, const double* x, const double* S_packed) {
+  return set_state_any(h, x, S_packed, 1, "srukf_set_state: null argument");
+}
+int srukf_get_state(srukf_t* h, double* x, double* S_packed) {
+  return get_state_any(h, x, S_packed, 1, "srukf_get_state: null handle");
+}
+int srukf_set_state_dense(srukf_t* h, const double* x, const double* S_dense) {
+  return set_state_any(h, x, S_dense, 0, "srukf_set_state_dense: null argument");
+}
+int srukf_get_state_dense(srukf_t* h, double* x, double* S_dense) {
+  return get_state_any(h, x, S_dense, 0, "srukf_get_state_dense: null handle");
 }
 
 static int ensure_split_buffers(srukf_t* h) {
   const DevParams& p = h->p;
-  const size_t L2 = 2 * (size_t)p.L;
   if (!h->rsig) CU(cudaMalloc(&h->rsig, sizeof(double) * (size_t)p.B * p.P * 4));
   if (h->chunk >= p.B) return SRUKF_OK;  // the step scratch already covers the whole batch
-  if (!h->dZ_all) CU(cudaMalloc(&h->dZ_all, sizeof(double) * (size_t)p.B * p.nf * L2));
+  if (!h->dZ_all) {
+    CU(cudaMalloc(&h->dZ_all, sizeof(double) * (size_t)p.B * p.np * p.Lc));
+    CU(cudaMemsetAsync(h->dZ_all, 0, sizeof(double) * (size_t)p.B * p.np * p.Lc, h->stream));
+  }
   return SRUKF_OK;
 }
 
@@ -345,16 +359,33 @@ int srukf_get_prediction(srukf_t* h, double* hbar, double* si, uint8_t* visible)
   return SRUKF_OK;
 }
 
-// gain + downdate over [b0, b0+nb) with scratch indexed from 0
+// gain + covariance update over [b0, b0+nb) with scratch indexed from 0
 static void run_update(srukf_t* h, StepPtrs q, int b0, int nb) {
   q.chunk0 = b0;
   prof_begin(h, 1);
   launch_gain(h->p, q, nb, h->stream);
   prof_end(h);
+  h->launches++;
   prof_begin(h, 2);
-  launch_downdate(h->p, q, nb, h->prm.downdate_mode, h->stream);
+  if (h->prm.downdate_mode == 0) {
+    cudaMemsetAsync(h->worklist, 0, sizeof(int), h->stream);
+    launch_update(h->p, q, nb, h->stream);
+    launch_downdate(h->p, q, h->gslots, 1, 1, h->stream);  // reference-order redo of flagged filters (usually none)
+    h->launches += 2;
+  } else {
+    for (int r0 = 0; r0 < nb; r0 += h->gslots) {
+      q.rel0 = r0;
+      int m = nb - r0 < h->gslots ? nb - r0 : h->gslots;
+      launch_downdate(h->p, q, m, h->prm.downdate_mode, 0, h->stream);
+      h->launches++;
+    }
+  }
   prof_end(h);
-  h->launches += 2;
+}
+
+// after a fused update over the whole batch the roles of the two S buffers swap
+static void flip_buffers(srukf_t* h) {
+  if (h->prm.downdate_mode == 0) { double* t = h->S; h->S = h->S2; h->S2 = t; }
 }
 
 int srukf_kalman_update(srukf_t* h, const double* z, const uint8_t* matched) {
@@ -365,13 +396,13 @@ int srukf_kalman_update(srukf_t* h, const double* z, const uint8_t* matched) {
   CU(cudaMemcpyAsync(h->z, z, sizeof(double) * (size_t)p.B * 2 * p.L, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->matched, matched, (size_t)p.B * p.L, cudaMemcpyHostToDevice, h->stream));
   StepPtrs q = base_ptrs(h);
-  const size_t L2 = 2 * (size_t)p.L;
   for (int b0 = 0; b0 < p.B; b0 += h->chunk) {
     int nb = p.B - b0 < h->chunk ? p.B - b0 : h->chunk;
     StepPtrs qq = q;
-    if (h->dZ_all) qq.dZ = h->dZ_all + (size_t)b0 * p.nf * L2;
+    if (h->dZ_all) qq.dZ = h->dZ_all + (size_t)b0 * p.np * p.Lc;
     run_update(h, qq, b0, nb);
   }
+  flip_buffers(h);
   CU(cudaGetLastError());
   h->phase = 0;
   return SRUKF_OK;
@@ -392,6 +423,7 @@ int srukf_step_dev(srukf_t* h, const double* d_u, const double* d_z, const uint8
     h->launches++;
     run_update(h, q, b0, nb);
   }
+  flip_buffers(h);
   CU(cudaGetLastError());
   h->phase = 0;
   return SRUKF_OK;
@@ -407,23 +439,18 @@ int srukf_step(srukf_t* h, const double* u, const double* z, const uint8_t* matc
   return srukf_step_dev(h, h->u, h->z, h->matched);
 }
 
-int srukf_state_dev(srukf_t* h, double** d_x, double** d_S_packed) {
-  if (!h) return fail(SRUKF_EINVAL, "srukf_state_dev: null handle");
-  if (d_x) *d_x = h->x;
-  if (d_S_packed) *d_S_packed = h->S;
-  return SRUKF_OK;
-}
-
 int srukf_set_state_dev(srukf_t* h, int b0, int nb, const double* d_x, const double* d_S_packed) {
   if (!h || b0 < 0 || nb <= 0 || b0 + nb > h->p.B) return fail(SRUKF_EINVAL, "srukf_set_state_dev: bad arguments");
   CU(cudaSetDevice(h->device));
   if (d_x)
     CU(cudaMemcpyAsync(h->x + (size_t)b0 * h->p.n, d_x, sizeof(double) * (size_t)nb * h->p.n, cudaMemcpyDeviceToDevice,
                        h->stream));
-  if (d_S_packed)
-    CU(cudaMemcpyAsync(h->S + (size_t)b0 * h->p.ntri, d_S_packed, sizeof(double) * (size_t)nb * h->p.ntri,
-                       cudaMemcpyDeviceToDevice, h->stream));
+  if (d_S_packed) {
+    launch_import(h->p, nb, 1, d_S_packed, h->S + (size_t)b0 * h->p.nbp, h->stream);
+    h->launches++;
+  }
   CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
   h->phase = 0;
   return SRUKF_OK;
 }
@@ -434,7 +461,7 @@ int srukf_get_cov_block(srukf_t* h, int r0, int nr, double* out) {
   double* tmp = nullptr;
   size_t bytes = sizeof(double) * (size_t)h->p.B * nr * nr;
   CU(cudaMalloc(&tmp, bytes));
-  launch_cov_block(h->p.B, h->p.n, h->p.ntri, h->S, r0, nr, tmp, h->stream);
+  launch_cov_block(h->p, h->S, r0, nr, tmp, h->stream);
   h->launches++;
   cudaError_t e = cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -462,7 +489,7 @@ int srukf_stats(srukf_t* h, const double* truth, double* out8) {
   if (!h || !truth || !out8) return fail(SRUKF_EINVAL, "srukf_stats: null argument");
   CU(cudaSetDevice(h->device));
   CU(cudaMemcpyAsync(h->truth, truth, sizeof(double) * (size_t)h->p.B * 3, cudaMemcpyHostToDevice, h->stream));
-  launch_stats(h->p.B, h->p.n, h->p.ntri, h->x, h->S, h->truth, h->perf, h->flags, h->stats_out, h->stream);
+  launch_stats(h->p, h->x, h->S, h->truth, h->perf, h->flags, h->stats_out, h->stream);
   h->launches += 2;
   CU(cudaMemcpyAsync(out8, h->stats_out, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));

@@ -14,6 +14,9 @@ namespace srukf {
 // Per-handle constants, passed by value to every kernel.
 struct DevParams {
   int B, L, n, nf, Na, P, ntri;
+  int np;    // n rounded up to a multiple of 8 (internal padded state dimension)
+  int Lc;    // 2L rounded up to a multiple of 8 (padded measurement dimension)
+  int nbp;   // doubles per filter in the internal blocked-packed layout of S
   // camera (SLAM.cpp:329-337)
   double cam_dx, cam_dy, cam_cx, cam_cy, cam_k1, cam_k2, f1, f2;
   double img_w, img_h;
@@ -30,8 +33,39 @@ struct DevParams {
 // packed upper-triangular row-major: row i holds columns i..n-1
 __host__ __device__ __forceinline__ int tri_off(int i, int n) { return i * n - (i * (i - 1)) / 2; }
 
-__device__ __forceinline__ double S_at(const double* __restrict__ S, int n, int i, int c) {
-  return (c >= i) ? S[tri_off(i, n) + (c - i)] : 0.0;
+// Internal layout of S in HBM ("blocked-packed"): rows are grouped in blocks of 8; row k stores columns
+// [8*floor(k/8), np) contiguously (explicit zeros left of the diagonal), so every row segment that a kernel
+// streams starts 64-byte aligned and an 8-row block is one contiguous run.  Rows/columns n..np-1 are padding
+// (identity on the diagonal).
+__host__ __device__ __forceinline__ int bp_block_off(int blk, int np) { return 8 * (blk * np - 4 * blk * (blk - 1)); }
+__host__ __device__ __forceinline__ int bp_row_off(int k, int np) {
+  int blk = k >> 3;
+  return bp_block_off(blk, np) + (k - 8 * blk) * (np - 8 * blk);
+}
+// address of element (k, c), c >= 8*floor(k/8)
+__host__ __device__ __forceinline__ int bp_idx(int k, int c, int np) { return bp_row_off(k, np) + (c - ((k >> 3) << 3)); }
+
+__device__ __forceinline__ double S_at(const double* __restrict__ S, int np, int i, int c) {
+  return (c >= i) ? S[bp_idx(i, c, np)] : 0.0;
+}
+
+// FP64 tensor-core MMA (DMMA): D(8x8) += A(8x4, row) * B(4x8, col).
+//   a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], c0/c1 = C[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

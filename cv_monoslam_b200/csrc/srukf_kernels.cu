@@ -5,8 +5,13 @@
 //                structured square-root update of S (only the 4 robot columns change), ceiling-camera
 //                projections of every sigma point, predicted pixels, per-feature 2x2 factors, robot-row
 //                cross covariances, and dZ = z(+) - z(-) per sigma pair.
-//   k_gain     : U0 = S_ff^T (wi*gamma*dZ*si^-1), robot rows, sequential-in-feature state update.
-//   k_downdate : G = S^T S - U U^T and the Gill-Murray-Wright modified Cholesky -> S.
+//   k_gain     : U0 = S_ff^T (wi*gamma*dZ*si^-1) on the FP64 tensor pipe (DMMA), robot rows,
+//                sequential-in-feature state update.  U is kept transposed (Ut[c][row]).
+//   k_update   : fused left-looking blocked factorisation of G = S^T S - U U^T (never materialised): per
+//                32-column panel one DMMA contraction over [S_old rows | Ut rows | finished S_new rows], then
+//                the panel's modified-Cholesky pivots and a triangular solve.  Writes the other S buffer.
+//   k_downdate : reference-order fallback (unblocked GMW, optional per-column sequence) for flagged filters
+//                and for downdate_mode 1/2.
 #include "srukf_device.cuh"
 
 namespace srukf {
@@ -25,11 +30,14 @@ struct StepPtrs {
   double* cshift;         // [B][2L]   sum_i w_i (z_i - hbar) (zero analytically when wc0 == wm0)
   double* pxyr;           // [B][4][2L] robot rows of Pxy
   double* rsig;           // [B][P][4] propagated robot pose per sigma point (split API only)
-  double* dZ;             // [chunk][nf][2L]   z(+) - z(-), later V
-  double* U;              // [chunk][n][2L]
-  double* G;              // [chunk][ntri]
+  double* dZ;             // [chunk][np][Lc]   z(+) - z(-), later V (rows >= nf and columns >= 2L stay zero)
+  double* U;              // [chunk][Lc][np]   U transposed
+  double* G;              // [gslots][ntri]    scratch of the unblocked fallback
   uint32_t* flags;        // [B]
   int chunk0;             // first filter of this chunk (scratch arrays are chunk-relative)
+  double* S2;             // [B][nbp] the other S buffer (k_update writes it)
+  int* worklist;          // [0] = count, [1..] = chunk-relative filter indices needing the fallback
+  int rel0;               // first chunk-relative filter of a k_downdate launch (non-worklist)
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -89,7 +97,8 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
   double* red = z0 + 2 * L;        // 40
   double* work = red + 40;         // max((n+10)*4, slots*13)
   double* xg = q.x + (size_t)b * n;
-  double* Sg = q.S + (size_t)b * p.ntri;
+  double* Sg = q.S + (size_t)b * p.nbp;
+  const int np = p.np;
   uint32_t flags = 0;
 
   for (int i = tid; i < n; i += NT) xs[i] = xg[i];
@@ -111,10 +120,10 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
       double n0 = 0.0, n1 = 0.0, n2 = 0.0;
       if (k >= 0) {
         if (k < n) {  // addWeighted(mu, 1, row, +-gamma, 0), :1159-1160
-          bx = bx * 1 + S_at(Sg, n, k, n - 4) * sg;
-          by = by * 1 + S_at(Sg, n, k, n - 3) * sg;
-          bz = bz * 1 + S_at(Sg, n, k, n - 2) * sg;
-          bt = bt * 1 + S_at(Sg, n, k, n - 1) * sg;
+          bx = bx * 1 + S_at(Sg, np, k, n - 4) * sg;
+          by = by * 1 + S_at(Sg, np, k, n - 3) * sg;
+          bz = bz * 1 + S_at(Sg, np, k, n - 2) * sg;
+          bt = bt * 1 + S_at(Sg, np, k, n - 1) * sg;
         } else if (k == n) n0 = Mt0 * sg;
         else if (k == n + 1) n1 = Mt1 * sg;
         else if (k == n + 2) n2 = Mt2 * sg;
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
         s[c] = hs * (ap + am);
       }
       if (k < nf) {
-        double* row = Sg + tri_off(k, n) + (nf - k);
+        double* row = Sg + bp_idx(k, nf, np);
 #pragma unroll
         for (int c = 0; c < 4; ++c) row[c] = e[c];
       } else {
@@ -182,8 +191,7 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
     __syncthreads();
     householder4(T, n + 10, red);
     if (tid < 4) {
-      double* row = Sg + tri_off(nf + tid, n);
-      for (int c = tid; c < 4; ++c) row[c - tid] = T[tid * 4 + c];
+      for (int c = tid; c < 4; ++c) Sg[bp_idx(nf + tid, nf + c, np)] = T[tid * 4 + c];
     }
     if (save_rsig) {
       double* rg = q.rsig + (size_t)b * P * 4;
@@ -216,7 +224,8 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
     __syncthreads();
     const int G = (L <= NT) ? NT / L : 1;
     double* acc = work;  // [G*L][13]
-    double* dZ = q.dZ + (size_t)blockIdx.x * nf * 2 * L;
+    const int Lc = p.Lc;
+    double* dZ = q.dZ + (size_t)blockIdx.x * np * Lc;
     for (int slot = tid; slot < G * L; slot += NT) {
       const int g = slot / L, j = slot - g * L;
       const double* f = xs + 6 * j;
@@ -227,7 +236,7 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
         double s[6] = {0, 0, 0, 0, 0, 0};
         if (k < nf && k <= 6 * j + 5) {
 #pragma unroll
-          for (int c = 0; c < 6; ++c) s[c] = S_at(Sg, n, k, 6 * j + c);
+          for (int c = 0; c < 6; ++c) s[c] = S_at(Sg, np, k, 6 * j + c);
         }
         double e0 = (k == n + 3) ? gsm : 0.0, e1 = (k == n + 4) ? gsm : 0.0;
         const double* rp = rs + (size_t)(k + 1) * 6;
@@ -240,8 +249,8 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
                         f[3] * 1 - s[3] * p.gamma, f[4] * 1 - s[4] * p.gamma, f[5] * 1 - s[5] * p.gamma, rm[0], rm[1],
                         rm[2], rm[4], rm[5], -e0, -e1, mx, my, flags);
         if (k < nf) {
-          dZ[(size_t)k * 2 * L + 2 * j] = px - mx;
-          dZ[(size_t)k * 2 * L + 2 * j + 1] = py - my;
+          dZ[(size_t)k * Lc + 2 * j] = px - mx;
+          dZ[(size_t)k * Lc + 2 * j + 1] = py - my;
         }
         double bpx = px - zx0, bpy = py - zy0, bmx = mx - zx0, bmy = my - zy0;
         sb0 += bpx + bmx;
@@ -311,28 +320,64 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
 }
 
 // -------------------------------------------------------------------------------------------------
+// Shared tiling constants of the DMMA kernels.
+//   The CTA's warps own 8-row strips of the output (strip s -> warp s % NW, slot s / NW); a strip times
+//   NB columns is NB/8 DMMA tiles.  K is streamed in chunks of KC rows through a cp.async ring in smem.
+// -------------------------------------------------------------------------------------------------
+constexpr int NB = 32;      // panel width (columns per contraction pass)
+constexpr int KC = 8;       // K rows per pipeline stage
+constexpr int NSTAGE = 4;   // cp.async ring depth
+constexpr int MAXQ = 5;     // strips per warp: np <= 8 * NW * MAXQ
+constexpr int CP_PITCH = NB + 2;
+
+__host__ __device__ __forceinline__ int x_pitch(int R) { return ((R + 15) & ~15) + 8; }  // == 8 mod 16: conflict-free frags
+
+// one KC-row chunk: NT threads copy rows [0,KC) x columns [0,R) (doubles) with 16-byte cp.async.
+// src_row(kk) gives the global pointer of column 0 of row kk; columns < zero_below are zero-filled.
+template <int NTHREADS, typename RowFn>
+__device__ __forceinline__ void load_chunk(double* dst, int pitch, int R, int zero_below, RowFn src_row) {
+  const int half = R >> 1;
+  for (int p = threadIdx.x; p < KC * half; p += NTHREADS) {
+    int kk = p / half, c2 = p - kk * half;
+    int col = 2 * c2;
+    const double* src = src_row(kk);
+    bool valid = col >= zero_below;
+    cp_async16(dst + kk * pitch + col, valid ? (const void*)(src + col) : (const void*)src, valid ? 16 : 0);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // k_gain -- KalmanUpdate gain part (SLAM.cpp:2066-2080) for all matched features at once.
 //   U0_f = S_ff^T V with V = wi*gamma*dZ*blockdiag(si^-1)   (calculateOneFeatureCrossCovariance :2020-2038
 //          restricted to the feature rows, where sigma_i - x = +-gamma*S[i,:]; U = Ki*si^T = Pxy*si^-1)
 //   U0_r = Pxy_r si^-1 for the 4 robot rows
 //   then feature by feature (:2079): U_j = U0_j - dx (c_j^T si_j^-1);  dx += U_j (si_j^-T (z_j - hbar_j))
+// The triangular product runs on the FP64 tensor pipe: output strips of 8 state rows x 32 measurement
+// columns, K = the 8-row blocks of S (one contiguous run each in the blocked-packed layout).
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_gain(DevParams p, StepPtrs q) {
-  extern __shared__ double sm[];
-  const int tid = threadIdx.x;
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p, StepPtrs q) {
+  constexpr int NTH = NW * 32;
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = q.chunk0 + blockIdx.x;
-  const int n = p.n, nf = p.nf, L = p.L, L2 = 2 * p.L;
-  double* sii = sm;            // L x 4
-  double* gv = sii + 4 * L;    // L x 2  si^-T (z - hbar)
-  double* ct = gv + 2 * L;     // L x 2  c^T si^-1
-  int* act = (int*)(ct + 2 * L);  // L
+  const int n = p.n, nf = p.nf, L = p.L, L2 = 2 * p.L, np = p.np, Lc = p.Lc;
+  const int pitchA = x_pitch(np);
+  constexpr int pitchB = NB + 8;
+  double* sii = sm;                 // L x 4
+  double* gv = sii + 4 * L;         // L x 2  si^-T (z - hbar)
+  double* ct = gv + 2 * L;          // L x 2  c^T si^-1
+  int* act = (int*)(ct + 2 * L);    // L (+ count), padded to an even number of ints
   int* nact = act + L;
-  const double* Sg = q.S + (size_t)b * p.ntri;
-  double* dZ = q.dZ + (size_t)blockIdx.x * nf * L2;
-  double* U = q.U + (size_t)blockIdx.x * n * L2;
+  double* Xs = ct + 2 * L + ((L + 2 + 1) / 2);   // NSTAGE x KC x pitchA
+  Xs = (double*)(((uintptr_t)Xs + 15) & ~(uintptr_t)15);
+  double* Bs = Xs + (size_t)NSTAGE * KC * pitchA;  // NSTAGE x KC x pitchB
+  const double* Sg = q.S + (size_t)b * p.nbp;
+  double* V = q.dZ + (size_t)blockIdx.x * np * Lc;
+  double* Ut = q.U + (size_t)blockIdx.x * Lc * np;
   if (tid == 0) *nact = 0;
   __syncthreads();
-  for (int j = tid; j < L; j += NT) {
+  for (int j = tid; j < L; j += NTH) {
     const double* s = q.si + ((size_t)b * L + j) * 4;
     const bool a = q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j];
     // si.inv(), :2077 (2x2 closed form)
@@ -358,48 +403,114 @@ __global__ void __launch_bounds__(NT) k_gain(DevParams p, StepPtrs q) {
     if (ok) atomicAdd(nact, 1);
   }
   __syncthreads();
-  if (*nact == 0) {  // KalmanUpdate returns early, :2050
-    for (int i = tid; i < n * L2; i += NT) U[i] = 0.0;
-    return;
-  }
-  // V = wi*gamma * dZ * blockdiag(sii) in place
+  if (*nact == 0) return;  // KalmanUpdate returns early, :2050 (k_update copies S through)
+  // V = wi*gamma * dZ * blockdiag(sii) in place (rows >= nf and columns >= 2L are zero by construction)
   const double wg = p.wi * p.gamma;
-  for (int i = tid; i < nf * L; i += NT) {
+  for (int i = tid; i < nf * L; i += NTH) {
     int k = i / L, j = i - k * L;
-    double* d = dZ + (size_t)k * L2 + 2 * j;
+    double* d = V + (size_t)k * Lc + 2 * j;
     double d0 = d[0], d1 = d[1];
     d[0] = wg * (d0 * sii[4 * j] + d1 * sii[4 * j + 2]);
     d[1] = wg * (d0 * sii[4 * j + 1] + d1 * sii[4 * j + 3]);
   }
   __syncthreads();
-  // U0_f = S_ff^T V
-  for (int i = tid; i < nf * L2; i += NT) {
-    int f = i / L2, c = i - f * L2;
-    double acc = 0.0;
-    for (int k = 0; k <= f; ++k) acc += Sg[tri_off(k, n) + (f - k)] * dZ[(size_t)k * L2 + c];
-    U[(size_t)f * L2 + c] = acc;
+  // ---- U0_f = S_ff^T V on DMMA, 32 measurement columns per pass ---------------------------------
+  const int nblk = np / 8;  // 8-row blocks of S == K chunks == output strips
+  for (int cg = 0; cg < Lc; cg += NB) {
+    const int ncol = (Lc - cg < NB) ? (Lc - cg) : NB;
+    const int nt = ncol / 8;
+    double acc[MAXQ][NB / 8][2];
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq)
+#pragma unroll
+      for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
+    auto issue = [&](int t) {
+      if (t < nblk) {
+        const int k0 = 8 * t, R = np - k0, st = t % NSTAGE;
+        const double* src = Sg + bp_block_off(t, np);
+        load_chunk<NTH>(Xs + (size_t)st * KC * pitchA, pitchA, R, 0, [&](int kk) { return src + (size_t)kk * R; });
+        const double* vsrc = V + (size_t)k0 * Lc + cg;
+        double* bd = Bs + (size_t)st * KC * pitchB;
+        for (int pp = tid; pp < KC * (ncol / 2); pp += NTH) {
+          int kk = pp / (ncol / 2), c2 = pp - kk * (ncol / 2);
+          cp_async16(bd + kk * pitchB + 2 * c2, vsrc + (size_t)kk * Lc + 2 * c2, 16);
+        }
+      }
+      cp_async_commit();
+    };
+    for (int t = 0; t < NSTAGE - 1; ++t) issue(t);
+    for (int t = 0; t < nblk; ++t) {
+      cp_async_wait<NSTAGE - 2>();
+      __syncthreads();
+      issue(t + NSTAGE - 1);
+      const double* xa = Xs + (size_t)(t % NSTAGE) * KC * pitchA;  // column 0 == state row 8t
+      const double* xb = Bs + (size_t)(t % NSTAGE) * KC * pitchB;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int kk = 4 * ks + (lane & 3);
+        double bf[NB / 8];
+#pragma unroll
+        for (int tt = 0; tt < NB / 8; ++tt) bf[tt] = (tt < nt) ? xb[kk * pitchB + 8 * tt + (lane >> 2)] : 0.0;
+#pragma unroll
+        for (int qq = 0; qq < MAXQ; ++qq) {
+          const int s = warp + NW * qq;  // output strip (state rows 8s..8s+7); receives S rows k <= its own
+          if (s >= t && s < nblk) {
+            double a = xa[kk * pitchA + 8 * (s - t) + (lane >> 2)];
+#pragma unroll
+            for (int tt = 0; tt < NB / 8; ++tt)
+              if (tt < nt) dmma(acc[qq][tt][0], acc[qq][tt][1], a, bf[tt]);
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // epilogue: Ut[c][f] (transposed store), feature rows only
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq) {
+      const int s = warp + NW * qq;
+      if (s < nblk) {
+        const int f = 8 * s + (lane >> 2);
+#pragma unroll
+        for (int tt = 0; tt < NB / 8; ++tt) {
+          if (tt < nt && f < nf) {
+            const int c = cg + 8 * tt + 2 * (lane & 3);
+            Ut[(size_t)c * np + f] = acc[qq][tt][0];
+            Ut[(size_t)(c + 1) * np + f] = acc[qq][tt][1];
+          }
+        }
+      }
+    }
   }
-  // U0_r = Pxy_r sii
-  for (int i = tid; i < 4 * L; i += NT) {
+  // U0_r = Pxy_r sii ; padding rows/columns of Ut are zero
+  for (int i = tid; i < 4 * L; i += NTH) {
     int r = i / L, j = i - r * L;
     const double* pr = q.pxyr + (size_t)b * 8 * L + (size_t)r * L2 + 2 * j;
-    double* u = U + (size_t)(nf + r) * L2 + 2 * j;
-    u[0] = pr[0] * sii[4 * j] + pr[1] * sii[4 * j + 2];
-    u[1] = pr[0] * sii[4 * j + 1] + pr[1] * sii[4 * j + 3];
+    Ut[(size_t)(2 * j) * np + nf + r] = pr[0] * sii[4 * j] + pr[1] * sii[4 * j + 2];
+    Ut[(size_t)(2 * j + 1) * np + nf + r] = pr[0] * sii[4 * j + 1] + pr[1] * sii[4 * j + 3];
+  }
+  for (int i = tid; i < Lc * (np - n); i += NTH) {
+    int c = i / (np - n), f = n + (i - c * (np - n));
+    Ut[(size_t)c * np + f] = 0.0;
+  }
+  for (int i = tid; i < (Lc - L2) * 4; i += NTH) {
+    int c = L2 + i / 4, f = nf + (i & 3);
+    Ut[(size_t)c * np + f] = 0.0;
   }
   __syncthreads();
   // feature-sequential state update, one state row per thread
   double* xg = q.x + (size_t)b * n;
   uint32_t flags = 0;
-  for (int r = tid; r < n; r += NT) {
+  for (int r = tid; r < n; r += NTH) {
     double dx = 0.0;
-    double* u = U + (size_t)r * L2;
     for (int j = 0; j < L; ++j) {
-      if (!act[j]) { u[2 * j] = 0.0; u[2 * j + 1] = 0.0; continue; }
-      double u0 = u[2 * j] - dx * ct[2 * j];
-      double u1 = u[2 * j + 1] - dx * ct[2 * j + 1];
-      u[2 * j] = u0;
-      u[2 * j + 1] = u1;
+      double* u0p = Ut + (size_t)(2 * j) * np + r;
+      double* u1p = u0p + np;
+      if (!act[j]) { *u0p = 0.0; *u1p = 0.0; continue; }
+      double u0 = *u0p - dx * ct[2 * j];
+      double u1 = *u1p - dx * ct[2 * j + 1];
+      *u0p = u0;
+      *u1p = u1;
       dx += u0 * gv[2 * j] + u1 * gv[2 * j + 1];
     }
     double xn = xg[r] + dx;
@@ -407,15 +518,250 @@ __global__ void __launch_bounds__(NT) k_gain(DevParams p, StepPtrs q) {
     if (!isfinite(xn)) flags |= SRUKF_FLAG_NAN;
   }
   flags = __reduce_or_sync(0xffffffffu, flags);
-  if ((tid & 31) == 0 && flags) atomicOr(q.flags + b, flags);
+  if (lane == 0 && flags) atomicOr(q.flags + b, flags);
 }
 
 // -------------------------------------------------------------------------------------------------
-// Gill-Murray-Wright modified Cholesky (SLAM.cpp:2197-2327) of the packed symmetric G (column j of the
-// lower triangle == row j of the packed upper layout), right-looking, in place; S receives sqrt(D) L^T.
+// k_update -- GSLCholeskyUpdate (DOWNDATING, NEEDNOT_REORDER; SLAM.cpp:2106-2121,2139-2153) for all matched
+// features at once: S_new = modifiedCholesky(S_old^T S_old - U U^T)  (SLAM.cpp:2197-2327).
+//
+// Left-looking, 32 columns per panel; G is never formed.  For panel columns J = [J0, J0+32) and rows i >= J0
+//     C(i, J) = sum_{k < J0+32} S_old(k,i) S_old(k,J) - sum_c Ut(c,i) Ut(c,J) - sum_{k < J0} S_new(k,i) S_new(k,J)
+// is one DMMA contraction over K = [S_old rows | Ut rows | S_new rows]; all three are K-major in HBM, so the
+// same smem chunk feeds the A fragment (rows i) and the B fragment (its first 32 columns).  Then
+//   - warp 0 factorises the 32x32 diagonal block in registers with the GMW pivot rule
+//       d_j = max(EPSILON, |c_jj|)                      (:2279-2285; theta_j^2/beta^2 handled below)
+//   - every thread solves one row below the block against it (C(i,j) = G(i,j) - sum_k L(j,k) C(i,k), :2253)
+//   - rows J of S_new = sqrt(d_j) * C(:,j)/d_j are written (:2321).
+// GMW's third pivot candidate theta_j^2/beta^2 exceeds d_j iff max_i S_new(j,i)^2 > beta^2, where beta^2 needs
+// max diag / max off-diag of G (:2204-2211).  Both maxima are accumulated on the fly (G's panel is visible after
+// the S_old and Ut sources) and compared at the end: on violation, or when a pivot is modified beyond the EPSILON
+// floor, the filter is queued for the reference-order fallback (k_downdate) which recomputes it from S_old.
+// -------------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams p, StepPtrs q) {
+  constexpr int NTH = NW * 32;
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = q.chunk0 + blockIdx.x;
+  const int n = p.n, L = p.L, np = p.np, Lc = p.Lc;
+  const double* Sold = q.S + (size_t)b * p.nbp;
+  double* Snew = q.S2 + (size_t)b * p.nbp;
+  const double* Ut = q.U + (size_t)blockIdx.x * Lc * np;
+  double* Ld = sm;                       // NB x (NB+1)
+  double* dsm = Ld + NB * (NB + 1);      // NB   pivots d_j
+  double* sdsm = dsm + NB;               // NB   sqrt(d_j)
+  double* red = sdsm + NB;               // 40
+  double* Xs = red + 40;                 // ring: NSTAGE x KC x pitch, aliased by the panel Cp[R][CP_PITCH]
+  Xs = (double*)(((uintptr_t)Xs + 15) & ~(uintptr_t)15);
+  double* Cp = Xs;
+  uint32_t flags = 0;
+
+  int nact = 0;
+  for (int j = 0; j < L; ++j) nact += (q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j]) ? 1 : 0;
+  if (nact == 0) {  // KalmanUpdate returned early (:2050): the factor is carried over unchanged
+    for (int i = tid; i < p.nbp; i += NTH) Snew[i] = Sold[i];
+    return;
+  }
+  double gmax = -1.0e300, zmax = 0.0, tmax = 0.0;
+
+  for (int J0 = 0; J0 < np; J0 += NB) {
+    const int nbe = (np - J0 < NB) ? (np - J0) : NB;
+    const int R = np - J0;
+    const int nt = nbe / 8;
+    const int pitch = x_pitch(R);
+    const int nA = (J0 + nbe) / KC, nU = Lc / KC, nC = J0 / KC;
+    const int nchunks = nA + nU + nC;
+    const int nstrip = R / 8;
+    double acc[MAXQ][NB / 8][2];
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq)
+#pragma unroll
+      for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
+
+    auto issue = [&](int t) {
+      if (t < nchunks) {
+        double* dst = Xs + (size_t)(t % NSTAGE) * KC * pitch;
+        if (t < nA) {  // S_old rows 8t..8t+7, columns [J0, np); stored from column 8t
+          const int k0 = 8 * t, len = np - k0;
+          const double* src = Sold + bp_block_off(t, np) + (J0 - k0);
+          load_chunk<NTH>(dst, pitch, R, (k0 > J0) ? (k0 - J0) : 0, [&](int kk) { return src + (size_t)kk * len; });
+        } else if (t < nA + nU) {
+          const double* src = Ut + (size_t)(8 * (t - nA)) * np + J0;
+          load_chunk<NTH>(dst, pitch, R, 0, [&](int kk) { return src + (size_t)kk * np; });
+        } else {
+          const int blk = t - nA - nU, k0 = 8 * blk, len = np - k0;
+          const double* src = Snew + bp_block_off(blk, np) + (J0 - k0);
+          load_chunk<NTH>(dst, pitch, R, 0, [&](int kk) { return src + (size_t)kk * len; });
+        }
+      }
+      cp_async_commit();
+    };
+    for (int t = 0; t < NSTAGE - 1; ++t) issue(t);
+    for (int t = 0; t < nchunks; ++t) {
+      cp_async_wait<NSTAGE - 2>();
+      __syncthreads();
+      issue(t + NSTAGE - 1);
+      const double* xs_ = Xs + (size_t)(t % NSTAGE) * KC * pitch;
+      const bool neg = (t >= nA);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int kk = 4 * ks + (lane & 3);
+        const double* row = xs_ + kk * pitch + (lane >> 2);
+        double bf[NB / 8];
+#pragma unroll
+        for (int tt = 0; tt < NB / 8; ++tt) bf[tt] = (tt < nt) ? row[8 * tt] : 0.0;
+#pragma unroll
+        for (int qq = 0; qq < MAXQ; ++qq) {
+          const int rs = warp + NW * qq;  // strip relative to the panel: rows J0 + 8rs ..
+          if (rs < nstrip) {
+            double a = row[8 * rs];
+            if (neg) a = -a;
+#pragma unroll
+            for (int tt = 0; tt < NB / 8; ++tt)
+              if (tt < nt && rs >= tt) dmma(acc[qq][tt][0], acc[qq][tt][1], a, bf[tt]);
+          }
+        }
+      }
+      if (t == nA + nU - 1) {  // acc == G(i, J): track max diag / max off-diag for beta^2 (:2204-2205)
+#pragma unroll
+        for (int qq = 0; qq < MAXQ; ++qq) {
+          const int rs = warp + NW * qq;
+          if (rs < nstrip) {
+            const int i = J0 + 8 * rs + (lane >> 2);
+#pragma unroll
+            for (int tt = 0; tt < NB / 8; ++tt) {
+              if (tt < nt && rs >= tt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int j = J0 + 8 * tt + 2 * (lane & 3) + e;
+                  const double v = acc[qq][tt][e];
+                  if (i < n && j < n) {
+                    if (i == j) gmax = fmax(gmax, v);
+                    else if (i > j) zmax = fmax(zmax, v);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // accumulators -> panel in smem (aliases the ring)
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq) {
+      const int rs = warp + NW * qq;
+      if (rs < nstrip) {
+        const int ri = 8 * rs + (lane >> 2);
+#pragma unroll
+        for (int tt = 0; tt < NB / 8; ++tt)
+          if (tt < nt) {
+            double2 v = make_double2(acc[qq][tt][0], acc[qq][tt][1]);
+            *reinterpret_cast<double2*>(Cp + (size_t)ri * CP_PITCH + 8 * tt + 2 * (lane & 3)) = v;
+          }
+      }
+    }
+    __syncthreads();
+    // ---- diagonal block: warp 0, one row per lane, right-looking in registers ----------------------
+    if (warp == 0) {
+      double r[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) r[k] = (lane < nbe && k < nbe && k <= lane) ? Cp[(size_t)lane * CP_PITCH + k] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (j < nbe) {
+          const double cjj = __shfl_sync(0xffffffffu, r[j], j);
+          const double d = fmax(p.epsilon, fabs(cjj));
+          if (lane == 0) {
+            dsm[j] = d;
+            sdsm[j] = sqrt(d);
+            if (d != cjj && J0 + j < n) flags |= (d > 16.0 * p.epsilon) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
+          }
+          const double lij = r[j] / d;
+#pragma unroll
+          for (int k = j + 1; k < NB; ++k) {
+            const double ckj = __shfl_sync(0xffffffffu, r[j], k);
+            r[k] -= lij * ckj;
+          }
+        }
+      }
+      __syncwarp();
+      // L factors for the solve below, and rows J0..J0+nbe-1 of S_new restricted to the block
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (j < nbe) {
+          const double d = dsm[j], sd = sdsm[j];
+          const int row = J0 + j, rb = (row >> 3) << 3;
+          const double l = r[j] / d;
+          if (lane < nbe) {
+            if (lane > j) Ld[lane * (NB + 1) + j] = l;
+            const int col = J0 + lane;
+            if (col >= rb) {
+              double v = (lane == j) ? sd : ((lane > j) ? sd * l : 0.0);
+              Snew[bp_row_off(row, np) + (col - rb)] = v;
+              if (lane > j && col < n) tmax = fmax(tmax, v * v);
+              if (lane == j && !isfinite(v)) flags |= SRUKF_FLAG_NAN;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- rows below the block: C(i,j) -= sum_{k<j} C(i,k) L(j,k), then S_new(j,i) = sd_j C(i,j)/d_j --
+    for (int i = J0 + nbe + tid; i < np; i += NTH) {
+      double r[NB];
+      const double* crow = Cp + (size_t)(i - J0) * CP_PITCH;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) r[k] = (k < nbe) ? crow[k] : 0.0;
+#pragma unroll
+      for (int j = 1; j < NB; ++j) {
+        if (j < nbe) {
+          double a = r[j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) a -= r[k] * Ld[j * (NB + 1) + k];
+          r[j] = a;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (j < nbe) {
+          const int row = J0 + j, rb = (row >> 3) << 3;
+          const double v = sdsm[j] * (r[j] / dsm[j]);
+          Snew[bp_row_off(row, np) + (i - rb)] = v;
+          if (i < n) tmax = fmax(tmax, v * v);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- GMW guard: theta_j^2/beta^2 would have raised a pivot iff max S_new(j,i)^2 > beta^2 -------------
+  gmax = block_max<NTH>(gmax, red);
+  zmax = block_max<NTH>(zmax, red);
+  tmax = block_max<NTH>(tmax, red);
+  double nu = sqrt((double)n * n - 1.0);
+  if (nu < 1.0) nu = 1.0;
+  const double beta2 = fmax(fmax(gmax, zmax / nu), 1e-15);
+  if (tid == 0 && tmax > beta2) flags |= SRUKF_FLAG_GMW_MODIFIED;
+  flags = __reduce_or_sync(0xffffffffu, flags);
+  if (lane == 0 && flags) {
+    atomicOr(q.flags + b, flags);
+    if (flags & SRUKF_FLAG_GMW_MODIFIED) {  // only warp 0 can raise it: one queue entry per filter and step
+      atomicOr(q.flags + b, SRUKF_FLAG_FALLBACK);
+      int slot = atomicAdd(q.worklist, 1);
+      q.worklist[1 + slot] = blockIdx.x;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Reference-order fallback: Gill-Murray-Wright modified Cholesky (SLAM.cpp:2197-2327) of the packed symmetric
+// G (column j of the lower triangle == row j of an upper-packed layout), right-looking, unblocked, in place;
+// S (blocked-packed) receives sqrt(D) L^T.
 // -------------------------------------------------------------------------------------------------
 __device__ void mchol_inplace(const DevParams& p, double* G, double* S, double* wcol, double* red, uint32_t& flags) {
-  const int tid = threadIdx.x, n = p.n;
+  const int tid = threadIdx.x, n = p.n, np = p.np;
   // :2204-2211
   double gmax = -1.0e300, zmax = 0.0;
   for (int j = 0; j < n; ++j) {
@@ -438,7 +784,7 @@ __device__ void mchol_inplace(const DevParams& p, double* G, double* S, double* 
     const double d = fmax(fmax(p.epsilon, fabs(cjj)), th * th / beta2);  // :2279-2285
     if (d != cjj) flags |= (d > 16.0 * p.epsilon) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
     const double sd = sqrt(d);
-    double* srow = S + tri_off(j, n);
+    double* srow = S + bp_idx(j, j, np);
     for (int i = tid; i < len; i += NT) {
       double c = col[i];
       wcol[i] = c;
@@ -456,107 +802,140 @@ __device__ void mchol_inplace(const DevParams& p, double* G, double* S, double* 
   }
 }
 
-// G = S^T S - sum_c U(:,c) U(:,c)^T over columns [c0, c1), packed
-__device__ void form_G(const DevParams& p, const double* __restrict__ S, const double* __restrict__ U, int c0, int c1,
+// G = S^T S - sum_c Ut(c,:)^T Ut(c,:) over c in [c0, c1), upper-packed
+__device__ void form_G(const DevParams& p, const double* __restrict__ S, const double* __restrict__ Ut, int c0, int c1,
                        double* G) {
-  const int n = p.n, L2 = 2 * p.L;
+  const int n = p.n, np = p.np;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int j = warp; j < n; j += NT / 32) {
     double* col = G + tri_off(j, n);
     for (int i = j + lane; i < n; i += 32) {
       double acc = 0.0;
-      for (int k = 0; k <= j; ++k) acc += S[tri_off(k, n) + (j - k)] * S[tri_off(k, n) + (i - k)];
+      for (int k = 0; k <= j; ++k) {
+        const double* row = S + bp_row_off(k, np) - ((k >> 3) << 3);
+        acc += row[j] * row[i];
+      }
       double sub = 0.0;
-      for (int c = c0; c < c1; ++c) sub += U[(size_t)j * L2 + c] * U[(size_t)i * L2 + c];
+      for (int c = c0; c < c1; ++c) sub += Ut[(size_t)c * np + j] * Ut[(size_t)c * np + i];
       col[i - j] = acc - sub;
     }
   }
 }
 
 // -------------------------------------------------------------------------------------------------
-// k_downdate -- GSLCholeskyUpdate, DOWNDATING / NEEDNOT_REORDER (SLAM.cpp:2106-2121,2139-2153).
-//   mode 0: one GMW factorisation of S^T S - U U^T (all matched features at once)
+// k_downdate -- GSLCholeskyUpdate, DOWNDATING / NEEDNOT_REORDER (SLAM.cpp:2106-2121,2139-2153), reference order.
 //   mode 1: the reference's sequence: for every matched feature, for each of its 2 U columns,
 //           re-form S^T S, subtract u u^T, re-factorise.
+//   mode 2: one unblocked GMW factorisation of S^T S - U U^T (all matched features at once).
+//   use_worklist: process only the filters queued by k_update (their result is rebuilt from S_old into S2);
+//   otherwise one CTA per filter of the chunk, in place on S.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mode) {
+__global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mode, int use_worklist) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
-  const int b = q.chunk0 + blockIdx.x;
-  const int n = p.n, L = p.L, L2 = 2 * p.L;
+  const int n = p.n, L = p.L, np = p.np;
   double* wcol = sm;       // n
   double* red = wcol + n;  // 40
-  double* Sg = q.S + (size_t)b * p.ntri;
-  const double* U = q.U + (size_t)blockIdx.x * n * L2;
-  double* G = q.G + (size_t)blockIdx.x * p.ntri;
-  uint32_t flags = 0;
-  int nact = 0;
-  for (int j = 0; j < L; ++j) nact += (q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j]) ? 1 : 0;
-  if (nact == 0) return;  // :2050
-  if (mode == 0) {
-    form_G(p, Sg, U, 0, L2, G);
-    __syncthreads();
-    mchol_inplace(p, G, Sg, wcol, red, flags);
-  } else {
-    for (int j = 0; j < L; ++j) {
-      if (!(q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j])) continue;
-      for (int c = 0; c < 2; ++c) {
-        form_G(p, Sg, U, 2 * j + c, 2 * j + c + 1, G);
-        __syncthreads();
-        mchol_inplace(p, G, Sg, wcol, red, flags);
-        __syncthreads();
+  const int nitems = use_worklist ? q.worklist[0] : (int)gridDim.x;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int rel = use_worklist ? q.worklist[1 + item] : q.rel0 + item;
+    const int b = q.chunk0 + rel;
+    double* Sg = (use_worklist ? q.S2 : q.S) + (size_t)b * p.nbp;
+    const double* Ut = q.U + (size_t)rel * p.Lc * np;
+    double* G = q.G + (size_t)blockIdx.x * p.ntri;
+    uint32_t flags = 0;
+    int nact = 0;
+    for (int j = 0; j < L; ++j) nact += (q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j]) ? 1 : 0;
+    if (nact == 0) continue;  // :2050
+    if (use_worklist) {       // rebuild from the untouched old factor
+      const double* So = q.S + (size_t)b * p.nbp;
+      for (int i = tid; i < p.nbp; i += NT) Sg[i] = So[i];
+      __syncthreads();
+    }
+    if (mode == 2) {
+      form_G(p, Sg, Ut, 0, 2 * L, G);
+      __syncthreads();
+      mchol_inplace(p, G, Sg, wcol, red, flags);
+    } else {
+      for (int j = 0; j < L; ++j) {
+        if (!(q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j])) continue;
+        for (int c = 0; c < 2; ++c) {
+          form_G(p, Sg, Ut, 2 * j + c, 2 * j + c + 1, G);
+          __syncthreads();
+          mchol_inplace(p, G, Sg, wcol, red, flags);
+          __syncthreads();
+        }
       }
     }
+    for (int i = tid; i < n; i += NT)
+      if (!isfinite(Sg[bp_idx(i, i, np)])) flags |= SRUKF_FLAG_NAN;
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if ((tid & 31) == 0 && flags) atomicOr(q.flags + b, flags);
+    __syncthreads();
   }
-  for (int i = tid; i < n; i += NT)
-    if (!isfinite(Sg[tri_off(i, n)])) flags |= SRUKF_FLAG_NAN;
-  flags = __reduce_or_sync(0xffffffffu, flags);
-  if ((tid & 31) == 0 && flags) atomicOr(q.flags + b, flags);
 }
 
 // -------------------------------------------------------------------------------------------------
 // auxiliary kernels
 // -------------------------------------------------------------------------------------------------
-// dense [B][n][n] <-> packed
-__global__ void k_pack(int n, int ntri, const double* __restrict__ dense, double* __restrict__ packed, int to_packed,
-                       double* dense_out) {
+// external formats <-> internal blocked-packed S.  fmt 0: dense [nb][n][n] row-major, fmt 1: upper-packed [nb][ntri]
+__global__ void k_import(int n, int np, int ntri, int nbp, int fmt, const double* __restrict__ ext,
+                         double* __restrict__ bp) {
   const int b = blockIdx.x;
+  double* dst = bp + (size_t)b * nbp;
+  for (int k = 0; k < np; ++k) {
+    const int rb = (k >> 3) << 3;
+    double* row = dst + bp_row_off(k, np);
+    for (int c = rb + threadIdx.x; c < np; c += blockDim.x) {
+      double v = 0.0;
+      if (k < n && c < n && c >= k)
+        v = fmt ? ext[(size_t)b * ntri + tri_off(k, n) + (c - k)] : ext[((size_t)b * n + k) * n + c];
+      else if (k >= n && c == k)
+        v = 1.0;
+      row[c - rb] = v;
+    }
+  }
+}
+__global__ void k_export(int n, int np, int ntri, int nbp, int fmt, const double* __restrict__ bp,
+                         double* __restrict__ ext) {
+  const int b = blockIdx.x;
+  const double* src = bp + (size_t)b * nbp;
   for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-    int i = idx / n, c = idx - i * n;
-    if (to_packed) {
-      if (c >= i) packed[(size_t)b * ntri + tri_off(i, n) + (c - i)] = dense[(size_t)b * n * n + idx];
+    int k = idx / n, c = idx - k * n;
+    if (fmt) {
+      if (c >= k) ext[(size_t)b * ntri + tri_off(k, n) + (c - k)] = src[bp_idx(k, c, np)];
     } else {
-      dense_out[(size_t)b * n * n + idx] = (c >= i) ? packed[(size_t)b * ntri + tri_off(i, n) + (c - i)] : 0.0;
+      ext[(size_t)b * n * n + idx] = (c >= k) ? src[bp_idx(k, c, np)] : 0.0;
     }
   }
 }
 
 // P[r0:r0+nr, r0:r0+nr] of S^T S (m_P_k, SLAM.cpp:2404)
-__global__ void k_cov_block(int n, int ntri, const double* __restrict__ S, int r0, int nr, double* out) {
+__global__ void k_cov_block(int n, int np, int nbp, const double* __restrict__ S, int r0, int nr, double* out) {
   const int b = blockIdx.x;
-  const double* Sg = S + (size_t)b * ntri;
+  const double* Sg = S + (size_t)b * nbp;
   for (int idx = threadIdx.x; idx < nr * nr; idx += blockDim.x) {
     int a = r0 + idx / nr, c = r0 + idx % nr;
     int m = a < c ? a : c;
     double acc = 0.0;
-    for (int k = 0; k <= m; ++k) acc += Sg[tri_off(k, n) + (a - k)] * Sg[tri_off(k, n) + (c - k)];
+    for (int k = 0; k <= m; ++k) acc += Sg[bp_idx(k, a, np)] * Sg[bp_idx(k, c, np)];
     out[(size_t)b * nr * nr + idx] = acc;
   }
 }
 
 // per-filter squared errors and NEES of (rx, ry, rtheta) -> perf[b][4]
-__global__ void __launch_bounds__(128) k_stats(int n, int ntri, const double* __restrict__ x,
+__global__ void __launch_bounds__(128) k_stats(int n, int np, int nbp, const double* __restrict__ x,
                                                const double* __restrict__ S, const double* __restrict__ truth,
                                                double* perf) {
   __shared__ double red[40];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const double* Sg = S + (size_t)b * ntri;
+  const double* Sg = S + (size_t)b * nbp;
   const int ia[3] = {n - 4, n - 3, n - 1};
   double acc[6] = {0, 0, 0, 0, 0, 0};  // P00 P01 P02 P11 P12 P22
   for (int k = tid; k < n; k += 128) {
     double v[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = (ia[c] >= k) ? Sg[tri_off(k, n) + (ia[c] - k)] : 0.0;
+    for (int c = 0; c < 3; ++c) v[c] = (ia[c] >= k) ? Sg[bp_idx(k, ia[c], np)] : 0.0;
     acc[0] += v[0] * v[0]; acc[1] += v[0] * v[1]; acc[2] += v[0] * v[2];
     acc[3] += v[1] * v[1]; acc[4] += v[1] * v[2]; acc[5] += v[2] * v[2];
   }
@@ -603,6 +982,11 @@ __global__ void __launch_bounds__(256) k_stats_reduce(int B, const double* __res
 // -------------------------------------------------------------------------------------------------
 // host-side launchers (called from srukf_capi.cu)
 // -------------------------------------------------------------------------------------------------
+int tile_warps(const DevParams& p) {  // warps per CTA of the DMMA kernels; 0 = unsupported size
+  if (p.np <= 8 * 8 * MAXQ) return 8;
+  if (p.np <= 8 * 16 * MAXQ) return 16;
+  return 0;
+}
 size_t predict_smem_bytes(const DevParams& p) {
   size_t slots = (p.L <= NT) ? (size_t)(NT / p.L) * p.L : (size_t)p.L;
   size_t work = slots * 13;
@@ -610,7 +994,15 @@ size_t predict_smem_bytes(const DevParams& p) {
   if (t4 > work) work = t4;
   return sizeof(double) * ((size_t)p.n + (size_t)p.P * 6 + 2 * (size_t)p.L + 40 + work);
 }
-size_t gain_smem_bytes(const DevParams& p) { return sizeof(double) * (8 * (size_t)p.L) + sizeof(int) * (p.L + 4); }
+size_t gain_smem_bytes(const DevParams& p) {
+  size_t head = sizeof(double) * (8 * (size_t)p.L + (p.L + 3) / 2 + 2) + 16;
+  return head + sizeof(double) * (size_t)NSTAGE * KC * (x_pitch(p.np) + NB + 8);
+}
+size_t update_smem_bytes(const DevParams& p) {
+  size_t ring = (size_t)NSTAGE * KC * x_pitch(p.np);
+  size_t panel = (size_t)p.np * CP_PITCH;
+  return sizeof(double) * (NB * (NB + 1) + 2 * NB + 40 + (ring > panel ? ring : panel)) + 16;
+}
 size_t downdate_smem_bytes(const DevParams& p) { return sizeof(double) * ((size_t)p.n + 40); }
 
 cudaError_t configure_kernels(const DevParams& p) {
@@ -619,7 +1011,11 @@ cudaError_t configure_kernels(const DevParams& p) {
   if ((e = cudaFuncSetAttribute(k_predict<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
   if ((e = cudaFuncSetAttribute(k_predict<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
   if ((e = cudaFuncSetAttribute(k_predict<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-  if ((e = cudaFuncSetAttribute(k_gain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gain_smem_bytes(p)))) return e;
+  int gs = (int)gain_smem_bytes(p), us = (int)update_smem_bytes(p);
+  if ((e = cudaFuncSetAttribute(k_gain<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
+  if ((e = cudaFuncSetAttribute(k_gain<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
+  if ((e = cudaFuncSetAttribute(k_update<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
+  if ((e = cudaFuncSetAttribute(k_update<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
   if ((e = cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)downdate_smem_bytes(p))))
     return e;
   return cudaSuccess;
@@ -633,24 +1029,29 @@ void launch_predict(const DevParams& p, const StepPtrs& q, int nblocks, bool mot
   else k_predict<false, true><<<nblocks, NT, smem, st>>>(p, q, 0);
 }
 void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
-  k_gain<<<nblocks, NT, gain_smem_bytes(p), st>>>(p, q);
+  if (tile_warps(p) == 8) k_gain<8><<<nblocks, 256, gain_smem_bytes(p), st>>>(p, q);
+  else k_gain<16><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q);
 }
-void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, cudaStream_t st) {
-  k_downdate<<<nblocks, NT, downdate_smem_bytes(p), st>>>(p, q, mode);
+void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
+  if (tile_warps(p) == 8) k_update<8><<<nblocks, 256, update_smem_bytes(p), st>>>(p, q);
+  else k_update<16><<<nblocks, 512, update_smem_bytes(p), st>>>(p, q);
 }
-void launch_pack(int B, int n, int ntri, const double* dense, double* packed, cudaStream_t st) {
-  k_pack<<<B, 256, 0, st>>>(n, ntri, dense, packed, 1, nullptr);
+void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, int use_worklist, cudaStream_t st) {
+  k_downdate<<<nblocks, NT, downdate_smem_bytes(p), st>>>(p, q, mode, use_worklist);
 }
-void launch_unpack(int B, int n, int ntri, const double* packed, double* dense, cudaStream_t st) {
-  k_pack<<<B, 256, 0, st>>>(n, ntri, nullptr, const_cast<double*>(packed), 0, dense);
+void launch_import(const DevParams& p, int nb, int fmt, const double* ext, double* bp, cudaStream_t st) {
+  k_import<<<nb, 256, 0, st>>>(p.n, p.np, p.ntri, p.nbp, fmt, ext, bp);
 }
-void launch_cov_block(int B, int n, int ntri, const double* S, int r0, int nr, double* out, cudaStream_t st) {
-  k_cov_block<<<B, 128, 0, st>>>(n, ntri, S, r0, nr, out);
+void launch_export(const DevParams& p, int nb, int fmt, const double* bp, double* ext, cudaStream_t st) {
+  k_export<<<nb, 256, 0, st>>>(p.n, p.np, p.ntri, p.nbp, fmt, bp, ext);
 }
-void launch_stats(int B, int n, int ntri, const double* x, const double* S, const double* truth, double* perf,
+void launch_cov_block(const DevParams& p, const double* S, int r0, int nr, double* out, cudaStream_t st) {
+  k_cov_block<<<p.B, 128, 0, st>>>(p.n, p.np, p.nbp, S, r0, nr, out);
+}
+void launch_stats(const DevParams& p, const double* x, const double* S, const double* truth, double* perf,
                   const uint32_t* flags, double* out, cudaStream_t st) {
-  k_stats<<<B, 128, 0, st>>>(n, ntri, x, S, truth, perf);
-  k_stats_reduce<<<1, 256, 0, st>>>(B, perf, flags, out);
+  k_stats<<<p.B, 128, 0, st>>>(p.n, p.np, p.nbp, x, S, truth, perf);
+  k_stats_reduce<<<1, 256, 0, st>>>(p.B, perf, flags, out);
 }
 
 }  // namespace srukf

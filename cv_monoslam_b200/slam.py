@@ -166,8 +166,3 @@ class CSLAMBatch:
     def set_state_dev(self, b0: int, nb: int, d_x: int | None, d_S_packed: int | None):
         """Device-to-device load of filters [b0, b0+nb) (integer device addresses)."""
         capi.check(self._lib.srukf_set_state_dev(self._h, b0, nb, d_x, d_S_packed))
-
-    def state_dev(self):
-        dx, dS = C.c_void_p(), C.c_void_p()
-        capi.check(self._lib.srukf_state_dev(self._h, C.byref(dx), C.byref(dS)))
-        return dx.value, dS.value

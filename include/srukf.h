@@ -39,6 +39,7 @@ extern "C" {
 #define SRUKF_FLAG_GMW_MODIFIED 4u   /* GMW pivot modified beyond the floor: one-shot downdate not proven equal */
 #define SRUKF_FLAG_OUT_OF_VIEW 8u    /* some sigma-point projection left the image and was zeroed (SLAM.cpp:3341-3345) */
 #define SRUKF_FLAG_INVISIBLE 16u     /* some feature had a zero predicted pixel (SLAM.cpp:1727) */
+#define SRUKF_FLAG_FALLBACK 32u      /* the fused update was redone in reference order (sequential GMW) for this filter */
 
 /* Replaces the scalar members CSLAM::cam_*, a1..a4, m_sigmaMeasure, m_weightType, m_sample.Alpha/Beta,
  * EPSILON, imageWidth/imageHeight (SLAM.h:148,203-204,206,240,261,293-301; defaults SLAM.cpp:164-343). */
@@ -51,8 +52,10 @@ typedef struct SrukfParams {
   double alpha, beta;    /* m_sample.Alpha / Beta (SLAM.cpp:263-264), weight type 1 only */
   double epsilon;        /* EPSILON (SLAM.cpp:52) */
   int32_t newton_iters;  /* cap of the distortion Newton loop (SLAM.cpp:3186: 100); exits early once converged */
-  int32_t downdate_mode; /* 0 = one-shot GMW of S^T S - U U^T with device-side guard (default);
-                            1 = sequential per-column GMW exactly as SLAM.cpp:2116-2153 */
+  int32_t downdate_mode; /* 0 = fused blocked GMW of S^T S - U U^T on the FP64 tensor pipe, with a device-side guard
+                                that re-runs flagged filters in reference order (default);
+                            1 = sequential per-column GMW exactly as SLAM.cpp:2116-2153 for every filter;
+                            2 = one unblocked GMW of S^T S - U U^T for every filter */
 } SrukfParams;
 
 typedef struct srukf_handle srukf_t;
@@ -85,8 +88,8 @@ int srukf_step(srukf_t *h, const double *u, const double *z, const uint8_t *matc
 
 /* device-pointer variants (inputs already resident in HBM; asynchronous on the handle's stream) */
 int srukf_step_dev(srukf_t *h, const double *d_u, const double *d_z, const uint8_t *d_matched);
-int srukf_state_dev(srukf_t *h, double **d_x, double **d_S_packed);
-/* device-to-device load of filters [b0, b0+nb): d_x [nb][n], d_S_packed [nb][n(n+1)/2] (either may be NULL) */
+/* device-to-device load of filters [b0, b0+nb): d_x [nb][n], d_S_packed [nb][n(n+1)/2] (either may be NULL).
+ * (The library keeps S in its own blocked layout in HBM; all exchanged formats are the ones of this header.) */
 int srukf_set_state_dev(srukf_t *h, int b0, int nb, const double *d_x, const double *d_S_packed);
 
 /* m_P_k block (SLAM.cpp:2404): P[r0:r0+nr, r0:r0+nr] of S^T S per filter, out [B][nr][nr]. */
@@ -105,7 +108,7 @@ int srukf_stream(srukf_t *h, uint64_t *stream);
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 int srukf_launch_count(srukf_t *h, uint64_t *count);
 /* Optional per-kernel timing with CUDA events on the handle's stream (bench.py's roofline leg).
- * ms[3] = cumulative milliseconds of {k_predict, k_gain, k_downdate} launches, launches[3] their counts,
+ * ms[3] = cumulative milliseconds of {k_predict, k_gain, k_update (+ fallback)} launches, launches[3] their counts,
  * both since profiling was last switched on.  srukf_get_kernel_times synchronises the stream. */
 int srukf_set_profiling(srukf_t *h, int on);
 int srukf_get_kernel_times(srukf_t *h, double *ms3, uint64_t *launches3);
