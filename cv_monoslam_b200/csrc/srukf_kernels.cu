@@ -320,102 +320,199 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
 }
 
 // -------------------------------------------------------------------------------------------------
-// Shared tiling constants of the DMMA kernels.
+// Shared tiling constants and the K-chunk pipeline of the DMMA kernels.
 //   The CTA's warps own 8-row strips of the output (strip s -> warp s % NW, slot s / NW); a strip times
-//   NB columns is NB/8 DMMA tiles.  K is streamed in chunks of KC rows through a cp.async ring in smem.
+//   NB columns is NB/8 DMMA tiles.  K is streamed in chunks of KC rows: thread 0 issues one 1-D TMA bulk copy
+//   per row into a ring of NSTAGE stages; "full" mbarriers carry the byte counts, "empty" mbarriers (one
+//   arrival per warp) hand stages back.  No __syncthreads inside a K loop.
 // -------------------------------------------------------------------------------------------------
 constexpr int NB = 32;      // panel width (columns per contraction pass)
 constexpr int KC = 8;       // K rows per pipeline stage
-constexpr int NSTAGE = 4;   // cp.async ring depth
+constexpr int NSTAGE = 4;   // ring depth
 constexpr int MAXQ = 5;     // strips per warp: np <= 8 * NW * MAXQ
 constexpr int CP_PITCH = NB + 2;
 
 __host__ __device__ __forceinline__ int x_pitch(int R) { return ((R + 15) & ~15) + 8; }  // == 8 mod 16: conflict-free frags
+__host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-// one KC-row chunk: NT threads copy rows [0,KC) x columns [0,R) (doubles) with 16-byte cp.async.
-// src_row(kk) gives the global pointer of column 0 of row kk; columns < zero_below are zero-filled.
-template <int NTHREADS, typename RowFn>
-__device__ __forceinline__ void load_chunk(double* dst, int pitch, int R, int zero_below, RowFn src_row) {
-  const int half = R >> 1;
-  for (int p = threadIdx.x; p < KC * half; p += NTHREADS) {
-    int kk = p / half, c2 = p - kk * half;
-    int col = 2 * c2;
-    const double* src = src_row(kk);
-    bool valid = col >= zero_below;
-    cp_async16(dst + kk * pitch + col, valid ? (const void*)(src + col) : (const void*)src, valid ? 16 : 0);
+struct Ring {
+  uint64_t* full;    // [NSTAGE]
+  uint64_t* empty;   // [NSTAGE]
+  uint32_t produced; // chunks issued so far (meaningful in thread 0 only)
+  uint32_t consumed; // chunks consumed so far by this warp
+};
+
+template <int NW>
+__device__ __forceinline__ void ring_init(Ring& r, uint64_t* bars) {
+  r.full = bars;
+  r.empty = bars + NSTAGE;
+  r.produced = 0;
+  r.consumed = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(r.full + i, 1);
+      mbar_init(r.empty + i, NW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
+// thread 0: claim the next stage (waits until every warp released its previous occupant)
+__device__ __forceinline__ int ring_acquire(Ring& r, uint32_t bytes) {
+  const uint32_t g = r.produced++;
+  const int st = g % NSTAGE;
+  const uint32_t use = g / NSTAGE;
+  if (use > 0) mbar_wait(r.empty + st, (use - 1) & 1);
+  mbar_expect_tx(r.full + st, bytes);
+  return st;
+}
+// all threads of a warp: wait for the next chunk, returns its stage
+__device__ __forceinline__ int ring_wait(Ring& r) {
+  const uint32_t g = r.consumed;
+  const int st = g % NSTAGE;
+  mbar_wait(r.full + st, (g / NSTAGE) & 1);
+  return st;
+}
+__device__ __forceinline__ void ring_release(Ring& r) {
+  const int st = r.consumed % NSTAGE;
+  r.consumed++;
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(r.empty + st);
+}
+
+// DMMA over one KC-row chunk: strips slots [QLO, QHI) of this warp x NTT column tiles.
+//   arow: chunk base of the A operand (K-major, strip s at column 8*s - acol0), brow: of the B operand.
+template <int NW, int QLO, int QHI, int NTT>
+__device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const double* arow, int apitch, int acol0,
+                                          const double* brow, int bpitch, int lane, int warp) {
+#pragma unroll
+  for (int ks = 0; ks < KC / 4; ++ks) {
+    const int kk = 4 * ks + (lane & 3);
+    const double* ar = arow + kk * apitch + (lane >> 2) - acol0;
+    const double* br = brow + kk * bpitch + (lane >> 2);
+    double bf[NTT];
+#pragma unroll
+    for (int tt = 0; tt < NTT; ++tt) bf[tt] = br[8 * tt];
+#pragma unroll
+    for (int q = QLO; q < QHI; ++q) {
+      const double a = ar[8 * (warp + NW * q)];
+#pragma unroll
+      for (int tt = 0; tt < NTT; ++tt) dmma(acc[q][tt][0], acc[q][tt][1], a, bf[tt]);
+    }
+  }
+}
+// runtime (qlo, qhi) -> compile-time instantiation (warp-uniform switch)
+template <int NW, int NTT>
+__device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int qlo, int qhi, const double* arow,
+                                             int apitch, int acol0, const double* brow, int bpitch, int lane, int warp) {
+#define SRUKF_CASE(LO, HI) \
+  case LO * 8 + HI: mma_chunk<NW, LO, HI, NTT>(acc, arow, apitch, acol0, brow, bpitch, lane, warp); break;
+  switch (qlo * 8 + qhi) {
+    SRUKF_CASE(0, 1) SRUKF_CASE(0, 2) SRUKF_CASE(0, 3) SRUKF_CASE(0, 4) SRUKF_CASE(0, 5)
+    SRUKF_CASE(1, 2) SRUKF_CASE(1, 3) SRUKF_CASE(1, 4) SRUKF_CASE(1, 5)
+    SRUKF_CASE(2, 3) SRUKF_CASE(2, 4) SRUKF_CASE(2, 5)
+    SRUKF_CASE(3, 4) SRUKF_CASE(3, 5)
+    SRUKF_CASE(4, 5)
+    default: break;
+  }
+#undef SRUKF_CASE
+}
+// fully predicated variant for the few irregular chunks (diagonal-block rows, narrow last panel):
+// strips rs >= rs_min, tiles tt in [tt_min, nt)
+template <int NW>
+__device__ __forceinline__ void mma_chunk_pred(double (&acc)[MAXQ][NB / 8][2], const double* arow, int pitch, int nstrip,
+                                               int rs_min, int tt_min, int nt, int lane, int warp) {
+#pragma unroll
+  for (int ks = 0; ks < KC / 4; ++ks) {
+    const double* row = arow + (4 * ks + (lane & 3)) * pitch + (lane >> 2);
+    double bf[NB / 8];
+#pragma unroll
+    for (int tt = 0; tt < NB / 8; ++tt) bf[tt] = (tt >= tt_min && tt < nt) ? row[8 * tt] : 0.0;
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) {
+      const int rs = warp + NW * q;
+      if (rs >= rs_min && rs < nstrip) {
+        const double a = row[8 * rs];
+#pragma unroll
+        for (int tt = 0; tt < NB / 8; ++tt)
+          if (tt >= tt_min && tt < nt) dmma(acc[q][tt][0], acc[q][tt][1], a, bf[tt]);
+      }
+    }
   }
 }
 
 // -------------------------------------------------------------------------------------------------
 // k_gain -- KalmanUpdate gain part (SLAM.cpp:2066-2080) for all matched features at once.
-//   U0_f = S_ff^T V with V = wi*gamma*dZ*blockdiag(si^-1)   (calculateOneFeatureCrossCovariance :2020-2038
-//          restricted to the feature rows, where sigma_i - x = +-gamma*S[i,:]; U = Ki*si^T = Pxy*si^-1)
-//   U0_r = Pxy_r si^-1 for the 4 robot rows
-//   then feature by feature (:2079): U_j = U0_j - dx (c_j^T si_j^-1);  dx += U_j (si_j^-T (z_j - hbar_j))
+//   U_f = S_ff^T (wi*gamma*dZ) si^-1   (calculateOneFeatureCrossCovariance :2020-2038 restricted to the feature
+//          rows, where sigma_i - x = +-gamma*S[i,:]; U = Ki*si^T = Pxy*si^-1; the 2x2 si^-1 acts on column pairs
+//          and is applied to the accumulators in the epilogue)
+//   U_r = Pxy_r si^-1 for the 4 robot rows
+//   x  += sum_j U_j si_j^-T (z_j - hbar_j)                                                         (:2079)
+// :2030 subtracts the *already updated* x, which couples feature j to the shifts of features < j through
+// sum_i w_i (z_i - hbar_j); that sum vanishes identically when wc0 == wm0 (weight types 0 and 2) and is kept,
+// as a feature-sequential pass, only for weight type 1.
 // The triangular product runs on the FP64 tensor pipe: output strips of 8 state rows x 32 measurement
 // columns, K = the 8-row blocks of S (one contiguous run each in the blocked-packed layout).
 // -------------------------------------------------------------------------------------------------
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
-  extern __shared__ __align__(16) double sm[];
+  constexpr int pitchB = NB + 8;
+  extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = q.chunk0 + blockIdx.x;
   const int n = p.n, nf = p.nf, L = p.L, L2 = 2 * p.L, np = p.np, Lc = p.Lc;
   const int pitchA = x_pitch(np);
-  constexpr int pitchB = NB + 8;
-  double* sii = sm;                 // L x 4
-  double* gv = sii + 4 * L;         // L x 2  si^-T (z - hbar)
-  double* ct = gv + 2 * L;          // L x 2  c^T si^-1
-  int* act = (int*)(ct + 2 * L);    // L (+ count), padded to an even number of ints
+  size_t off = 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * NSTAGE * sizeof(uint64_t));
+  double* sii = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 4 * (Lc / 2);   // per column pair
+  double* gv = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 2 * (Lc / 2);    // si^-T (z - hbar)
+  double* ct = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 2 * (Lc / 2);    // c^T si^-1
+  int* act = reinterpret_cast<int*>(smraw + off); off = align16(off + sizeof(int) * (L + 1));
+  double* Xs = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NSTAGE * KC * pitchA;
+  double* Bs = reinterpret_cast<double*>(smraw + off);
   int* nact = act + L;
-  double* Xs = ct + 2 * L + ((L + 2 + 1) / 2);   // NSTAGE x KC x pitchA
-  Xs = (double*)(((uintptr_t)Xs + 15) & ~(uintptr_t)15);
-  double* Bs = Xs + (size_t)NSTAGE * KC * pitchA;  // NSTAGE x KC x pitchB
   const double* Sg = q.S + (size_t)b * p.nbp;
-  double* V = q.dZ + (size_t)blockIdx.x * np * Lc;
+  const double* dZ = q.dZ + (size_t)blockIdx.x * np * Lc;
   double* Ut = q.U + (size_t)blockIdx.x * Lc * np;
   if (tid == 0) *nact = 0;
   __syncthreads();
-  for (int j = tid; j < L; j += NTH) {
-    const double* s = q.si + ((size_t)b * L + j) * 4;
-    const bool a = q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j];
-    // si.inv(), :2077 (2x2 closed form)
-    double det = s[0] * s[3] - s[1] * s[2];
-    double i00 = 0, i01 = 0, i10 = 0, i11 = 0;
-    bool ok = a && (det != 0.0);
-    if (ok) {
-      double d = 1.0 / det;
-      i00 = s[3] * d; i01 = -s[1] * d; i10 = -s[2] * d; i11 = s[0] * d;
+  for (int j = tid; j < Lc / 2; j += NTH) {
+    double i00 = 0, i01 = 0, i10 = 0, i11 = 0, in0 = 0, in1 = 0, c0 = 0, c1 = 0;
+    if (j < L) {
+      const double* s = q.si + ((size_t)b * L + j) * 4;
+      const bool a = q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j];
+      // si.inv(), :2077 (2x2 closed form)
+      double det = s[0] * s[3] - s[1] * s[2];
+      bool ok = a && (det != 0.0);
+      if (ok) {
+        double d = 1.0 / det;
+        i00 = s[3] * d; i01 = -s[1] * d; i10 = -s[2] * d; i11 = s[0] * d;
+        in0 = q.z[((size_t)b * L + j) * 2] - q.hbar[(size_t)b * L2 + 2 * j];
+        in1 = q.z[((size_t)b * L + j) * 2 + 1] - q.hbar[(size_t)b * L2 + 2 * j + 1];
+        c0 = q.cshift[(size_t)b * L2 + 2 * j];
+        c1 = q.cshift[(size_t)b * L2 + 2 * j + 1];
+        atomicAdd(nact, 1);
+      }
+      act[j] = ok ? 1 : 0;
     }
     sii[4 * j] = i00; sii[4 * j + 1] = i01; sii[4 * j + 2] = i10; sii[4 * j + 3] = i11;
-    double in0 = 0, in1 = 0;
-    if (ok) {
-      in0 = q.z[((size_t)b * L + j) * 2] - q.hbar[(size_t)b * L2 + 2 * j];
-      in1 = q.z[((size_t)b * L + j) * 2 + 1] - q.hbar[(size_t)b * L2 + 2 * j + 1];
-    }
     gv[2 * j] = i00 * in0 + i10 * in1;
     gv[2 * j + 1] = i01 * in0 + i11 * in1;
-    double c0 = q.cshift[(size_t)b * L2 + 2 * j], c1 = q.cshift[(size_t)b * L2 + 2 * j + 1];
     ct[2 * j] = c0 * i00 + c1 * i10;
     ct[2 * j + 1] = c0 * i01 + c1 * i11;
-    act[j] = ok ? 1 : 0;
-    if (ok) atomicAdd(nact, 1);
   }
-  __syncthreads();
+  Ring ring;
+  ring_init<NW>(ring, bars);
   if (*nact == 0) return;  // KalmanUpdate returns early, :2050 (k_update copies S through)
-  // V = wi*gamma * dZ * blockdiag(sii) in place (rows >= nf and columns >= 2L are zero by construction)
+  const bool seq_shift = (p.wc0 != p.wm0);
   const double wg = p.wi * p.gamma;
-  for (int i = tid; i < nf * L; i += NTH) {
-    int k = i / L, j = i - k * L;
-    double* d = V + (size_t)k * Lc + 2 * j;
-    double d0 = d[0], d1 = d[1];
-    d[0] = wg * (d0 * sii[4 * j] + d1 * sii[4 * j + 2]);
-    d[1] = wg * (d0 * sii[4 * j + 1] + d1 * sii[4 * j + 3]);
-  }
-  __syncthreads();
-  // ---- U0_f = S_ff^T V on DMMA, 32 measurement columns per pass ---------------------------------
-  const int nblk = np / 8;  // 8-row blocks of S == K chunks == output strips
+  const int nblk = np / 8;                            // 8-row blocks of S == K chunks == output strips
+  const int nq_w = (nblk > warp) ? (nblk - warp - 1) / NW + 1 : 0;
+  double dxp[MAXQ];
+#pragma unroll
+  for (int qq = 0; qq < MAXQ; ++qq) dxp[qq] = 0.0;
+
   for (int cg = 0; cg < Lc; cg += NB) {
     const int ncol = (Lc - cg < NB) ? (Lc - cg) : NB;
     const int nt = ncol / 8;
@@ -424,48 +521,37 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
     for (int qq = 0; qq < MAXQ; ++qq)
 #pragma unroll
       for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
-    auto issue = [&](int t) {
-      if (t < nblk) {
-        const int k0 = 8 * t, R = np - k0, st = t % NSTAGE;
-        const double* src = Sg + bp_block_off(t, np);
-        load_chunk<NTH>(Xs + (size_t)st * KC * pitchA, pitchA, R, 0, [&](int kk) { return src + (size_t)kk * R; });
-        const double* vsrc = V + (size_t)k0 * Lc + cg;
-        double* bd = Bs + (size_t)st * KC * pitchB;
-        for (int pp = tid; pp < KC * (ncol / 2); pp += NTH) {
-          int kk = pp / (ncol / 2), c2 = pp - kk * (ncol / 2);
-          cp_async16(bd + kk * pitchB + 2 * c2, vsrc + (size_t)kk * Lc + 2 * c2, 16);
-        }
+    // only blocks whose rows can touch a feature row matter: S rows >= nf (robot) have zero dZ
+    const int nchunk = (nf + 7) / 8;
+    auto produce = [&](int t) {  // thread 0
+      const int R = np - 8 * t;
+      const int st = ring_acquire(ring, (uint32_t)(KC * (R + ncol) * sizeof(double)));
+      const double* src = Sg + bp_block_off(t, np);
+      double* xd = Xs + (size_t)st * KC * pitchA;
+      double* bd = Bs + (size_t)st * KC * pitchB;
+      const double* vsrc = dZ + (size_t)(8 * t) * Lc + cg;
+#pragma unroll
+      for (int kk = 0; kk < KC; ++kk) {
+        tma_load_1d(xd + kk * pitchA, src + (size_t)kk * R, (uint32_t)(R * sizeof(double)), ring.full + st);
+        tma_load_1d(bd + kk * pitchB, vsrc + (size_t)kk * Lc, (uint32_t)(ncol * sizeof(double)), ring.full + st);
       }
-      cp_async_commit();
     };
-    for (int t = 0; t < NSTAGE - 1; ++t) issue(t);
-    for (int t = 0; t < nblk; ++t) {
-      cp_async_wait<NSTAGE - 2>();
-      __syncthreads();
-      issue(t + NSTAGE - 1);
-      const double* xa = Xs + (size_t)(t % NSTAGE) * KC * pitchA;  // column 0 == state row 8t
-      const double* xb = Bs + (size_t)(t % NSTAGE) * KC * pitchB;
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const int kk = 4 * ks + (lane & 3);
-        double bf[NB / 8];
-#pragma unroll
-        for (int tt = 0; tt < NB / 8; ++tt) bf[tt] = (tt < nt) ? xb[kk * pitchB + 8 * tt + (lane >> 2)] : 0.0;
-#pragma unroll
-        for (int qq = 0; qq < MAXQ; ++qq) {
-          const int s = warp + NW * qq;  // output strip (state rows 8s..8s+7); receives S rows k <= its own
-          if (s >= t && s < nblk) {
-            double a = xa[kk * pitchA + 8 * (s - t) + (lane >> 2)];
-#pragma unroll
-            for (int tt = 0; tt < NB / 8; ++tt)
-              if (tt < nt) dmma(acc[qq][tt][0], acc[qq][tt][1], a, bf[tt]);
-          }
-        }
-      }
+    if (tid == 0)
+      for (int t = 0; t < NSTAGE - 1 && t < nchunk; ++t) produce(t);
+    for (int t = 0; t < nchunk; ++t) {
+      if (tid == 0 && t + NSTAGE - 1 < nchunk) produce(t + NSTAGE - 1);
+      const int st = ring_wait(ring);
+      const double* xa = Xs + (size_t)st * KC * pitchA;  // column 0 == state row 8t
+      const double* xb = Bs + (size_t)st * KC * pitchB;
+      // output strip s = warp + NW*q receives S rows k <= its own: active slots are q >= qlo
+      const int qlo = (t > warp) ? (t - warp + NW - 1) / NW : 0;
+      if (nt == NB / 8) mma_chunk_rt<NW, NB / 8>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, lane, warp);
+      else if (nt == 1) mma_chunk_rt<NW, 1>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, lane, warp);
+      else if (nt == 2) mma_chunk_rt<NW, 2>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, lane, warp);
+      else mma_chunk_rt<NW, 3>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, lane, warp);
+      ring_release(ring);
     }
-    cp_async_wait<0>();
-    __syncthreads();
-    // epilogue: Ut[c][f] (transposed store), feature rows only
+    // epilogue: apply wi*gamma and si^-1 to each column pair, store Ut[c][f] (transposed), accumulate the shift
 #pragma unroll
     for (int qq = 0; qq < MAXQ; ++qq) {
       const int s = warp + NW * qq;
@@ -473,49 +559,84 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
         const int f = 8 * s + (lane >> 2);
 #pragma unroll
         for (int tt = 0; tt < NB / 8; ++tt) {
-          if (tt < nt && f < nf) {
+          if (tt < nt) {
             const int c = cg + 8 * tt + 2 * (lane & 3);
-            Ut[(size_t)c * np + f] = acc[qq][tt][0];
-            Ut[(size_t)(c + 1) * np + f] = acc[qq][tt][1];
+            const int j = c >> 1;
+            const double a0 = wg * acc[qq][tt][0], a1 = wg * acc[qq][tt][1];
+            const double u0 = a0 * sii[4 * j] + a1 * sii[4 * j + 2];
+            const double u1 = a0 * sii[4 * j + 1] + a1 * sii[4 * j + 3];
+            if (f < nf) {
+              Ut[(size_t)c * np + f] = u0;
+              Ut[(size_t)(c + 1) * np + f] = u1;
+            }
+            dxp[qq] += u0 * gv[2 * j] + u1 * gv[2 * j + 1];
           }
         }
       }
     }
   }
-  // U0_r = Pxy_r sii ; padding rows/columns of Ut are zero
-  for (int i = tid; i < 4 * L; i += NTH) {
-    int r = i / L, j = i - r * L;
-    const double* pr = q.pxyr + (size_t)b * 8 * L + (size_t)r * L2 + 2 * j;
-    Ut[(size_t)(2 * j) * np + nf + r] = pr[0] * sii[4 * j] + pr[1] * sii[4 * j + 2];
-    Ut[(size_t)(2 * j + 1) * np + nf + r] = pr[0] * sii[4 * j + 1] + pr[1] * sii[4 * j + 3];
+  double* xg = q.x + (size_t)b * n;
+  uint32_t flags = 0;
+  if (!seq_shift) {
+    // x_f += U_f g  (sum over the 4 lanes that share a state row)
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq) {
+      double v = dxp[qq];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      const int f = 8 * (warp + NW * qq) + (lane >> 2);
+      if ((lane & 3) == 0 && f < nf) {
+        const double xn = xg[f] + v;
+        xg[f] = xn;
+        if (!isfinite(xn)) flags |= SRUKF_FLAG_NAN;
+      }
+    }
+  }
+  // robot rows: U_r = Pxy_r sii ; padding rows/columns of Ut are zero
+  for (int i = tid; i < 4 * (Lc / 2); i += NTH) {
+    int r = i / (Lc / 2), j = i - r * (Lc / 2);
+    double u0 = 0.0, u1 = 0.0;
+    if (j < L) {
+      const double* pr = q.pxyr + (size_t)b * 8 * L + (size_t)r * L2 + 2 * j;
+      u0 = pr[0] * sii[4 * j] + pr[1] * sii[4 * j + 2];
+      u1 = pr[0] * sii[4 * j + 1] + pr[1] * sii[4 * j + 3];
+    }
+    Ut[(size_t)(2 * j) * np + nf + r] = u0;
+    Ut[(size_t)(2 * j + 1) * np + nf + r] = u1;
   }
   for (int i = tid; i < Lc * (np - n); i += NTH) {
     int c = i / (np - n), f = n + (i - c * (np - n));
     Ut[(size_t)c * np + f] = 0.0;
   }
-  for (int i = tid; i < (Lc - L2) * 4; i += NTH) {
-    int c = L2 + i / 4, f = nf + (i & 3);
-    Ut[(size_t)c * np + f] = 0.0;
-  }
   __syncthreads();
-  // feature-sequential state update, one state row per thread
-  double* xg = q.x + (size_t)b * n;
-  uint32_t flags = 0;
-  for (int r = tid; r < n; r += NTH) {
-    double dx = 0.0;
-    for (int j = 0; j < L; ++j) {
-      double* u0p = Ut + (size_t)(2 * j) * np + r;
-      double* u1p = u0p + np;
-      if (!act[j]) { *u0p = 0.0; *u1p = 0.0; continue; }
-      double u0 = *u0p - dx * ct[2 * j];
-      double u1 = *u1p - dx * ct[2 * j + 1];
-      *u0p = u0;
-      *u1p = u1;
-      dx += u0 * gv[2 * j] + u1 * gv[2 * j + 1];
+  if (!seq_shift) {
+    if (tid < 4) {
+      double dx = 0.0;
+      for (int j = 0; j < L; ++j)
+        dx += Ut[(size_t)(2 * j) * np + nf + tid] * gv[2 * j] + Ut[(size_t)(2 * j + 1) * np + nf + tid] * gv[2 * j + 1];
+      const double xn = xg[nf + tid] + dx;
+      xg[nf + tid] = xn;
+      if (!isfinite(xn)) flags |= SRUKF_FLAG_NAN;
     }
-    double xn = xg[r] + dx;
-    xg[r] = xn;
-    if (!isfinite(xn)) flags |= SRUKF_FLAG_NAN;
+  } else {
+    // weight type 1: feature-sequential pass, one state row per thread:
+    //   U_j = U0_j - dx (c_j^T si_j^-1);  dx += U_j (si_j^-T (z_j - hbar_j))
+    for (int r = tid; r < n; r += NTH) {
+      double dx = 0.0;
+      for (int j = 0; j < L; ++j) {
+        double* u0p = Ut + (size_t)(2 * j) * np + r;
+        double* u1p = u0p + np;
+        if (!act[j]) continue;
+        double u0 = *u0p - dx * ct[2 * j];
+        double u1 = *u1p - dx * ct[2 * j + 1];
+        *u0p = u0;
+        *u1p = u1;
+        dx += u0 * gv[2 * j] + u1 * gv[2 * j + 1];
+      }
+      double xn = xg[r] + dx;
+      xg[r] = xn;
+      if (!isfinite(xn)) flags |= SRUKF_FLAG_NAN;
+    }
   }
   flags = __reduce_or_sync(0xffffffffu, flags);
   if (lane == 0 && flags) atomicOr(q.flags + b, flags);
@@ -528,7 +649,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
 // Left-looking, 32 columns per panel; G is never formed.  For panel columns J = [J0, J0+32) and rows i >= J0
 //     C(i, J) = sum_{k < J0+32} S_old(k,i) S_old(k,J) - sum_c Ut(c,i) Ut(c,J) - sum_{k < J0} S_new(k,i) S_new(k,J)
 // is one DMMA contraction over K = [S_old rows | Ut rows | S_new rows]; all three are K-major in HBM, so the
-// same smem chunk feeds the A fragment (rows i) and the B fragment (its first 32 columns).  Then
+// same smem chunk feeds the A fragment (rows i) and the B fragment (its first 32 columns).  The two negative
+// sources are folded in by flipping the sign of the accumulators between sources.  Then
 //   - warp 0 factorises the 32x32 diagonal block in registers with the GMW pivot rule
 //       d_j = max(EPSILON, |c_jj|)                      (:2279-2285; theta_j^2/beta^2 handled below)
 //   - every thread solves one row below the block against it (C(i,j) = G(i,j) - sum_k L(j,k) C(i,k), :2253)
@@ -541,19 +663,20 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = q.chunk0 + blockIdx.x;
   const int n = p.n, L = p.L, np = p.np, Lc = p.Lc;
   const double* Sold = q.S + (size_t)b * p.nbp;
   double* Snew = q.S2 + (size_t)b * p.nbp;
   const double* Ut = q.U + (size_t)blockIdx.x * Lc * np;
-  double* Ld = sm;                       // NB x (NB+1)
-  double* dsm = Ld + NB * (NB + 1);      // NB   pivots d_j
-  double* sdsm = dsm + NB;               // NB   sqrt(d_j)
-  double* red = sdsm + NB;               // 40
-  double* Xs = red + 40;                 // ring: NSTAGE x KC x pitch, aliased by the panel Cp[R][CP_PITCH]
-  Xs = (double*)(((uintptr_t)Xs + 15) & ~(uintptr_t)15);
+  size_t off = 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * NSTAGE * sizeof(uint64_t));
+  double* Ld = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB * (NB + 1);
+  double* dsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;    // pivots d_j
+  double* sdsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;   // sqrt(d_j)
+  double* red = reinterpret_cast<double*>(smraw + off); off = align16(off + sizeof(double) * 40);
+  double* Xs = reinterpret_cast<double*>(smraw + off);  // ring: NSTAGE x KC x pitch, aliased by the panel Cp
   double* Cp = Xs;
   uint32_t flags = 0;
 
@@ -563,6 +686,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     for (int i = tid; i < p.nbp; i += NTH) Snew[i] = Sold[i];
     return;
   }
+  Ring ring;
+  ring_init<NW>(ring, bars);
   double gmax = -1.0e300, zmax = 0.0, tmax = 0.0;
 
   for (int J0 = 0; J0 < np; J0 += NB) {
@@ -570,86 +695,96 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     const int R = np - J0;
     const int nt = nbe / 8;
     const int pitch = x_pitch(R);
-    const int nA = (J0 + nbe) / KC, nU = Lc / KC, nC = J0 / KC;
+    const int jb = J0 / 8;
+    const int nA1 = jb + 1;            // S_old chunks whose stored range covers [J0, np)
+    const int nA = jb + nt;            // ... plus the chunks inside the panel's diagonal block
+    const int nU = Lc / KC, nC = jb;
     const int nchunks = nA + nU + nC;
     const int nstrip = R / 8;
+    const int nq_w = (nstrip > warp) ? (nstrip - warp - 1) / NW + 1 : 0;
+    const bool regular = (nt == NB / 8);
     double acc[MAXQ][NB / 8][2];
 #pragma unroll
     for (int qq = 0; qq < MAXQ; ++qq)
 #pragma unroll
       for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
 
-    auto issue = [&](int t) {
-      if (t < nchunks) {
-        double* dst = Xs + (size_t)(t % NSTAGE) * KC * pitch;
-        if (t < nA) {  // S_old rows 8t..8t+7, columns [J0, np); stored from column 8t
-          const int k0 = 8 * t, len = np - k0;
-          const double* src = Sold + bp_block_off(t, np) + (J0 - k0);
-          load_chunk<NTH>(dst, pitch, R, (k0 > J0) ? (k0 - J0) : 0, [&](int kk) { return src + (size_t)kk * len; });
-        } else if (t < nA + nU) {
-          const double* src = Ut + (size_t)(8 * (t - nA)) * np + J0;
-          load_chunk<NTH>(dst, pitch, R, 0, [&](int kk) { return src + (size_t)kk * np; });
-        } else {
-          const int blk = t - nA - nU, k0 = 8 * blk, len = np - k0;
-          const double* src = Snew + bp_block_off(blk, np) + (J0 - k0);
-          load_chunk<NTH>(dst, pitch, R, 0, [&](int kk) { return src + (size_t)kk * len; });
-        }
+    auto produce = [&](int t) {  // thread 0: one bulk copy per K row
+      const double* src;
+      int stride, dcol = 0, len = R;
+      if (t < nA) {              // S_old rows 8t..8t+7 (stored from column 8t)
+        const int k0 = 8 * t;
+        stride = np - k0;
+        if (k0 <= J0) src = Sold + bp_block_off(t, np) + (J0 - k0);
+        else { src = Sold + bp_block_off(t, np); dcol = k0 - J0; len = np - k0; }  // left part is never read
+      } else if (t < nA + nU) {
+        src = Ut + (size_t)(8 * (t - nA)) * np + J0;
+        stride = np;
+      } else {
+        const int blk = t - nA - nU;
+        stride = np - 8 * blk;
+        src = Snew + bp_block_off(blk, np) + (J0 - 8 * blk);
       }
-      cp_async_commit();
+      const int st = ring_acquire(ring, (uint32_t)(KC * len * sizeof(double)));
+      double* dst = Xs + (size_t)st * KC * pitch + dcol;
+#pragma unroll
+      for (int kk = 0; kk < KC; ++kk)
+        tma_load_1d(dst + kk * pitch, src + (size_t)kk * stride, (uint32_t)(len * sizeof(double)), ring.full + st);
     };
-    for (int t = 0; t < NSTAGE - 1; ++t) issue(t);
-    for (int t = 0; t < nchunks; ++t) {
-      cp_async_wait<NSTAGE - 2>();
-      __syncthreads();
-      issue(t + NSTAGE - 1);
-      const double* xs_ = Xs + (size_t)(t % NSTAGE) * KC * pitch;
-      const bool neg = (t >= nA);
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const int kk = 4 * ks + (lane & 3);
-        const double* row = xs_ + kk * pitch + (lane >> 2);
-        double bf[NB / 8];
-#pragma unroll
-        for (int tt = 0; tt < NB / 8; ++tt) bf[tt] = (tt < nt) ? row[8 * tt] : 0.0;
-#pragma unroll
-        for (int qq = 0; qq < MAXQ; ++qq) {
-          const int rs = warp + NW * qq;  // strip relative to the panel: rows J0 + 8rs ..
-          if (rs < nstrip) {
-            double a = row[8 * rs];
-            if (neg) a = -a;
-#pragma unroll
-            for (int tt = 0; tt < NB / 8; ++tt)
-              if (tt < nt && rs >= tt) dmma(acc[qq][tt][0], acc[qq][tt][1], a, bf[tt]);
-          }
+    auto consume = [&](int t0, int t1) {
+      for (int t = t0; t < t1; ++t) {
+        if (tid == 0 && t + NSTAGE - 1 < nchunks) produce(t + NSTAGE - 1);
+        const int st = ring_wait(ring);
+        const double* xs_ = Xs + (size_t)st * KC * pitch;
+        if (t >= nA1 && t < nA) {   // rows inside the diagonal block: only strips/tiles at or right of them
+          const int kq = t - jb;
+          mma_chunk_pred<NW>(acc, xs_, pitch, nstrip, kq, kq, nt, lane, warp);
+        } else if (regular) {
+          mma_chunk_rt<NW, NB / 8>(acc, 0, nq_w, xs_, pitch, 0, xs_, pitch, lane, warp);
+        } else {
+          mma_chunk_pred<NW>(acc, xs_, pitch, nstrip, 0, 0, nt, lane, warp);
         }
+        ring_release(ring);
       }
-      if (t == nA + nU - 1) {  // acc == G(i, J): track max diag / max off-diag for beta^2 (:2204-2205)
+    };
+    auto negate = [&]() {
 #pragma unroll
-        for (int qq = 0; qq < MAXQ; ++qq) {
-          const int rs = warp + NW * qq;
-          if (rs < nstrip) {
-            const int i = J0 + 8 * rs + (lane >> 2);
+      for (int qq = 0; qq < MAXQ; ++qq)
 #pragma unroll
-            for (int tt = 0; tt < NB / 8; ++tt) {
-              if (tt < nt && rs >= tt) {
+        for (int t = 0; t < NB / 8; ++t) { acc[qq][t][0] = -acc[qq][t][0]; acc[qq][t][1] = -acc[qq][t][1]; }
+    };
+    if (tid == 0) {
+      fence_proxy_async();  // the ring aliases the previous panel's Cp (generic-proxy stores)
+      for (int t = 0; t < NSTAGE - 1 && t < nchunks; ++t) produce(t);
+    }
+    consume(0, nA);          // + S_old^T S_old
+    negate();
+    consume(nA, nA + nU);    // acc = -(S^T S - U U^T) = -G(i, J)
+    // track max diag / max off-diag of G for beta^2 (:2204-2205)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int j = J0 + 8 * tt + 2 * (lane & 3) + e;
-                  const double v = acc[qq][tt][e];
-                  if (i < n && j < n) {
-                    if (i == j) gmax = fmax(gmax, v);
-                    else if (i > j) zmax = fmax(zmax, v);
-                  }
-                }
+    for (int qq = 0; qq < MAXQ; ++qq) {
+      const int rs = warp + NW * qq;
+      if (rs < nstrip) {
+        const int i = J0 + 8 * rs + (lane >> 2);
+#pragma unroll
+        for (int tt = 0; tt < NB / 8; ++tt) {
+          if (tt < nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int j = J0 + 8 * tt + 2 * (lane & 3) + e;
+              const double v = -acc[qq][tt][e];
+              if (i < n && j < n) {
+                if (i == j) gmax = fmax(gmax, v);
+                else if (i > j) zmax = fmax(zmax, v);
               }
             }
           }
         }
       }
     }
-    cp_async_wait<0>();
-    __syncthreads();
-    // accumulators -> panel in smem (aliases the ring)
+    consume(nA + nU, nchunks);  // + S_new^T S_new
+    negate();                   // acc = C(i, J)
+    __syncthreads();            // every warp is done with the ring: reuse it as the panel
 #pragma unroll
     for (int qq = 0; qq < MAXQ; ++qq) {
       const int rs = warp + NW * qq;
@@ -734,7 +869,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
         }
       }
     }
-    __syncthreads();
+    fence_proxy_async();  // order this panel's generic-proxy smem/global accesses before the next bulk copies
+    __syncthreads();      // S_new rows of this panel are visible to the next panel's bulk copies; Cp is free
   }
   // ---- GMW guard: theta_j^2/beta^2 would have raised a pivot iff max S_new(j,i)^2 > beta^2 -------------
   gmax = block_max<NTH>(gmax, red);
@@ -995,13 +1131,18 @@ size_t predict_smem_bytes(const DevParams& p) {
   return sizeof(double) * ((size_t)p.n + (size_t)p.P * 6 + 2 * (size_t)p.L + 40 + work);
 }
 size_t gain_smem_bytes(const DevParams& p) {
-  size_t head = sizeof(double) * (8 * (size_t)p.L + (p.L + 3) / 2 + 2) + 16;
-  return head + sizeof(double) * (size_t)NSTAGE * KC * (x_pitch(p.np) + NB + 8);
+  size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
+  off += sizeof(double) * 8 * (p.Lc / 2);
+  off = align16(off + sizeof(int) * (p.L + 1));
+  return off + sizeof(double) * (size_t)NSTAGE * KC * (x_pitch(p.np) + NB + 8);
 }
 size_t update_smem_bytes(const DevParams& p) {
+  size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
+  off += sizeof(double) * (NB * (NB + 1) + 2 * NB);
+  off = align16(off + sizeof(double) * 40);
   size_t ring = (size_t)NSTAGE * KC * x_pitch(p.np);
   size_t panel = (size_t)p.np * CP_PITCH;
-  return sizeof(double) * (NB * (NB + 1) + 2 * NB + 40 + (ring > panel ? ring : panel)) + 16;
+  return off + sizeof(double) * (ring > panel ? ring : panel);
 }
 size_t downdate_smem_bytes(const DevParams& p) { return sizeof(double) * ((size_t)p.n + 40); }
 
