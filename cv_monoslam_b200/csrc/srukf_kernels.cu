@@ -643,6 +643,64 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
 }
 
 // -------------------------------------------------------------------------------------------------
+// GMW-pivoted LDL^T of the panel's nbe x nbe diagonal block by ONE warp: lane i holds row i in registers,
+// column j's pivot is broadcast with a shuffle, d_j = max(EPSILON, |c_jj|) (SLAM.cpp:2279-2285), the row is
+// scaled (L(i,j) = C(i,j)/d_j, :2232) and the remaining columns are updated (:2253) -- a 32-step dependent
+// chain, so everything that is not on the chain (sqrt, flags, stores) is hoisted out of it.
+// Outputs: L (for the solve of the rows below), d, sqrt(d), and rows J0.. of S_new inside the block (:2321).
+// -------------------------------------------------------------------------------------------------
+template <bool FULL>
+__device__ __forceinline__ void diag_block(const double* Cp, double* Ld, double* dsm, double* sdsm, double* Snew,
+                                           int J0, int nbe, int n, int np, double eps, int lane, uint32_t& flags,
+                                           double& tmax) {
+  double r[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+    r[k] = (k <= lane && (FULL || (lane < nbe && k < nbe))) ? Cp[(size_t)lane * CP_PITCH + k] : 0.0;
+  double dmine = 1.0;
+  bool modified = false;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    if (FULL || j < nbe) {
+      const double cjj = __shfl_sync(0xffffffffu, r[j], j);
+      const double d = fmax(eps, fabs(cjj));
+      if (lane == j) { dmine = d; modified = (d != cjj); }
+      const double lij = r[j] / d;
+#pragma unroll
+      for (int k = j + 1; k < NB; ++k) {
+        if (FULL || k < nbe) {
+          const double ckj = __shfl_sync(0xffffffffu, r[j], k);  // C(k,j), still unscaled in lane k
+          r[k] = fma(-lij, ckj, r[k]);
+        }
+      }
+      r[j] = lij;
+    }
+  }
+  const double sd = sqrt(dmine);
+  if (lane < nbe) {
+    dsm[lane] = dmine;
+    sdsm[lane] = sd;
+    if (modified && J0 + lane < n) flags |= (dmine > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
+    if (!isfinite(sd)) flags |= SRUKF_FLAG_NAN;
+  }
+  __syncwarp();
+  const int col = J0 + lane;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    if ((FULL || j < nbe) && lane < nbe) {
+      const double sdj = sdsm[j];
+      const int row = J0 + j, rb = (row >> 3) << 3;
+      if (lane > j) Ld[lane * (NB + 1) + j] = r[j];
+      if (col >= rb) {
+        const double v = (lane == j) ? sdj : ((lane > j) ? sdj * r[j] : 0.0);
+        Snew[bp_row_off(row, np) + (col - rb)] = v;
+        if (lane > j && col < n) tmax = fmax(tmax, v * v);
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // k_update -- GSLCholeskyUpdate (DOWNDATING, NEEDNOT_REORDER; SLAM.cpp:2106-2121,2139-2153) for all matched
 // features at once: S_new = modifiedCholesky(S_old^T S_old - U U^T)  (SLAM.cpp:2197-2327).
 //
@@ -801,47 +859,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     __syncthreads();
     // ---- diagonal block: warp 0, one row per lane, right-looking in registers ----------------------
     if (warp == 0) {
-      double r[NB];
-#pragma unroll
-      for (int k = 0; k < NB; ++k) r[k] = (lane < nbe && k < nbe && k <= lane) ? Cp[(size_t)lane * CP_PITCH + k] : 0.0;
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        if (j < nbe) {
-          const double cjj = __shfl_sync(0xffffffffu, r[j], j);
-          const double d = fmax(p.epsilon, fabs(cjj));
-          if (lane == 0) {
-            dsm[j] = d;
-            sdsm[j] = sqrt(d);
-            if (d != cjj && J0 + j < n) flags |= (d > 16.0 * p.epsilon) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
-          }
-          const double lij = r[j] / d;
-#pragma unroll
-          for (int k = j + 1; k < NB; ++k) {
-            const double ckj = __shfl_sync(0xffffffffu, r[j], k);
-            r[k] -= lij * ckj;
-          }
-        }
-      }
-      __syncwarp();
-      // L factors for the solve below, and rows J0..J0+nbe-1 of S_new restricted to the block
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        if (j < nbe) {
-          const double d = dsm[j], sd = sdsm[j];
-          const int row = J0 + j, rb = (row >> 3) << 3;
-          const double l = r[j] / d;
-          if (lane < nbe) {
-            if (lane > j) Ld[lane * (NB + 1) + j] = l;
-            const int col = J0 + lane;
-            if (col >= rb) {
-              double v = (lane == j) ? sd : ((lane > j) ? sd * l : 0.0);
-              Snew[bp_row_off(row, np) + (col - rb)] = v;
-              if (lane > j && col < n) tmax = fmax(tmax, v * v);
-              if (lane == j && !isfinite(v)) flags |= SRUKF_FLAG_NAN;
-            }
-          }
-        }
-      }
+      if (nbe == NB) diag_block<true>(Cp, Ld, dsm, sdsm, Snew, J0, nbe, n, np, p.epsilon, lane, flags, tmax);
+      else diag_block<false>(Cp, Ld, dsm, sdsm, Snew, J0, nbe, n, np, p.epsilon, lane, flags, tmax);
     }
     __syncthreads();
     // ---- rows below the block: C(i,j) -= sum_{k<j} C(i,k) L(j,k), then S_new(j,i) = sd_j C(i,j)/d_j --
