@@ -330,7 +330,7 @@ constexpr int NB = 32;      // panel width (columns per contraction pass)
 constexpr int KC = 8;       // K rows per pipeline stage
 constexpr int NSTAGE = 4;   // ring depth
 constexpr int MAXQ = 5;     // strips per warp: np <= 8 * NW * MAXQ
-constexpr int CP_PITCH = NB + 2;
+constexpr int CP_PITCH = NB + 1;  // odd pitch: one row per lane/thread is bank-conflict free
 
 __host__ __device__ __forceinline__ int x_pitch(int R) { return ((R + 15) & ~15) + 8; }  // == 8 mod 16: conflict-free frags
 __host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -338,7 +338,7 @@ __host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) &
 struct Ring {
   uint64_t* full;    // [NSTAGE]
   uint64_t* empty;   // [NSTAGE]
-  uint32_t produced; // chunks issued so far (meaningful in thread 0 only)
+  uint32_t produced; // chunks issued so far (meaningful in warp 0 only)
   uint32_t consumed; // chunks consumed so far by this warp
 };
 
@@ -357,13 +357,17 @@ __device__ __forceinline__ void ring_init(Ring& r, uint64_t* bars) {
   }
   __syncthreads();
 }
-// thread 0: claim the next stage (waits until every warp released its previous occupant)
+// warp 0 (converged): claim the next stage.  Lane 0 waits until every warp released the stage's previous occupant
+// and posts the byte count; afterwards the lanes issue the row copies in parallel.
 __device__ __forceinline__ int ring_acquire(Ring& r, uint32_t bytes) {
   const uint32_t g = r.produced++;
   const int st = g % NSTAGE;
   const uint32_t use = g / NSTAGE;
-  if (use > 0) mbar_wait(r.empty + st, (use - 1) & 1);
-  mbar_expect_tx(r.full + st, bytes);
+  if ((threadIdx.x & 31) == 0) {
+    if (use > 0) mbar_wait(r.empty + st, (use - 1) & 1);
+    mbar_expect_tx(r.full + st, bytes);
+  }
+  __syncwarp();
   return st;
 }
 // all threads of a warp: wait for the next chunk, returns its stage
@@ -523,23 +527,22 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
       for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
     // only blocks whose rows can touch a feature row matter: S rows >= nf (robot) have zero dZ
     const int nchunk = (nf + 7) / 8;
-    auto produce = [&](int t) {  // thread 0
+    auto produce = [&](int t) {  // warp 0: lanes 0..7 copy the S rows, lanes 8..15 the dZ rows of the chunk
       const int R = np - 8 * t;
       const int st = ring_acquire(ring, (uint32_t)(KC * (R + ncol) * sizeof(double)));
-      const double* src = Sg + bp_block_off(t, np);
-      double* xd = Xs + (size_t)st * KC * pitchA;
-      double* bd = Bs + (size_t)st * KC * pitchB;
-      const double* vsrc = dZ + (size_t)(8 * t) * Lc + cg;
-#pragma unroll
-      for (int kk = 0; kk < KC; ++kk) {
-        tma_load_1d(xd + kk * pitchA, src + (size_t)kk * R, (uint32_t)(R * sizeof(double)), ring.full + st);
-        tma_load_1d(bd + kk * pitchB, vsrc + (size_t)kk * Lc, (uint32_t)(ncol * sizeof(double)), ring.full + st);
+      if (lane < KC) {
+        const double* src = Sg + bp_block_off(t, np) + (size_t)lane * R;
+        tma_load_1d(Xs + ((size_t)st * KC + lane) * pitchA, src, (uint32_t)(R * sizeof(double)), ring.full + st);
+      } else if (lane < 2 * KC) {
+        const int kk = lane - KC;
+        const double* vsrc = dZ + (size_t)(8 * t + kk) * Lc + cg;
+        tma_load_1d(Bs + ((size_t)st * KC + kk) * pitchB, vsrc, (uint32_t)(ncol * sizeof(double)), ring.full + st);
       }
     };
-    if (tid == 0)
+    if (warp == 0)
       for (int t = 0; t < NSTAGE - 1 && t < nchunk; ++t) produce(t);
     for (int t = 0; t < nchunk; ++t) {
-      if (tid == 0 && t + NSTAGE - 1 < nchunk) produce(t + NSTAGE - 1);
+      if (warp == 0 && t + NSTAGE - 1 < nchunk) produce(t + NSTAGE - 1);
       const int st = ring_wait(ring);
       const double* xa = Xs + (size_t)st * KC * pitchA;  // column 0 == state row 8t
       const double* xb = Bs + (size_t)st * KC * pitchB;
@@ -643,41 +646,35 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
 }
 
 // -------------------------------------------------------------------------------------------------
-// GMW-pivoted LDL^T of the panel's nbe x nbe diagonal block by ONE warp: lane i holds row i in registers,
-// column j's pivot is broadcast with a shuffle, d_j = max(EPSILON, |c_jj|) (SLAM.cpp:2279-2285), the row is
+// GMW-pivoted LDL^T of the panel's nbe x nbe diagonal block by ONE warp: lane i owns row i of the panel in smem,
+// column j's pivot is broadcast from shared memory, d_j = max(EPSILON, |c_jj|) (SLAM.cpp:2279-2285), the row is
 // scaled (L(i,j) = C(i,j)/d_j, :2232) and the remaining columns are updated (:2253) -- a 32-step dependent
 // chain, so everything that is not on the chain (sqrt, flags, stores) is hoisted out of it.
 // Outputs: L (for the solve of the rows below), d, sqrt(d), and rows J0.. of S_new inside the block (:2321).
 // -------------------------------------------------------------------------------------------------
-template <bool FULL>
-__device__ __forceinline__ void diag_block(const double* Cp, double* Ld, double* dsm, double* sdsm, double* Snew,
-                                           int J0, int nbe, int n, int np, double eps, int lane, uint32_t& flags,
-                                           double& tmax) {
-  double r[NB];
-#pragma unroll
-  for (int k = 0; k < NB; ++k)
-    r[k] = (k <= lane && (FULL || (lane < nbe && k < nbe))) ? Cp[(size_t)lane * CP_PITCH + k] : 0.0;
+__device__ __noinline__ void diag_block(double* Cp, double* Ld, double* dsm, double* sdsm, double* Snew, int J0,
+                                        int nbe, int n, int np, double eps, int lane, uint32_t& flags, double& tmax) {
+  // Compact loops on purpose: this runs once per panel, and fully unrolled register code (tens of KB of SASS
+  // executed exactly once) was instruction-fetch bound.
+  double* myrow = Cp + (size_t)lane * CP_PITCH;
+  const bool live = lane < nbe;
   double dmine = 1.0;
   bool modified = false;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    if (FULL || j < nbe) {
-      const double cjj = __shfl_sync(0xffffffffu, r[j], j);
-      const double d = fmax(eps, fabs(cjj));
-      if (lane == j) { dmine = d; modified = (d != cjj); }
-      const double lij = r[j] / d;
-#pragma unroll
-      for (int k = j + 1; k < NB; ++k) {
-        if (FULL || k < nbe) {
-          const double ckj = __shfl_sync(0xffffffffu, r[j], k);  // C(k,j), still unscaled in lane k
-          r[k] = fma(-lij, ckj, r[k]);
-        }
-      }
-      r[j] = lij;
+  for (int j = 0; j < nbe; ++j) {
+    const double cjj = Cp[(size_t)j * CP_PITCH + j];
+    const double d = fmax(eps, fabs(cjj));
+    if (lane == j) { dmine = d; modified = (d != cjj); }
+    if (live) {
+      const double lij = myrow[j] / d;
+      const double* colj = Cp + j;
+#pragma unroll 4
+      for (int k = j + 1; k < nbe; ++k) myrow[k] = fma(-lij, colj[(size_t)k * CP_PITCH], myrow[k]);
+      Ld[lane * (NB + 1) + j] = lij;
     }
+    __syncwarp();
   }
   const double sd = sqrt(dmine);
-  if (lane < nbe) {
+  if (live) {
     dsm[lane] = dmine;
     sdsm[lane] = sd;
     if (modified && J0 + lane < n) flags |= (dmine > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
@@ -685,14 +682,12 @@ __device__ __forceinline__ void diag_block(const double* Cp, double* Ld, double*
   }
   __syncwarp();
   const int col = J0 + lane;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    if ((FULL || j < nbe) && lane < nbe) {
-      const double sdj = sdsm[j];
+  if (live) {
+    for (int j = 0; j < nbe; ++j) {
       const int row = J0 + j, rb = (row >> 3) << 3;
-      if (lane > j) Ld[lane * (NB + 1) + j] = r[j];
       if (col >= rb) {
-        const double v = (lane == j) ? sdj : ((lane > j) ? sdj * r[j] : 0.0);
+        const double sdj = sdsm[j];
+        const double v = (lane == j) ? sdj : ((lane > j) ? sdj * Ld[lane * (NB + 1) + j] : 0.0);
         Snew[bp_row_off(row, np) + (col - rb)] = v;
         if (lane > j && col < n) tmax = fmax(tmax, v * v);
       }
@@ -767,7 +762,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
 #pragma unroll
       for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
 
-    auto produce = [&](int t) {  // thread 0: one bulk copy per K row
+    auto produce = [&](int t) {  // warp 0: one bulk copy per K row, issued by lanes 0..7
       const double* src;
       int stride, dcol = 0, len = R;
       if (t < nA) {              // S_old rows 8t..8t+7 (stored from column 8t)
@@ -784,14 +779,13 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
         src = Snew + bp_block_off(blk, np) + (J0 - 8 * blk);
       }
       const int st = ring_acquire(ring, (uint32_t)(KC * len * sizeof(double)));
-      double* dst = Xs + (size_t)st * KC * pitch + dcol;
-#pragma unroll
-      for (int kk = 0; kk < KC; ++kk)
-        tma_load_1d(dst + kk * pitch, src + (size_t)kk * stride, (uint32_t)(len * sizeof(double)), ring.full + st);
+      if (lane < KC)
+        tma_load_1d(Xs + ((size_t)st * KC + lane) * pitch + dcol, src + (size_t)lane * stride,
+                    (uint32_t)(len * sizeof(double)), ring.full + st);
     };
     auto consume = [&](int t0, int t1) {
       for (int t = t0; t < t1; ++t) {
-        if (tid == 0 && t + NSTAGE - 1 < nchunks) produce(t + NSTAGE - 1);
+        if (warp == 0 && t + NSTAGE - 1 < nchunks) produce(t + NSTAGE - 1);
         const int st = ring_wait(ring);
         const double* xs_ = Xs + (size_t)st * KC * pitch;
         if (t >= nA1 && t < nA) {   // rows inside the diagonal block: only strips/tiles at or right of them
@@ -811,10 +805,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
 #pragma unroll
         for (int t = 0; t < NB / 8; ++t) { acc[qq][t][0] = -acc[qq][t][0]; acc[qq][t][1] = -acc[qq][t][1]; }
     };
-    if (tid == 0) {
-      fence_proxy_async();  // the ring aliases the previous panel's Cp (generic-proxy stores)
+    if (warp == 0)
       for (int t = 0; t < NSTAGE - 1 && t < nchunks; ++t) produce(t);
-    }
     consume(0, nA);          // + S_old^T S_old
     negate();
     consume(nA, nA + nU);    // acc = -(S^T S - U U^T) = -G(i, J)
@@ -851,41 +843,33 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
 #pragma unroll
         for (int tt = 0; tt < NB / 8; ++tt)
           if (tt < nt) {
-            double2 v = make_double2(acc[qq][tt][0], acc[qq][tt][1]);
-            *reinterpret_cast<double2*>(Cp + (size_t)ri * CP_PITCH + 8 * tt + 2 * (lane & 3)) = v;
+            double* dst = Cp + (size_t)ri * CP_PITCH + 8 * tt + 2 * (lane & 3);
+            dst[0] = acc[qq][tt][0];
+            dst[1] = acc[qq][tt][1];
           }
       }
     }
     __syncthreads();
     // ---- diagonal block: warp 0, one row per lane, right-looking in registers ----------------------
     if (warp == 0) {
-      if (nbe == NB) diag_block<true>(Cp, Ld, dsm, sdsm, Snew, J0, nbe, n, np, p.epsilon, lane, flags, tmax);
-      else diag_block<false>(Cp, Ld, dsm, sdsm, Snew, J0, nbe, n, np, p.epsilon, lane, flags, tmax);
+      diag_block(Cp, Ld, dsm, sdsm, Snew, J0, nbe, n, np, p.epsilon, lane, flags, tmax);
     }
     __syncthreads();
     // ---- rows below the block: C(i,j) -= sum_{k<j} C(i,k) L(j,k), then S_new(j,i) = sd_j C(i,j)/d_j --
     for (int i = J0 + nbe + tid; i < np; i += NTH) {
-      double r[NB];
-      const double* crow = Cp + (size_t)(i - J0) * CP_PITCH;
-#pragma unroll
-      for (int k = 0; k < NB; ++k) r[k] = (k < nbe) ? crow[k] : 0.0;
-#pragma unroll
-      for (int j = 1; j < NB; ++j) {
-        if (j < nbe) {
-          double a = r[j];
-#pragma unroll
-          for (int k = 0; k < j; ++k) a -= r[k] * Ld[j * (NB + 1) + k];
-          r[j] = a;
-        }
+      double* crow = Cp + (size_t)(i - J0) * CP_PITCH;
+      for (int j = 1; j < nbe; ++j) {
+        double a = crow[j];
+        const double* lrow = Ld + j * (NB + 1);
+#pragma unroll 4
+        for (int k = 0; k < j; ++k) a = fma(-crow[k], lrow[k], a);
+        crow[j] = a;
       }
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        if (j < nbe) {
-          const int row = J0 + j, rb = (row >> 3) << 3;
-          const double v = sdsm[j] * (r[j] / dsm[j]);
-          Snew[bp_row_off(row, np) + (i - rb)] = v;
-          if (i < n) tmax = fmax(tmax, v * v);
-        }
+      for (int j = 0; j < nbe; ++j) {
+        const int row = J0 + j, rb = (row >> 3) << 3;
+        const double v = sdsm[j] * (crow[j] / dsm[j]);
+        Snew[bp_row_off(row, np) + (i - rb)] = v;
+        if (i < n) tmax = fmax(tmax, v * v);
       }
     }
     fence_proxy_async();  // order this panel's generic-proxy smem/global accesses before the next bulk copies
