@@ -61,6 +61,7 @@ SYMBOLS = {
     "srukf_launch_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "srukf_set_profiling": (C.c_int, [_VP, C.c_int]),
     "srukf_get_kernel_times": (C.c_int, [_VP, _VP, _VP]),
+    "srukf_get_phase_cycles": (C.c_int, [_VP, _VP]),
     "srukf_last_error": (C.c_char_p, []),
     "srukf_version": (C.c_char_p, []),
 }

@@ -2,6 +2,7 @@
 // point needs a CUDA device and fails with SRUKF_ENODEV / SRUKF_ECUDA otherwise.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -14,7 +15,7 @@ struct StepPtrs {
   double* x; double* S; const double* u; const double* z; const uint8_t* matched;
   double* hbar; double* si; uint8_t* visible; double* cshift; double* pxyr; double* rsig;
   double* dZ; double* U; double* G; uint32_t* flags; int chunk0;
-  double* S2; int* worklist; int rel0;
+  double* S2; int* worklist; int rel0; unsigned long long* dbg;
 };
 int tile_warps(const DevParams& p);
 cudaError_t configure_kernels(const DevParams& p);
@@ -60,6 +61,7 @@ struct srukf_handle {
   double *dZ = nullptr, *U = nullptr, *G = nullptr;
   int gslots = 0;          // CTAs (and G scratch slots) of the reference-order fallback kernel
   int* worklist = nullptr;
+  unsigned long long* dbg = nullptr;  // phase-cycle counters (SRUKF_PHASE_TIMING=1)
   // split-API persistent intermediates (allocated on first use)
   double *rsig = nullptr, *dZ_all = nullptr, *U_all = nullptr, *G_all = nullptr;
   int phase = 0;           // 0 idle, 1 motion done, 2 measurement done
@@ -217,6 +219,12 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   CUH(cudaMemsetAsync(h->dZ, 0, sizeof(double) * (size_t)chunk * p.np * p.Lc, h->stream));
   CUH(cudaMemsetAsync(h->U, 0, sizeof(double) * (size_t)chunk * p.Lc * p.np, h->stream));
   CUH(cudaMemsetAsync(h->worklist, 0, sizeof(int) * ((size_t)chunk + 1), h->stream));
+  if (const char* e_ = getenv("SRUKF_PHASE_TIMING")) {
+    if (e_[0] == '1') {
+      CUH(cudaMalloc(&h->dbg, sizeof(unsigned long long) * 8));
+      CUH(cudaMemsetAsync(h->dbg, 0, sizeof(unsigned long long) * 8, h->stream));
+    }
+  }
   CUH(cudaStreamSynchronize(h->stream));
 #undef CUH
   *out = h;
@@ -227,7 +235,7 @@ int srukf_destroy(srukf_t* h) {
   if (!h) return SRUKF_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+  void* ptrs[] = {h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -241,7 +249,7 @@ static StepPtrs base_ptrs(srukf_t* h) {
   q.x = h->x; q.S = h->S; q.u = h->u; q.z = h->z; q.matched = h->matched;
   q.hbar = h->hbar; q.si = h->si; q.visible = h->visible; q.cshift = h->cshift; q.pxyr = h->pxyr;
   q.rsig = h->rsig; q.dZ = h->dZ; q.U = h->U; q.G = h->G; q.flags = h->flags; q.chunk0 = 0;
-  q.S2 = h->S2; q.worklist = h->worklist; q.rel0 = 0;
+  q.S2 = h->S2; q.worklist = h->worklist; q.rel0 = 0; q.dbg = h->dbg;
   return q;
 }
 
@@ -520,6 +528,15 @@ int srukf_get_kernel_times(srukf_t* h, double* ms3, uint64_t* launches3) {
   CU(cudaStreamSynchronize(h->stream));
   prof_collect(h);
   for (int i = 0; i < 3; ++i) { ms3[i] = h->prof_ms[i]; if (launches3) launches3[i] = h->prof_n[i]; }
+  return SRUKF_OK;
+}
+
+int srukf_get_phase_cycles(srukf_t* h, uint64_t* out8) {
+  if (!h || !out8) return fail(SRUKF_EINVAL, "srukf_get_phase_cycles: null argument");
+  if (!h->dbg) return fail(SRUKF_ESTATE, "srukf_get_phase_cycles: create the handle with SRUKF_PHASE_TIMING=1");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(out8, h->dbg, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return SRUKF_OK;
 }
 

@@ -38,6 +38,7 @@ struct StepPtrs {
   double* S2;             // [B][nbp] the other S buffer (k_update writes it)
   int* worklist;          // [0] = count, [1..] = chunk-relative filter indices needing the fallback
   int rel0;               // first chunk-relative filter of a k_downdate launch (non-worklist)
+  unsigned long long* dbg; // optional [8] phase-cycle counters of k_update (diagnostics; may be null)
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -388,9 +389,9 @@ __device__ __forceinline__ void ring_release(Ring& r) {
 //   arow: chunk base of the A operand (K-major, strip s at column 8*s - acol0), brow: of the B operand.
 template <int NW, int QLO, int QHI, int NTT>
 __device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const double* arow, int apitch, int acol0,
-                                          const double* brow, int bpitch, int lane, int warp) {
-#pragma unroll
-  for (int ks = 0; ks < KC / 4; ++ks) {
+                                          const double* brow, int bpitch, int nks, int lane, int warp) {
+#pragma unroll 2
+  for (int ks = 0; ks < nks; ++ks) {
     const int kk = 4 * ks + (lane & 3);
     const double* ar = arow + kk * apitch + (lane >> 2) - acol0;
     const double* br = brow + kk * bpitch + (lane >> 2);
@@ -408,9 +409,10 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const 
 // runtime (qlo, qhi) -> compile-time instantiation (warp-uniform switch)
 template <int NW, int NTT>
 __device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int qlo, int qhi, const double* arow,
-                                             int apitch, int acol0, const double* brow, int bpitch, int lane, int warp) {
+                                             int apitch, int acol0, const double* brow, int bpitch, int nks, int lane,
+                                             int warp) {
 #define SRUKF_CASE(LO, HI) \
-  case LO * 8 + HI: mma_chunk<NW, LO, HI, NTT>(acc, arow, apitch, acol0, brow, bpitch, lane, warp); break;
+  case LO * 8 + HI: mma_chunk<NW, LO, HI, NTT>(acc, arow, apitch, acol0, brow, bpitch, nks, lane, warp); break;
   switch (qlo * 8 + qhi) {
     SRUKF_CASE(0, 1) SRUKF_CASE(0, 2) SRUKF_CASE(0, 3) SRUKF_CASE(0, 4) SRUKF_CASE(0, 5)
     SRUKF_CASE(1, 2) SRUKF_CASE(1, 3) SRUKF_CASE(1, 4) SRUKF_CASE(1, 5)
@@ -425,9 +427,8 @@ __device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int
 // strips rs >= rs_min, tiles tt in [tt_min, nt)
 template <int NW>
 __device__ __forceinline__ void mma_chunk_pred(double (&acc)[MAXQ][NB / 8][2], const double* arow, int pitch, int nstrip,
-                                               int rs_min, int tt_min, int nt, int lane, int warp) {
-#pragma unroll
-  for (int ks = 0; ks < KC / 4; ++ks) {
+                                               int rs_min, int tt_min, int nt, int nks, int lane, int warp) {
+  for (int ks = 0; ks < nks; ++ks) {
     const double* row = arow + (4 * ks + (lane & 3)) * pitch + (lane >> 2);
     double bf[NB / 8];
 #pragma unroll
@@ -548,10 +549,10 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
       const double* xb = Bs + (size_t)st * KC * pitchB;
       // output strip s = warp + NW*q receives S rows k <= its own: active slots are q >= qlo
       const int qlo = (t > warp) ? (t - warp + NW - 1) / NW : 0;
-      if (nt == NB / 8) mma_chunk_rt<NW, NB / 8>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, lane, warp);
-      else if (nt == 1) mma_chunk_rt<NW, 1>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, lane, warp);
-      else if (nt == 2) mma_chunk_rt<NW, 2>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, lane, warp);
-      else mma_chunk_rt<NW, 3>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, lane, warp);
+      if (nt == NB / 8) mma_chunk_rt<NW, NB / 8>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, KC / 4, lane, warp);
+      else if (nt == 1) mma_chunk_rt<NW, 1>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, KC / 4, lane, warp);
+      else if (nt == 2) mma_chunk_rt<NW, 2>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, KC / 4, lane, warp);
+      else mma_chunk_rt<NW, 3>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, KC / 4, lane, warp);
       ring_release(ring);
     }
     // epilogue: apply wi*gamma and si^-1 to each column pair, store Ut[c][f] (transposed), accumulate the shift
@@ -742,6 +743,11 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   Ring ring;
   ring_init<NW>(ring, bars);
   double gmax = -1.0e300, zmax = 0.0, tmax = 0.0;
+  // optional phase timing (warp 0 lane 0 of every CTA): K loop / barrier skew / panel store / diag / solve
+  const bool timing = (q.dbg != nullptr) && tid == 0;
+  long long tph[6] = {0, 0, 0, 0, 0, 0};
+  long long tlast = timing ? clock64() : 0;
+#define SRUKF_TICK(i) if (timing) { long long tnow_ = clock64(); tph[i] += tnow_ - tlast; tlast = tnow_; }
 
   for (int J0 = 0; J0 < np; J0 += NB) {
     const int nbe = (np - J0 < NB) ? (np - J0) : NB;
@@ -749,52 +755,68 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     const int nt = nbe / 8;
     const int pitch = x_pitch(R);
     const int jb = J0 / 8;
-    const int nA1 = jb + 1;            // S_old chunks whose stored range covers [J0, np)
-    const int nA = jb + nt;            // ... plus the chunks inside the panel's diagonal block
-    const int nU = Lc / KC, nC = jb;
-    const int nchunks = nA + nU + nC;
     const int nstrip = R / 8;
     const int nq_w = (nstrip > warp) ? (nstrip - warp - 1) / NW + 1 : 0;
     const bool regular = (nt == NB / 8);
+    // K rows per pipeline stage: as many 8-row blocks as fit the fixed stage size (8 rows at full width), so the
+    // DMMA work and the bytes in flight per mbarrier round trip stay roughly constant as the panel narrows
+    int rpc = ((KC * x_pitch(np)) / pitch) & ~7;
+    if (rpc > 32) rpc = 32;
+    // chunk list: [A1: S_old rows 0..J0+7 | A2: S_old rows inside the diagonal block, 8 at a time |
+    //              B: Ut rows | C: finished S_new rows 0..J0-1]
+    const int rowsA1 = J0 + 8, rowsB = Lc, rowsC = J0;
+    const int cA1 = (rowsA1 + rpc - 1) / rpc, cA2 = nt - 1, cB = (rowsB + rpc - 1) / rpc, cC = (rowsC + rpc - 1) / rpc;
+    const int nA = cA1 + cA2;
+    const int nchunks = nA + cB + cC;
     double acc[MAXQ][NB / 8][2];
 #pragma unroll
     for (int qq = 0; qq < MAXQ; ++qq)
 #pragma unroll
       for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
 
-    auto produce = [&](int t) {  // warp 0: one bulk copy per K row, issued by lanes 0..7
+    // rows of chunk t: first row (within its source) and count
+    auto chunk_rows = [&](int t, int& row0) -> int {
+      if (t < cA1) { row0 = t * rpc; return (rowsA1 - row0 < rpc) ? rowsA1 - row0 : rpc; }
+      if (t < nA) { row0 = rowsA1 + 8 * (t - cA1); return 8; }
+      if (t < nA + cB) { row0 = (t - nA) * rpc; return (rowsB - row0 < rpc) ? rowsB - row0 : rpc; }
+      row0 = (t - nA - cB) * rpc;
+      return (rowsC - row0 < rpc) ? rowsC - row0 : rpc;
+    };
+    auto produce = [&](int t) {  // warp 0: one bulk copy per K row, one row per lane
+      int row0;
+      const int nrows = chunk_rows(t, row0);
+      const int k = row0 + lane;
       const double* src;
-      int stride, dcol = 0, len = R;
-      if (t < nA) {              // S_old rows 8t..8t+7 (stored from column 8t)
-        const int k0 = 8 * t;
-        stride = np - k0;
-        if (k0 <= J0) src = Sold + bp_block_off(t, np) + (J0 - k0);
-        else { src = Sold + bp_block_off(t, np); dcol = k0 - J0; len = np - k0; }  // left part is never read
-      } else if (t < nA + nU) {
-        src = Ut + (size_t)(8 * (t - nA)) * np + J0;
-        stride = np;
+      int dcol = 0, len = R;
+      if (t < nA) {              // S_old row k (stored from column 8*floor(k/8))
+        const int kb = (k >> 3) << 3;
+        if (kb <= J0) src = Sold + bp_row_off(k, np) + (J0 - kb);
+        else { src = Sold + bp_row_off(k, np); dcol = kb - J0; len = np - kb; }  // left part is never read
+      } else if (t < nA + cB) {
+        src = Ut + (size_t)k * np + J0;
       } else {
-        const int blk = t - nA - nU;
-        stride = np - 8 * blk;
-        src = Snew + bp_block_off(blk, np) + (J0 - 8 * blk);
+        src = Snew + bp_row_off(k, np) + (J0 - ((k >> 3) << 3));
       }
-      const int st = ring_acquire(ring, (uint32_t)(KC * len * sizeof(double)));
-      if (lane < KC)
-        tma_load_1d(Xs + ((size_t)st * KC + lane) * pitch + dcol, src + (size_t)lane * stride,
+      // the A2 chunks are the only ones with a shortened row; all their rows share the same length
+      const int st = ring_acquire(ring, (uint32_t)(nrows * len * sizeof(double)));
+      if (lane < nrows)
+        tma_load_1d(Xs + (size_t)st * KC * x_pitch(np) + (size_t)lane * pitch + dcol, src,
                     (uint32_t)(len * sizeof(double)), ring.full + st);
     };
     auto consume = [&](int t0, int t1) {
       for (int t = t0; t < t1; ++t) {
         if (warp == 0 && t + NSTAGE - 1 < nchunks) produce(t + NSTAGE - 1);
+        int row0;
+        const int nrows = chunk_rows(t, row0);
         const int st = ring_wait(ring);
-        const double* xs_ = Xs + (size_t)st * KC * pitch;
-        if (t >= nA1 && t < nA) {   // rows inside the diagonal block: only strips/tiles at or right of them
-          const int kq = t - jb;
-          mma_chunk_pred<NW>(acc, xs_, pitch, nstrip, kq, kq, nt, lane, warp);
+        const double* xs_ = Xs + (size_t)st * KC * x_pitch(np);
+        if (t >= cA1 && t < nA) {   // rows inside the diagonal block: only strips/tiles at or right of them
+          const int kq = t - cA1 + 1;
+          mma_chunk_pred<NW>(acc, xs_, pitch, nstrip, kq, kq, nt, 2, lane, warp);
         } else if (regular) {
-          mma_chunk_rt<NW, NB / 8>(acc, 0, nq_w, xs_, pitch, 0, xs_, pitch, lane, warp);
+          mma_chunk_rt<NW, NB / 8>(acc, 0, nq_w, xs_, pitch, 0, xs_, pitch, nrows / 4, lane, warp);
         } else {
-          mma_chunk_pred<NW>(acc, xs_, pitch, nstrip, 0, 0, nt, lane, warp);
+          mma_chunk_pred<NW>(acc, xs_, pitch, nstrip, 0, 0, nt, nrows / 4, lane, warp);
         }
         ring_release(ring);
       }
@@ -809,7 +831,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
       for (int t = 0; t < NSTAGE - 1 && t < nchunks; ++t) produce(t);
     consume(0, nA);          // + S_old^T S_old
     negate();
-    consume(nA, nA + nU);    // acc = -(S^T S - U U^T) = -G(i, J)
+    consume(nA, nA + cB);    // acc = -(S^T S - U U^T) = -G(i, J)
     // track max diag / max off-diag of G for beta^2 (:2204-2205)
 #pragma unroll
     for (int qq = 0; qq < MAXQ; ++qq) {
@@ -832,9 +854,11 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
         }
       }
     }
-    consume(nA + nU, nchunks);  // + S_new^T S_new
+    consume(nA + cB, nchunks);  // + S_new^T S_new
     negate();                   // acc = C(i, J)
+    SRUKF_TICK(0)
     __syncthreads();            // every warp is done with the ring: reuse it as the panel
+    SRUKF_TICK(1)
 #pragma unroll
     for (int qq = 0; qq < MAXQ; ++qq) {
       const int rs = warp + NW * qq;
@@ -850,10 +874,12 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
       }
     }
     __syncthreads();
+    SRUKF_TICK(2)
     // ---- diagonal block: warp 0, one row per lane, right-looking in registers ----------------------
     if (warp == 0) {
       diag_block(Cp, Ld, dsm, sdsm, Snew, J0, nbe, n, np, p.epsilon, lane, flags, tmax);
     }
+    SRUKF_TICK(3)
     __syncthreads();
     // ---- rows below the block: C(i,j) -= sum_{k<j} C(i,k) L(j,k), then S_new(j,i) = sd_j C(i,j)/d_j --
     for (int i = J0 + nbe + tid; i < np; i += NTH) {
@@ -872,9 +898,17 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
         if (i < n) tmax = fmax(tmax, v * v);
       }
     }
+    SRUKF_TICK(4)
     fence_proxy_async();  // order this panel's generic-proxy smem/global accesses before the next bulk copies
     __syncthreads();      // S_new rows of this panel are visible to the next panel's bulk copies; Cp is free
+    SRUKF_TICK(5)
   }
+  if (timing) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) atomicAdd(q.dbg + i, (unsigned long long)tph[i]);
+    atomicAdd(q.dbg + 7, 1ull);
+  }
+#undef SRUKF_TICK
   // ---- GMW guard: theta_j^2/beta^2 would have raised a pivot iff max S_new(j,i)^2 > beta^2 -------------
   gmax = block_max<NTH>(gmax, red);
   zmax = block_max<NTH>(zmax, red);
