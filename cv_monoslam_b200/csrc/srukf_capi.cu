@@ -133,6 +133,7 @@ static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
   d.img_w = s.image_width; d.img_h = s.image_height;
   d.a1 = s.a1; d.a2 = s.a2; d.a3 = s.a3; d.a4 = s.a4; d.sigma_measure = s.sigma_measure;
   d.epsilon = s.epsilon; d.newton_iters = s.newton_iters;
+  { const char* e_ = getenv("SRUKF_DBG_SKIP_MMA"); d.dbg_skip_mma = (e_ && e_[0] == '1') ? 1 : 0; }
   // calculateSampleParameter, SLAM.cpp:1050-1103 (operation order kept)
   const int Na = d.Na;
   double wm0, wc0, wi, wi_sr, gamma;

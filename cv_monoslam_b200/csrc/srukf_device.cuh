@@ -28,6 +28,7 @@ struct DevParams {
   double cpair;  // sqrt(2) * wi_sr * gamma (== 1 analytically for all three weight types)
   double epsilon;
   int newton_iters;
+  int dbg_skip_mma;  // diagnostics only: stream the K chunks but skip the DMMAs (SRUKF_DBG_SKIP_MMA=1)
 };
 
 // packed upper-triangular row-major: row i holds columns i..n-1
@@ -92,6 +93,14 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16-byte asynchronous global->shared copy (LDGSTS, L2 only) and its completion hook onto an mbarrier:
+// the executing thread arrives on `bar` once all of its earlier cp.async operations have landed.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // distortOnePointRW, SLAM.cpp:3177-3213.  The Newton loop (fixed 100 iterations in the reference)

@@ -323,9 +323,11 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
 // -------------------------------------------------------------------------------------------------
 // Shared tiling constants and the K-chunk pipeline of the DMMA kernels.
 //   The CTA's warps own 8-row strips of the output (strip s -> warp s % NW, slot s / NW); a strip times
-//   NB columns is NB/8 DMMA tiles.  K is streamed in chunks of KC rows: thread 0 issues one 1-D TMA bulk copy
-//   per row into a ring of NSTAGE stages; "full" mbarriers carry the byte counts, "empty" mbarriers (one
-//   arrival per warp) hand stages back.  No __syncthreads inside a K loop.
+//   NB columns is NB/8 DMMA tiles.  K is streamed in chunks of >= KC rows into a ring of NSTAGE stages with
+//   16-byte cp.async (LDGSTS) issued by all warps (one row per warp at a time, coalesced 512 B per instruction);
+//   each thread's copies complete onto the stage's "full" mbarrier, "empty" mbarriers (one arrival per warp)
+//   hand stages back.  No __syncthreads inside a K loop.  (1-D TMA bulk copies, one per row, were measured
+//   at ~130 cycles per copy and made the loop copy-count bound: profiles/r01_update_tuning.md.)
 // -------------------------------------------------------------------------------------------------
 constexpr int NB = 32;      // panel width (columns per contraction pass)
 constexpr int KC = 8;       // K rows per pipeline stage
@@ -337,40 +339,37 @@ __host__ __device__ __forceinline__ int x_pitch(int R) { return ((R + 15) & ~15)
 __host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 struct Ring {
-  uint64_t* full;    // [NSTAGE]
-  uint64_t* empty;   // [NSTAGE]
-  uint32_t produced; // chunks issued so far (meaningful in warp 0 only)
-  uint32_t consumed; // chunks consumed so far by this warp
+  uint64_t* full;    // [NSTAGE]  one arrival per thread: its cp.async copies of the chunk have landed
+  uint64_t* empty;   // [NSTAGE]  one arrival per warp: the warp is done reading the chunk
+  uint32_t issued;   // chunks this warp has issued loads for
+  uint32_t consumed; // chunks this warp has consumed
 };
 
 template <int NW>
 __device__ __forceinline__ void ring_init(Ring& r, uint64_t* bars) {
   r.full = bars;
   r.empty = bars + NSTAGE;
-  r.produced = 0;
+  r.issued = 0;
   r.consumed = 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
-      mbar_init(r.full + i, 1);
+      mbar_init(r.full + i, NW * 32);
       mbar_init(r.empty + i, NW);
     }
     mbar_fence_init();
   }
   __syncthreads();
 }
-// warp 0 (converged): claim the next stage.  Lane 0 waits until every warp released the stage's previous occupant
-// and posts the byte count; afterwards the lanes issue the row copies in parallel.
-__device__ __forceinline__ int ring_acquire(Ring& r, uint32_t bytes) {
-  const uint32_t g = r.produced++;
+// every warp: claim the stage of the next chunk to load (waits until all warps released its previous occupant)
+__device__ __forceinline__ int ring_acquire(Ring& r) {
+  const uint32_t g = r.issued++;
   const int st = g % NSTAGE;
   const uint32_t use = g / NSTAGE;
-  if ((threadIdx.x & 31) == 0) {
-    if (use > 0) mbar_wait(r.empty + st, (use - 1) & 1);
-    mbar_expect_tx(r.full + st, bytes);
-  }
-  __syncwarp();
+  if (use > 0) mbar_wait(r.empty + st, (use - 1) & 1);
   return st;
 }
+// every thread, after issuing its cp.async share of the chunk in stage st
+__device__ __forceinline__ void ring_commit(Ring& r, int st) { cp_async_mbar_arrive(r.full + st); }
 // all threads of a warp: wait for the next chunk, returns its stage
 __device__ __forceinline__ int ring_wait(Ring& r) {
   const uint32_t g = r.consumed;
@@ -383,6 +382,10 @@ __device__ __forceinline__ void ring_release(Ring& r) {
   r.consumed++;
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(r.empty + st);
+}
+// one warp copies `len` doubles (even, 16-byte aligned on both sides) of one row
+__device__ __forceinline__ void warp_copy_row(double* dst, const double* src, int len, int lane) {
+  for (int c = 2 * lane; c < len; c += 64) cp_async16(dst + c, src + c);
 }
 
 // DMMA over one KC-row chunk: strips slots [QLO, QHI) of this warp x NTT column tiles.
@@ -528,22 +531,18 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
       for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
     // only blocks whose rows can touch a feature row matter: S rows >= nf (robot) have zero dZ
     const int nchunk = (nf + 7) / 8;
-    auto produce = [&](int t) {  // warp 0: lanes 0..7 copy the S rows, lanes 8..15 the dZ rows of the chunk
+    auto produce = [&](int t) {  // every warp copies one S row and one dZ row of the 8-row chunk (NW >= KC)
       const int R = np - 8 * t;
-      const int st = ring_acquire(ring, (uint32_t)(KC * (R + ncol) * sizeof(double)));
-      if (lane < KC) {
-        const double* src = Sg + bp_block_off(t, np) + (size_t)lane * R;
-        tma_load_1d(Xs + ((size_t)st * KC + lane) * pitchA, src, (uint32_t)(R * sizeof(double)), ring.full + st);
-      } else if (lane < 2 * KC) {
-        const int kk = lane - KC;
-        const double* vsrc = dZ + (size_t)(8 * t + kk) * Lc + cg;
-        tma_load_1d(Bs + ((size_t)st * KC + kk) * pitchB, vsrc, (uint32_t)(ncol * sizeof(double)), ring.full + st);
+      const int st = ring_acquire(ring);
+      if (warp < KC) {
+        warp_copy_row(Xs + ((size_t)st * KC + warp) * pitchA, Sg + bp_block_off(t, np) + (size_t)warp * R, R, lane);
+        warp_copy_row(Bs + ((size_t)st * KC + warp) * pitchB, dZ + (size_t)(8 * t + warp) * Lc + cg, ncol, lane);
       }
+      ring_commit(ring, st);
     };
-    if (warp == 0)
-      for (int t = 0; t < NSTAGE - 1 && t < nchunk; ++t) produce(t);
+    for (int t = 0; t < NSTAGE - 1 && t < nchunk; ++t) produce(t);
     for (int t = 0; t < nchunk; ++t) {
-      if (warp == 0 && t + NSTAGE - 1 < nchunk) produce(t + NSTAGE - 1);
+      if (t + NSTAGE - 1 < nchunk) produce(t + NSTAGE - 1);
       const int st = ring_wait(ring);
       const double* xa = Xs + (size_t)st * KC * pitchA;  // column 0 == state row 8t
       const double* xb = Bs + (size_t)st * KC * pitchB;
@@ -647,52 +646,102 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
 }
 
 // -------------------------------------------------------------------------------------------------
-// GMW-pivoted LDL^T of the panel's nbe x nbe diagonal block by ONE warp: lane i owns row i of the panel in smem,
-// column j's pivot is broadcast from shared memory, d_j = max(EPSILON, |c_jj|) (SLAM.cpp:2279-2285), the row is
-// scaled (L(i,j) = C(i,j)/d_j, :2232) and the remaining columns are updated (:2253) -- a 32-step dependent
-// chain, so everything that is not on the chain (sqrt, flags, stores) is hoisted out of it.
-// Outputs: L (for the solve of the rows below), d, sqrt(d), and rows J0.. of S_new inside the block (:2321).
+// Panel factorisation (the part of k_update after the contraction).
+//
+// The panel C (R rows x nbe <= 32 columns, row-major in smem, pitch CP_PITCH) is the Schur complement of the
+// finished panels.  It is factorised left-looking in sub-panels of 8 columns, GMW-pivoted LDL^T
+// (SLAM.cpp:2197-2327 with d_j = max(EPSILON, |c_jj|), :2279-2285):
+//   U  (all warps, DMMA)   C(:, sub) -= L(:, <sub) * W(sub rows, <sub)^T,  W = unscaled C of the diagonal rows
+//   D  (one warp, 8 lanes) 8x8 diagonal block: pivots, L = C/d (:2232), in-block updates (:2253) -- the only
+//                          sequential chain (8 pivots); 28 shuffle-FMAs in registers
+//   T  (one thread per row) rows below: C(i,j) -= sum_{k<j in sub} L(i,k) W(j,k), L(i,j) = C(i,j)/d_j
+// Afterwards Cp holds L; S_new(j, i) = sqrt(d_j) L(i, j) (:2321) is written by the caller.
 // -------------------------------------------------------------------------------------------------
-__device__ __noinline__ void diag_block(double* Cp, double* Ld, double* dsm, double* sdsm, double* Snew, int J0,
-                                        int nbe, int n, int np, double eps, int lane, uint32_t& flags, double& tmax) {
-  // Compact loops on purpose: this runs once per panel, and fully unrolled register code (tens of KB of SASS
-  // executed exactly once) was instruction-fetch bound.
-  double* myrow = Cp + (size_t)lane * CP_PITCH;
-  const bool live = lane < nbe;
-  double dmine = 1.0;
-  bool modified = false;
-  for (int j = 0; j < nbe; ++j) {
-    const double cjj = Cp[(size_t)j * CP_PITCH + j];
-    const double d = fmax(eps, fabs(cjj));
-    if (lane == j) { dmine = d; modified = (d != cjj); }
-    if (live) {
-      const double lij = myrow[j] / d;
-      const double* colj = Cp + j;
-#pragma unroll 4
-      for (int k = j + 1; k < nbe; ++k) myrow[k] = fma(-lij, colj[(size_t)k * CP_PITCH], myrow[k]);
-      Ld[lane * (NB + 1) + j] = lij;
+constexpr int WD_PITCH = NB + 1;
+
+template <int NW>
+__device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm, double* sdsm, int R, int nbe, int J0,
+                                             int n, double eps, uint32_t& flags) {
+  constexpr int NTH = NW * 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nsub = nbe / 8;
+  for (int sb = 0; sb < nsub; ++sb) {
+    const int c0 = 8 * sb;
+    if (sb > 0) {
+      // ---- U: strips of 8 rows from c0 down, one 8x8 tile each, K = c0 ----
+      for (int rs = sb + warp; rs < R / 8; rs += NW) {
+        const int i = 8 * rs + (lane >> 2);
+        double* ctile = Cp + (size_t)i * CP_PITCH + c0 + 2 * (lane & 3);
+        double a0 = ctile[0], a1 = ctile[1];
+        const double* arow = Cp + (size_t)i * CP_PITCH + (lane & 3);
+        const double* brow = Wd + (size_t)(c0 + (lane >> 2)) * WD_PITCH + (lane & 3);
+        for (int k0 = 0; k0 < c0; k0 += 4) dmma(a0, a1, -arow[k0], brow[k0]);
+        ctile[0] = a0;
+        ctile[1] = a1;
+      }
+      __syncthreads();
     }
-    __syncwarp();
-  }
-  const double sd = sqrt(dmine);
-  if (live) {
-    dsm[lane] = dmine;
-    sdsm[lane] = sd;
-    if (modified && J0 + lane < n) flags |= (dmine > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
-    if (!isfinite(sd)) flags |= SRUKF_FLAG_NAN;
-  }
-  __syncwarp();
-  const int col = J0 + lane;
-  if (live) {
-    for (int j = 0; j < nbe; ++j) {
-      const int row = J0 + j, rb = (row >> 3) << 3;
-      if (col >= rb) {
-        const double sdj = sdsm[j];
-        const double v = (lane == j) ? sdj : ((lane > j) ? sdj * Ld[lane * (NB + 1) + j] : 0.0);
-        Snew[bp_row_off(row, np) + (col - rb)] = v;
-        if (lane > j && col < n) tmax = fmax(tmax, v * v);
+    // ---- D: 8x8 diagonal block, warp 0, lanes 0..7 own rows c0..c0+7 ----
+    if (warp == 0) {
+      const int li = lane & 7;
+      double r[8];
+      const double* myrow = Cp + (size_t)(c0 + li) * CP_PITCH + c0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = myrow[k];
+      double dmine = 1.0, w[8];
+      bool modified = false;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double cjj = __shfl_sync(0xffffffffu, r[j], j);
+        const double d = fmax(eps, fabs(cjj));
+        if (li == j) { dmine = d; modified = (d != cjj); }
+        w[j] = r[j];
+        const double lij = r[j] / d;
+#pragma unroll
+        for (int k = j + 1; k < 8; ++k) {
+          const double ckj = __shfl_sync(0xffffffffu, r[j], k);  // C(k,j), unscaled
+          r[k] = fma(-lij, ckj, r[k]);
+        }
+        r[j] = lij;
+      }
+      if (lane < 8) {
+        const double sd = sqrt(dmine);
+        dsm[c0 + lane] = dmine;
+        sdsm[c0 + lane] = sd;
+        if (modified && J0 + c0 + lane < n) flags |= (dmine > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
+        if (!isfinite(sd)) flags |= SRUKF_FLAG_NAN;
+        double* wrow = Wd + (size_t)(c0 + lane) * WD_PITCH + c0;
+        double* crow = Cp + (size_t)(c0 + lane) * CP_PITCH + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          wrow[j] = w[j];                       // unscaled C(i,j) (only j <= i is used)
+          if (j < lane) crow[j] = r[j];         // L(i,j)
+        }
       }
     }
+    __syncthreads();
+    // ---- T: rows below the 8x8 block ----
+    for (int i = c0 + 8 + tid; i < R; i += NTH) {
+      double* crow = Cp + (size_t)i * CP_PITCH + c0;
+      double cf[8], l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        double a = crow[j];
+        const double* wj = Wd + (size_t)(c0 + j) * WD_PITCH + c0;
+#pragma unroll
+        for (int k = 0; k < j; ++k) a = fma(-l[k], wj[k], a);
+        cf[j] = a;
+        l[j] = a / dsm[c0 + j];
+      }
+      if (i < nbe) {   // rows of the panel's own diagonal block feed later sub-panels as W
+        double* wrow = Wd + (size_t)i * WD_PITCH + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wrow[j] = cf[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) crow[j] = l[j];
+    }
+    __syncthreads();
   }
 }
 
@@ -704,11 +753,8 @@ __device__ __noinline__ void diag_block(double* Cp, double* Ld, double* dsm, dou
 //     C(i, J) = sum_{k < J0+32} S_old(k,i) S_old(k,J) - sum_c Ut(c,i) Ut(c,J) - sum_{k < J0} S_new(k,i) S_new(k,J)
 // is one DMMA contraction over K = [S_old rows | Ut rows | S_new rows]; all three are K-major in HBM, so the
 // same smem chunk feeds the A fragment (rows i) and the B fragment (its first 32 columns).  The two negative
-// sources are folded in by flipping the sign of the accumulators between sources.  Then
-//   - warp 0 factorises the 32x32 diagonal block in registers with the GMW pivot rule
-//       d_j = max(EPSILON, |c_jj|)                      (:2279-2285; theta_j^2/beta^2 handled below)
-//   - every thread solves one row below the block against it (C(i,j) = G(i,j) - sum_k L(j,k) C(i,k), :2253)
-//   - rows J of S_new = sqrt(d_j) * C(:,j)/d_j are written (:2321).
+// sources are folded in by flipping the sign of the accumulators between sources.  The panel is then factorised
+// in shared memory (factor_panel) and rows J of S_new = sqrt(d_j) * L(:, j) are written (:2321).
 // GMW's third pivot candidate theta_j^2/beta^2 exceeds d_j iff max_i S_new(j,i)^2 > beta^2, where beta^2 needs
 // max diag / max off-diag of G (:2204-2211).  Both maxima are accumulated on the fly (G's panel is visible after
 // the S_old and Ut sources) and compared at the end: on violation, or when a pivot is modified beyond the EPSILON
@@ -724,13 +770,14 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   const double* Sold = q.S + (size_t)b * p.nbp;
   double* Snew = q.S2 + (size_t)b * p.nbp;
   const double* Ut = q.U + (size_t)blockIdx.x * Lc * np;
+  const int stage_doubles = KC * x_pitch(np);
   size_t off = 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * NSTAGE * sizeof(uint64_t));
-  double* Ld = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB * (NB + 1);
+  double* Wd = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB * WD_PITCH;
   double* dsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;    // pivots d_j
   double* sdsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;   // sqrt(d_j)
   double* red = reinterpret_cast<double*>(smraw + off); off = align16(off + sizeof(double) * 40);
-  double* Xs = reinterpret_cast<double*>(smraw + off);  // ring: NSTAGE x KC x pitch, aliased by the panel Cp
+  double* Xs = reinterpret_cast<double*>(smraw + off);  // ring: NSTAGE stages, aliased by the panel Cp
   double* Cp = Xs;
   uint32_t flags = 0;
 
@@ -743,7 +790,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   Ring ring;
   ring_init<NW>(ring, bars);
   double gmax = -1.0e300, zmax = 0.0, tmax = 0.0;
-  // optional phase timing (warp 0 lane 0 of every CTA): K loop / barrier skew / panel store / diag / solve
+  // optional phase timing (thread 0 of every CTA): K loop / barrier skew / panel store / factor / write-out
   const bool timing = (q.dbg != nullptr) && tid == 0;
   long long tph[6] = {0, 0, 0, 0, 0, 0};
   long long tlast = timing ? clock64() : 0;
@@ -754,13 +801,12 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     const int R = np - J0;
     const int nt = nbe / 8;
     const int pitch = x_pitch(R);
-    const int jb = J0 / 8;
     const int nstrip = R / 8;
     const int nq_w = (nstrip > warp) ? (nstrip - warp - 1) / NW + 1 : 0;
     const bool regular = (nt == NB / 8);
     // K rows per pipeline stage: as many 8-row blocks as fit the fixed stage size (8 rows at full width), so the
     // DMMA work and the bytes in flight per mbarrier round trip stay roughly constant as the panel narrows
-    int rpc = ((KC * x_pitch(np)) / pitch) & ~7;
+    int rpc = (stage_doubles / pitch) & ~7;
     if (rpc > 32) rpc = 32;
     // chunk list: [A1: S_old rows 0..J0+7 | A2: S_old rows inside the diagonal block, 8 at a time |
     //              B: Ut rows | C: finished S_new rows 0..J0-1]
@@ -782,35 +828,37 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
       row0 = (t - nA - cB) * rpc;
       return (rowsC - row0 < rpc) ? rowsC - row0 : rpc;
     };
-    auto produce = [&](int t) {  // warp 0: one bulk copy per K row, one row per lane
+    auto produce = [&](int t) {  // every warp copies rows warp, warp+NW, .. of the chunk
       int row0;
       const int nrows = chunk_rows(t, row0);
-      const int k = row0 + lane;
-      const double* src;
-      int dcol = 0, len = R;
-      if (t < nA) {              // S_old row k (stored from column 8*floor(k/8))
-        const int kb = (k >> 3) << 3;
-        if (kb <= J0) src = Sold + bp_row_off(k, np) + (J0 - kb);
-        else { src = Sold + bp_row_off(k, np); dcol = kb - J0; len = np - kb; }  // left part is never read
-      } else if (t < nA + cB) {
-        src = Ut + (size_t)k * np + J0;
-      } else {
-        src = Snew + bp_row_off(k, np) + (J0 - ((k >> 3) << 3));
+      const int st = ring_acquire(ring);
+      double* sdst = Xs + (size_t)st * stage_doubles;
+      for (int rr = warp; rr < nrows; rr += NW) {
+        const int k = row0 + rr;
+        const double* src;
+        int dcol = 0, len = R;
+        if (t < nA) {              // S_old row k (stored from column 8*floor(k/8))
+          const int kb = (k >> 3) << 3;
+          if (kb <= J0) src = Sold + bp_row_off(k, np) + (J0 - kb);
+          else { src = Sold + bp_row_off(k, np); dcol = kb - J0; len = np - kb; }  // left part is never read
+        } else if (t < nA + cB) {
+          src = Ut + (size_t)k * np + J0;
+        } else {
+          src = Snew + bp_row_off(k, np) + (J0 - ((k >> 3) << 3));
+        }
+        warp_copy_row(sdst + (size_t)rr * pitch + dcol, src, len, lane);
       }
-      // the A2 chunks are the only ones with a shortened row; all their rows share the same length
-      const int st = ring_acquire(ring, (uint32_t)(nrows * len * sizeof(double)));
-      if (lane < nrows)
-        tma_load_1d(Xs + (size_t)st * KC * x_pitch(np) + (size_t)lane * pitch + dcol, src,
-                    (uint32_t)(len * sizeof(double)), ring.full + st);
+      ring_commit(ring, st);
     };
     auto consume = [&](int t0, int t1) {
       for (int t = t0; t < t1; ++t) {
-        if (warp == 0 && t + NSTAGE - 1 < nchunks) produce(t + NSTAGE - 1);
+        if (t + NSTAGE - 1 < nchunks) produce(t + NSTAGE - 1);
         int row0;
         const int nrows = chunk_rows(t, row0);
         const int st = ring_wait(ring);
-        const double* xs_ = Xs + (size_t)st * KC * x_pitch(np);
-        if (t >= cA1 && t < nA) {   // rows inside the diagonal block: only strips/tiles at or right of them
+        const double* xs_ = Xs + (size_t)st * stage_doubles;
+        if (p.dbg_skip_mma) {
+        } else if (t >= cA1 && t < nA) {   // rows inside the diagonal block: only strips/tiles at or right of them
           const int kq = t - cA1 + 1;
           mma_chunk_pred<NW>(acc, xs_, pitch, nstrip, kq, kq, nt, 2, lane, warp);
         } else if (regular) {
@@ -827,8 +875,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
 #pragma unroll
         for (int t = 0; t < NB / 8; ++t) { acc[qq][t][0] = -acc[qq][t][0]; acc[qq][t][1] = -acc[qq][t][1]; }
     };
-    if (warp == 0)
-      for (int t = 0; t < NSTAGE - 1 && t < nchunks; ++t) produce(t);
+    for (int t = 0; t < NSTAGE - 1 && t < nchunks; ++t) produce(t);
     consume(0, nA);          // + S_old^T S_old
     negate();
     consume(nA, nA + cB);    // acc = -(S^T S - U U^T) = -G(i, J)
@@ -875,32 +922,25 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     }
     __syncthreads();
     SRUKF_TICK(2)
-    // ---- diagonal block: warp 0, one row per lane, right-looking in registers ----------------------
-    if (warp == 0) {
-      diag_block(Cp, Ld, dsm, sdsm, Snew, J0, nbe, n, np, p.epsilon, lane, flags, tmax);
-    }
+    factor_panel<NW>(Cp, Wd, dsm, sdsm, R, nbe, J0, n, p.epsilon, flags);
     SRUKF_TICK(3)
-    __syncthreads();
-    // ---- rows below the block: C(i,j) -= sum_{k<j} C(i,k) L(j,k), then S_new(j,i) = sd_j C(i,j)/d_j --
-    for (int i = J0 + nbe + tid; i < np; i += NTH) {
-      double* crow = Cp + (size_t)(i - J0) * CP_PITCH;
-      for (int j = 1; j < nbe; ++j) {
-        double a = crow[j];
-        const double* lrow = Ld + j * (NB + 1);
-#pragma unroll 4
-        for (int k = 0; k < j; ++k) a = fma(-crow[k], lrow[k], a);
-        crow[j] = a;
-      }
+    // ---- rows J0.. of S_new: S_new(J0+j, J0+i) = sd_j L(i,j) for i > j, sd_j on the diagonal, explicit zeros
+    //      left of the diagonal inside the row's stored range (blocked-packed layout) ----
+    for (int i = tid; i < R; i += NTH) {
+      const double* crow = Cp + (size_t)i * CP_PITCH;
+      const int col = J0 + i;
       for (int j = 0; j < nbe; ++j) {
         const int row = J0 + j, rb = (row >> 3) << 3;
-        const double v = sdsm[j] * (crow[j] / dsm[j]);
-        Snew[bp_row_off(row, np) + (i - rb)] = v;
-        if (i < n) tmax = fmax(tmax, v * v);
+        if (col >= rb) {
+          const double sdj = sdsm[j];
+          const double v = (i == j) ? sdj : ((i > j) ? sdj * crow[j] : 0.0);
+          Snew[bp_row_off(row, np) + (col - rb)] = v;
+          if (i > j && col < n) tmax = fmax(tmax, v * v);
+        }
       }
     }
     SRUKF_TICK(4)
-    fence_proxy_async();  // order this panel's generic-proxy smem/global accesses before the next bulk copies
-    __syncthreads();      // S_new rows of this panel are visible to the next panel's bulk copies; Cp is free
+    __syncthreads();  // S_new rows of this panel are visible to the next panel's loads; Cp is free
     SRUKF_TICK(5)
   }
   if (timing) {
@@ -1177,7 +1217,7 @@ size_t update_smem_bytes(const DevParams& p) {
   size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
   off += sizeof(double) * (NB * (NB + 1) + 2 * NB);
   off = align16(off + sizeof(double) * 40);
-  size_t ring = (size_t)NSTAGE * KC * x_pitch(p.np);
+  size_t ring = (size_t)NSTAGE * KC * x_pitch(p.np);  // stage size is fixed: 8 rows at full width
   size_t panel = (size_t)p.np * CP_PITCH;
   return off + sizeof(double) * (ring > panel ? ring : panel);
 }

@@ -15,7 +15,7 @@ g.sync()
 out = np.zeros(8, dtype=np.uint64)
 capi.check(g._lib.srukf_get_phase_cycles(g._h, capi.ptr(out)))
 n = float(out[7])
-names = ["K loop", "post-K barrier", "panel store+sync", "diag block", "solve (TRSM)", "end barrier"]
+names = ["K loop", "post-K barrier", "panel store+sync", "factor panel", "write S_new", "end barrier"]
 tot = float(out[:6].sum())
 for nm, v in zip(names, out[:6]):
     print(f"{nm:18s} {float(v)/n:12.0f} cycles/filter  {100*float(v)/tot:5.1f}%")
