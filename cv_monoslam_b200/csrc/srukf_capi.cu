@@ -8,6 +8,9 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "srukf_device.cuh"
 
 namespace srukf {
@@ -16,7 +19,11 @@ struct StepPtrs {
   double* hbar; double* si; uint8_t* visible; double* cshift; double* pxyr; double* rsig;
   double* dZ; double* U; double* G; uint32_t* flags; int chunk0;
   double* S2; int* worklist; int rel0; unsigned long long* dbg;
+  const CUtensorMap* tmaps; int sbuf; int tm_dz; int dz_filter0;
 };
+// tensor-map table layout and box geometry (must match srukf_kernels.cu)
+constexpr int TM_S0 = 0, TM_S1 = 4, TM_UT = 8, TM_DZ = 12, TM_DZ_ALL = 13, TM_COUNT = 14;
+constexpr int TP = 72, BP_B = 40;
 int tile_warps(const DevParams& p);
 cudaError_t configure_kernels(const DevParams& p);
 size_t predict_smem_bytes(const DevParams& p);
@@ -49,8 +56,10 @@ struct srukf_handle {
   DevParams p{};
   SrukfParams prm{};
   cudaStream_t stream = nullptr;
-  // state: S lives in the internal blocked-packed layout; k_update ping-pongs between S and S2
-  double *x = nullptr, *S = nullptr, *S2 = nullptr;
+  // state: S lives in the internal square layout; k_update ping-pongs between the two buffers
+  double *x = nullptr, *S = nullptr, *S2 = nullptr;   // S = current, S2 = the other one
+  int sbuf = 0;                                       // index of the current buffer in the tensor-map table
+  CUtensorMap* tmaps = nullptr;                       // device table of TMA tensor maps
   // per-step inputs (device copies for the host-pointer API)
   double *u = nullptr, *z = nullptr; uint8_t* matched = nullptr;
   // prediction outputs
@@ -126,7 +135,7 @@ static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
   d.ntri = d.n * (d.n + 1) / 2;
   d.np = (d.n + 7) & ~7;
   d.Lc = (2 * L + 7) & ~7;
-  d.nbp = bp_block_off(d.np / 8, d.np);
+  d.nbp = d.np * d.np;
   d.cam_dx = s.cam_dx; d.cam_dy = s.cam_dy; d.cam_cx = s.cam_cx; d.cam_cy = s.cam_cy;
   d.cam_k1 = s.cam_k1; d.cam_k2 = s.cam_k2;
   d.f1 = s.cam_f / s.cam_dx; d.f2 = s.cam_f / s.cam_dy;  // SLAM.cpp:336-337
@@ -158,6 +167,50 @@ static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
   d.cpair = std::sqrt(2.0) * wi_sr * gamma;
 }
 
+// 3-D tiled tensor map over doubles: dims {d0, d1, d2} (d0 contiguous), box {b0, b1, 1}
+static int encode_map(CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+      return fail(SRUKF_ECUDA, "cuTensorMapEncodeTiled is not available from the driver", e);
+    encode = (PFN_cuTensorMapEncodeTiled)fn;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * sizeof(double), d0 * d1 * sizeof(double)};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+    return SRUKF_ECUDA;
+  }
+  return SRUKF_OK;
+}
+
+// (re)build the handle's tensor-map table: S buffers (by allocation order), Ut, dZ scratch, dZ_all
+static int build_tensor_maps(srukf_handle* h, double* sbuf0, double* sbuf1) {
+  const DevParams& p = h->p;
+  CUtensorMap hm[TM_COUNT];
+  memset(hm, 0, sizeof(hm));
+  int rc;
+  for (int r = 0; r < 4; ++r) {
+    if ((rc = encode_map(&hm[TM_S0 + r], sbuf0, p.np, p.np, p.B, TP, 8 * (r + 1)))) return rc;
+    if ((rc = encode_map(&hm[TM_S1 + r], sbuf1 ? sbuf1 : sbuf0, p.np, p.np, p.B, TP, 8 * (r + 1)))) return rc;
+    if ((rc = encode_map(&hm[TM_UT + r], h->U, p.np, p.Lc, h->chunk, TP, 8 * (r + 1)))) return rc;
+  }
+  if ((rc = encode_map(&hm[TM_DZ], h->dZ, p.Lc, p.np, h->chunk, BP_B, 8))) return rc;
+  if ((rc = encode_map(&hm[TM_DZ_ALL], h->dZ_all ? h->dZ_all : h->dZ, p.Lc, p.np, h->dZ_all ? p.B : h->chunk, BP_B, 8)))
+    return rc;
+  if (!h->tmaps) CU(cudaMalloc(&h->tmaps, sizeof(hm)));
+  CU(cudaMemcpyAsync(h->tmaps, hm, sizeof(hm), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return SRUKF_OK;
+}
+
 int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** out) {
   if (!out || B <= 0 || L <= 0) return fail(SRUKF_EINVAL, "srukf_create: bad arguments");
   int ndev = 0;
@@ -187,7 +240,10 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   const size_t n = p.n, L2 = 2 * (size_t)L;
   CUH(cudaMalloc(&h->x, sizeof(double) * B * n));
   CUH(cudaMalloc(&h->S, sizeof(double) * (size_t)B * p.nbp));
-  if (prm.downdate_mode == 0) CUH(cudaMalloc(&h->S2, sizeof(double) * (size_t)B * p.nbp));
+  if (prm.downdate_mode == 0) {
+    CUH(cudaMalloc(&h->S2, sizeof(double) * (size_t)B * p.nbp));
+    CUH(cudaMemsetAsync(h->S2, 0, sizeof(double) * (size_t)B * p.nbp, h->stream));
+  }
   CUH(cudaMalloc(&h->u, sizeof(double) * B * 3));
   CUH(cudaMalloc(&h->z, sizeof(double) * B * L2));
   CUH(cudaMalloc(&h->matched, (size_t)B * L));
@@ -222,12 +278,16 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   CUH(cudaMemsetAsync(h->worklist, 0, sizeof(int) * ((size_t)chunk + 1), h->stream));
   if (const char* e_ = getenv("SRUKF_PHASE_TIMING")) {
     if (e_[0] == '1') {
-      CUH(cudaMalloc(&h->dbg, sizeof(unsigned long long) * 8));
-      CUH(cudaMemsetAsync(h->dbg, 0, sizeof(unsigned long long) * 8, h->stream));
+      CUH(cudaMalloc(&h->dbg, sizeof(unsigned long long) * 16));
+      CUH(cudaMemsetAsync(h->dbg, 0, sizeof(unsigned long long) * 16, h->stream));
     }
   }
   CUH(cudaStreamSynchronize(h->stream));
 #undef CUH
+  {
+    int rc_ = build_tensor_maps(h, h->S, h->S2);
+    if (rc_) { srukf_destroy(h); return rc_; }
+  }
   *out = h;
   return SRUKF_OK;
 }
@@ -236,7 +296,7 @@ int srukf_destroy(srukf_t* h) {
   if (!h) return SRUKF_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+  void* ptrs[] = {h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -251,6 +311,7 @@ static StepPtrs base_ptrs(srukf_t* h) {
   q.hbar = h->hbar; q.si = h->si; q.visible = h->visible; q.cshift = h->cshift; q.pxyr = h->pxyr;
   q.rsig = h->rsig; q.dZ = h->dZ; q.U = h->U; q.G = h->G; q.flags = h->flags; q.chunk0 = 0;
   q.S2 = h->S2; q.worklist = h->worklist; q.rel0 = 0; q.dbg = h->dbg;
+  q.tmaps = h->tmaps; q.sbuf = h->sbuf; q.tm_dz = TM_DZ; q.dz_filter0 = 0;
   return q;
 }
 
@@ -325,6 +386,9 @@ static int ensure_split_buffers(srukf_t* h) {
   if (!h->dZ_all) {
     CU(cudaMalloc(&h->dZ_all, sizeof(double) * (size_t)p.B * p.np * p.Lc));
     CU(cudaMemsetAsync(h->dZ_all, 0, sizeof(double) * (size_t)p.B * p.np * p.Lc, h->stream));
+    // buffers by allocation order: the current one is index h->sbuf
+    int rc_ = build_tensor_maps(h, h->sbuf ? h->S2 : h->S, h->sbuf ? h->S : h->S2);
+    if (rc_) return rc_;
   }
   return SRUKF_OK;
 }
@@ -394,7 +458,7 @@ static void run_update(srukf_t* h, StepPtrs q, int b0, int nb) {
 
 // after a fused update over the whole batch the roles of the two S buffers swap
 static void flip_buffers(srukf_t* h) {
-  if (h->prm.downdate_mode == 0) { double* t = h->S; h->S = h->S2; h->S2 = t; }
+  if (h->prm.downdate_mode == 0) { double* t = h->S; h->S = h->S2; h->S2 = t; h->sbuf ^= 1; }
 }
 
 int srukf_kalman_update(srukf_t* h, const double* z, const uint8_t* matched) {
@@ -408,7 +472,7 @@ int srukf_kalman_update(srukf_t* h, const double* z, const uint8_t* matched) {
   for (int b0 = 0; b0 < p.B; b0 += h->chunk) {
     int nb = p.B - b0 < h->chunk ? p.B - b0 : h->chunk;
     StepPtrs qq = q;
-    if (h->dZ_all) qq.dZ = h->dZ_all + (size_t)b0 * p.np * p.Lc;
+    if (h->dZ_all) { qq.dZ = h->dZ_all + (size_t)b0 * p.np * p.Lc; qq.tm_dz = TM_DZ_ALL; qq.dz_filter0 = b0; }
     run_update(h, qq, b0, nb);
   }
   flip_buffers(h);
@@ -536,7 +600,7 @@ int srukf_get_phase_cycles(srukf_t* h, uint64_t* out8) {
   if (!h || !out8) return fail(SRUKF_EINVAL, "srukf_get_phase_cycles: null argument");
   if (!h->dbg) return fail(SRUKF_ESTATE, "srukf_get_phase_cycles: create the handle with SRUKF_PHASE_TIMING=1");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(out8, h->dbg, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(out8, h->dbg, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return SRUKF_OK;
 }

@@ -16,7 +16,7 @@ struct DevParams {
   int B, L, n, nf, Na, P, ntri;
   int np;    // n rounded up to a multiple of 8 (internal padded state dimension)
   int Lc;    // 2L rounded up to a multiple of 8 (padded measurement dimension)
-  int nbp;   // doubles per filter in the internal blocked-packed layout of S
+  int nbp;   // doubles per filter in the internal layout of S (np * np)
   // camera (SLAM.cpp:329-337)
   double cam_dx, cam_dy, cam_cx, cam_cy, cam_k1, cam_k2, f1, f2;
   double img_w, img_h;
@@ -34,17 +34,12 @@ struct DevParams {
 // packed upper-triangular row-major: row i holds columns i..n-1
 __host__ __device__ __forceinline__ int tri_off(int i, int n) { return i * n - (i * (i - 1)) / 2; }
 
-// Internal layout of S in HBM ("blocked-packed"): rows are grouped in blocks of 8; row k stores columns
-// [8*floor(k/8), np) contiguously (explicit zeros left of the diagonal), so every row segment that a kernel
-// streams starts 64-byte aligned and an 8-row block is one contiguous run.  Rows/columns n..np-1 are padding
-// (identity on the diagonal).
-__host__ __device__ __forceinline__ int bp_block_off(int blk, int np) { return 8 * (blk * np - 4 * blk * (blk - 1)); }
-__host__ __device__ __forceinline__ int bp_row_off(int k, int np) {
-  int blk = k >> 3;
-  return bp_block_off(blk, np) + (k - 8 * blk) * (np - 8 * blk);
-}
-// address of element (k, c), c >= 8*floor(k/8)
-__host__ __device__ __forceinline__ int bp_idx(int k, int c, int np) { return bp_row_off(k, np) + (c - ((k >> 3) << 3)); }
+// Internal layout of S in HBM: one np x np row-major square per filter (np = n rounded up to a multiple of 8),
+// upper triangular, everything below the diagonal stays zero, rows/columns n..np-1 are padding (identity).
+// The square costs 2x the packed size in capacity but no extra traffic (kernels only stream the row suffixes
+// they need), and it makes every K-chunk of the DMMA kernels a regular strided box that ONE TMA tensor copy
+// can fetch (the packed layouts needed one copy per row and were copy-count bound).
+__host__ __device__ __forceinline__ int bp_idx(int k, int c, int np) { return k * np + c; }
 
 __device__ __forceinline__ double S_at(const double* __restrict__ S, int np, int i, int c) {
   return (c >= i) ? S[bp_idx(i, c, np)] : 0.0;
@@ -92,7 +87,16 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 3-D tiled TMA load (cp.async.bulk.tensor, SASS UTMALDG): box of the tensor map at (c0, c1, c2) -> smem
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// orders this thread's earlier generic-proxy accesses (shared AND global) before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // 16-byte asynchronous global->shared copy (LDGSTS, L2 only) and its completion hook onto an mbarrier:
 // the executing thread arrives on `bar` once all of its earlier cp.async operations have landed.
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {

@@ -12,6 +12,8 @@
 //                the panel's modified-Cholesky pivots and a triangular solve.  Writes the other S buffer.
 //   k_downdate : reference-order fallback (unblocked GMW, optional per-column sequence) for flagged filters
 //                and for downdate_mode 1/2.
+#include <cuda.h>
+
 #include "srukf_device.cuh"
 
 namespace srukf {
@@ -38,7 +40,11 @@ struct StepPtrs {
   double* S2;             // [B][nbp] the other S buffer (k_update writes it)
   int* worklist;          // [0] = count, [1..] = chunk-relative filter indices needing the fallback
   int rel0;               // first chunk-relative filter of a k_downdate launch (non-worklist)
-  unsigned long long* dbg; // optional [8] phase-cycle counters of k_update (diagnostics; may be null)
+  unsigned long long* dbg; // optional [16] phase-cycle counters of k_update (diagnostics; may be null)
+  const CUtensorMap* tmaps; // [TM_COUNT] TMA tensor maps of the handle (device memory)
+  int sbuf;                // which S buffer is "current" (q.S): 0 or 1
+  int tm_dz;               // TM_DZ (chunk scratch) or TM_DZ_ALL (split API)
+  int dz_filter0;          // first filter of this launch inside the dZ tensor
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -323,53 +329,68 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
 // -------------------------------------------------------------------------------------------------
 // Shared tiling constants and the K-chunk pipeline of the DMMA kernels.
 //   The CTA's warps own 8-row strips of the output (strip s -> warp s % NW, slot s / NW); a strip times
-//   NB columns is NB/8 DMMA tiles.  K is streamed in chunks of >= KC rows into a ring of NSTAGE stages with
-//   16-byte cp.async (LDGSTS) issued by all warps (one row per warp at a time, coalesced 512 B per instruction);
-//   each thread's copies complete onto the stage's "full" mbarrier, "empty" mbarriers (one arrival per warp)
-//   hand stages back.  No __syncthreads inside a K loop.  (1-D TMA bulk copies, one per row, were measured
-//   at ~130 cycles per copy and made the loop copy-count bound: profiles/r01_update_tuning.md.)
+//   NB columns is NB/8 DMMA tiles.  K is streamed in chunks of 8..32 rows into a ring of NSTAGE stages by
+//   3-D TMA tensor copies (cp.async.bulk.tensor): a chunk is ceil(width/64) boxes of [rows x 72 doubles]
+//   (64 payload columns + 8 columns of overlap, so the smem row pitch 72 == 8 mod 16 keeps the DMMA fragment
+//   loads bank-conflict free), issued by one elected thread.  "full" mbarriers carry the byte counts, "empty"
+//   mbarriers (one arrival per warp) hand stages back.  No __syncthreads inside a K loop.
+//   Measured alternatives (profiles/r01_update_tuning.md): one 1-D bulk copy per row (~130 cycles per copy,
+//   copy-count bound) and cp.async by all warps (~1.2k issue cycles per chunk stolen from the DMMA warps).
 // -------------------------------------------------------------------------------------------------
 constexpr int NB = 32;      // panel width (columns per contraction pass)
-constexpr int KC = 8;       // K rows per pipeline stage
-constexpr int NSTAGE = 4;   // ring depth
+constexpr int KC = 8;       // K rows per pipeline stage at full width
+#ifndef SRUKF_NSTAGE
+#define SRUKF_NSTAGE 4
+#endif
+constexpr int NSTAGE = SRUKF_NSTAGE;   // ring depth
 constexpr int MAXQ = 5;     // strips per warp: np <= 8 * NW * MAXQ
+constexpr int TW = 64;      // payload columns per TMA box
+constexpr int TP = 72;      // box width == smem row pitch inside a box (doubles)
+constexpr int BP_B = 40;    // box width of the dZ operand of k_gain (32 payload columns + 8)
 constexpr int CP_PITCH = NB + 1;  // odd pitch: one row per lane/thread is bank-conflict free
+constexpr int WD_PITCH = NB + 1;
 
-__host__ __device__ __forceinline__ int x_pitch(int R) { return ((R + 15) & ~15) + 8; }  // == 8 mod 16: conflict-free frags
+// indices into the handle's tensor-map table (StepPtrs::tmaps)
+constexpr int TM_S0 = 0;    // +0..3: S buffer 0, boxes of 8/16/24/32 rows x TP columns
+constexpr int TM_S1 = 4;    // +0..3: S buffer 1
+constexpr int TM_UT = 8;    // +0..3: Ut scratch
+// 12: dZ scratch (chunk), box 8 rows x BP_B columns; 13: dZ of the whole batch (split API) -- see StepPtrs::tm_dz
+
 __host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+__host__ __device__ __forceinline__ int ntiles(int width) { return (width + TW - 1) / TW; }
+__host__ __device__ __forceinline__ int stage_doubles_for(int np) { return KC * ntiles(np) * TP; }
 
 struct Ring {
-  uint64_t* full;    // [NSTAGE]  one arrival per thread: its cp.async copies of the chunk have landed
+  uint64_t* full;    // [NSTAGE]  expect_tx by the producer thread + TMA complete_tx
   uint64_t* empty;   // [NSTAGE]  one arrival per warp: the warp is done reading the chunk
-  uint32_t issued;   // chunks this warp has issued loads for
-  uint32_t consumed; // chunks this warp has consumed
+  uint32_t produced; // chunks issued so far (meaningful in thread 0 only)
+  uint32_t consumed; // chunks consumed so far by this warp
 };
 
 template <int NW>
 __device__ __forceinline__ void ring_init(Ring& r, uint64_t* bars) {
   r.full = bars;
   r.empty = bars + NSTAGE;
-  r.issued = 0;
+  r.produced = 0;
   r.consumed = 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
-      mbar_init(r.full + i, NW * 32);
+      mbar_init(r.full + i, 1);
       mbar_init(r.empty + i, NW);
     }
     mbar_fence_init();
   }
   __syncthreads();
 }
-// every warp: claim the stage of the next chunk to load (waits until all warps released its previous occupant)
-__device__ __forceinline__ int ring_acquire(Ring& r) {
-  const uint32_t g = r.issued++;
+// thread 0: claim the next stage (waits until every warp released its previous occupant) and post the byte count
+__device__ __forceinline__ int ring_acquire(Ring& r, uint32_t bytes) {
+  const uint32_t g = r.produced++;
   const int st = g % NSTAGE;
   const uint32_t use = g / NSTAGE;
   if (use > 0) mbar_wait(r.empty + st, (use - 1) & 1);
+  mbar_expect_tx(r.full + st, bytes);
   return st;
 }
-// every thread, after issuing its cp.async share of the chunk in stage st
-__device__ __forceinline__ void ring_commit(Ring& r, int st) { cp_async_mbar_arrive(r.full + st); }
 // all threads of a warp: wait for the next chunk, returns its stage
 __device__ __forceinline__ int ring_wait(Ring& r) {
   const uint32_t g = r.consumed;
@@ -383,27 +404,30 @@ __device__ __forceinline__ void ring_release(Ring& r) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(r.empty + st);
 }
-// one warp copies `len` doubles (even, 16-byte aligned on both sides) of one row
-__device__ __forceinline__ void warp_copy_row(double* dst, const double* src, int len, int lane) {
-  for (int c = 2 * lane; c < len; c += 64) cp_async16(dst + c, src + c);
-}
 
-// DMMA over one KC-row chunk: strips slots [QLO, QHI) of this warp x NTT column tiles.
-//   arow: chunk base of the A operand (K-major, strip s at column 8*s - acol0), brow: of the B operand.
+// DMMA over one chunk held as boxes [tile][row][TP]: strip slots [QLO, QHI) of this warp x NTT column tiles.
+//   The chunk's column 0 is output row/column `c0` of the panel; strip s covers chunk columns 8*(s-s0)..+7,
+//   i.e. box (8*(s-s0)) / 64 at offset (8*(s-s0)) % 64.  B fragments come from `bbase` (pitch bpitch).
 template <int NW, int QLO, int QHI, int NTT>
-__device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const double* arow, int apitch, int acol0,
-                                          const double* brow, int bpitch, int nks, int lane, int warp) {
+__device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const double* abase, int tstride, int s0,
+                                          const double* bbase, int bpitch, int nks, int lane, int warp) {
+  int aoff[QHI > QLO ? QHI - QLO : 1];
+#pragma unroll
+  for (int q = QLO; q < QHI; ++q) {
+    const int rel = 8 * (warp + NW * q - s0);
+    aoff[q - QLO] = (rel >> 6) * tstride + (rel & 63);
+  }
 #pragma unroll 2
   for (int ks = 0; ks < nks; ++ks) {
     const int kk = 4 * ks + (lane & 3);
-    const double* ar = arow + kk * apitch + (lane >> 2) - acol0;
-    const double* br = brow + kk * bpitch + (lane >> 2);
+    const double* ar = abase + kk * TP + (lane >> 2);
+    const double* br = bbase + kk * bpitch + (lane >> 2);
     double bf[NTT];
 #pragma unroll
     for (int tt = 0; tt < NTT; ++tt) bf[tt] = br[8 * tt];
 #pragma unroll
     for (int q = QLO; q < QHI; ++q) {
-      const double a = ar[8 * (warp + NW * q)];
+      const double a = ar[aoff[q - QLO]];
 #pragma unroll
       for (int tt = 0; tt < NTT; ++tt) dmma(acc[q][tt][0], acc[q][tt][1], a, bf[tt]);
     }
@@ -411,11 +435,11 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const 
 }
 // runtime (qlo, qhi) -> compile-time instantiation (warp-uniform switch)
 template <int NW, int NTT>
-__device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int qlo, int qhi, const double* arow,
-                                             int apitch, int acol0, const double* brow, int bpitch, int nks, int lane,
+__device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int qlo, int qhi, const double* abase,
+                                             int tstride, int s0, const double* bbase, int bpitch, int nks, int lane,
                                              int warp) {
 #define SRUKF_CASE(LO, HI) \
-  case LO * 8 + HI: mma_chunk<NW, LO, HI, NTT>(acc, arow, apitch, acol0, brow, bpitch, nks, lane, warp); break;
+  case LO * 8 + HI: mma_chunk<NW, LO, HI, NTT>(acc, abase, tstride, s0, bbase, bpitch, nks, lane, warp); break;
   switch (qlo * 8 + qhi) {
     SRUKF_CASE(0, 1) SRUKF_CASE(0, 2) SRUKF_CASE(0, 3) SRUKF_CASE(0, 4) SRUKF_CASE(0, 5)
     SRUKF_CASE(1, 2) SRUKF_CASE(1, 3) SRUKF_CASE(1, 4) SRUKF_CASE(1, 5)
@@ -426,27 +450,14 @@ __device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int
   }
 #undef SRUKF_CASE
 }
-// fully predicated variant for the few irregular chunks (diagonal-block rows, narrow last panel):
-// strips rs >= rs_min, tiles tt in [tt_min, nt)
 template <int NW>
-__device__ __forceinline__ void mma_chunk_pred(double (&acc)[MAXQ][NB / 8][2], const double* arow, int pitch, int nstrip,
-                                               int rs_min, int tt_min, int nt, int nks, int lane, int warp) {
-  for (int ks = 0; ks < nks; ++ks) {
-    const double* row = arow + (4 * ks + (lane & 3)) * pitch + (lane >> 2);
-    double bf[NB / 8];
-#pragma unroll
-    for (int tt = 0; tt < NB / 8; ++tt) bf[tt] = (tt >= tt_min && tt < nt) ? row[8 * tt] : 0.0;
-#pragma unroll
-    for (int q = 0; q < MAXQ; ++q) {
-      const int rs = warp + NW * q;
-      if (rs >= rs_min && rs < nstrip) {
-        const double a = row[8 * rs];
-#pragma unroll
-        for (int tt = 0; tt < NB / 8; ++tt)
-          if (tt >= tt_min && tt < nt) dmma(acc[q][tt][0], acc[q][tt][1], a, bf[tt]);
-      }
-    }
-  }
+__device__ __forceinline__ void mma_chunk_any(double (&acc)[MAXQ][NB / 8][2], int qlo, int qhi, int nt,
+                                              const double* abase, int tstride, int s0, const double* bbase, int bpitch,
+                                              int nks, int lane, int warp) {
+  if (nt == NB / 8) mma_chunk_rt<NW, NB / 8>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
+  else if (nt == 1) mma_chunk_rt<NW, 1>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
+  else if (nt == 2) mma_chunk_rt<NW, 2>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
+  else mma_chunk_rt<NW, 3>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -460,28 +471,27 @@ __device__ __forceinline__ void mma_chunk_pred(double (&acc)[MAXQ][NB / 8][2], c
 // sum_i w_i (z_i - hbar_j); that sum vanishes identically when wc0 == wm0 (weight types 0 and 2) and is kept,
 // as a feature-sequential pass, only for weight type 1.
 // The triangular product runs on the FP64 tensor pipe: output strips of 8 state rows x 32 measurement
-// columns, K = the 8-row blocks of S (one contiguous run each in the blocked-packed layout).
+// columns, K = 8-row blocks of S, each fetched from column 8t on by TMA.
 // -------------------------------------------------------------------------------------------------
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
-  constexpr int pitchB = NB + 8;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = q.chunk0 + blockIdx.x;
   const int n = p.n, nf = p.nf, L = p.L, L2 = 2 * p.L, np = p.np, Lc = p.Lc;
-  const int pitchA = x_pitch(np);
+  const int sdoubles = stage_doubles_for(np);
   size_t off = 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * NSTAGE * sizeof(uint64_t));
   double* sii = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 4 * (Lc / 2);   // per column pair
   double* gv = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 2 * (Lc / 2);    // si^-T (z - hbar)
   double* ct = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 2 * (Lc / 2);    // c^T si^-1
-  int* act = reinterpret_cast<int*>(smraw + off); off = align16(off + sizeof(int) * (L + 1));
-  double* Xs = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NSTAGE * KC * pitchA;
+  int* act = reinterpret_cast<int*>(smraw + off); off = (off + sizeof(int) * (L + 1) + 127) & ~(size_t)127;
+  double* Xs = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NSTAGE * sdoubles;
   double* Bs = reinterpret_cast<double*>(smraw + off);
   int* nact = act + L;
-  const double* Sg = q.S + (size_t)b * p.nbp;
-  const double* dZ = q.dZ + (size_t)blockIdx.x * np * Lc;
+  const CUtensorMap* tmS = q.tmaps + (q.sbuf ? TM_S1 : TM_S0);   // 8-row boxes
+  const CUtensorMap* tmZ = q.tmaps + q.tm_dz;
   double* Ut = q.U + (size_t)blockIdx.x * Lc * np;
   if (tid == 0) *nact = 0;
   __syncthreads();
@@ -531,27 +541,23 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
       for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
     // only blocks whose rows can touch a feature row matter: S rows >= nf (robot) have zero dZ
     const int nchunk = (nf + 7) / 8;
-    auto produce = [&](int t) {  // every warp copies one S row and one dZ row of the 8-row chunk (NW >= KC)
-      const int R = np - 8 * t;
-      const int st = ring_acquire(ring);
-      if (warp < KC) {
-        warp_copy_row(Xs + ((size_t)st * KC + warp) * pitchA, Sg + bp_block_off(t, np) + (size_t)warp * R, R, lane);
-        warp_copy_row(Bs + ((size_t)st * KC + warp) * pitchB, dZ + (size_t)(8 * t + warp) * Lc + cg, ncol, lane);
-      }
-      ring_commit(ring, st);
+    auto produce = [&](int t) {  // thread 0: S rows 8t..8t+7 from column 8t on (boxes of 64+8 columns) + dZ rows
+      const int nbx = ntiles(np - 8 * t);
+      const int st = ring_acquire(ring, (uint32_t)((nbx * KC * TP + KC * BP_B) * sizeof(double)));
+      double* xd = Xs + (size_t)st * sdoubles;
+      for (int j = 0; j < nbx; ++j) tma_load_3d(xd + (size_t)j * KC * TP, tmS, 8 * t + TW * j, 8 * t, b, ring.full + st);
+      tma_load_3d(Bs + (size_t)st * KC * BP_B, tmZ, cg, 8 * t, q.dz_filter0 + blockIdx.x, ring.full + st);
     };
-    for (int t = 0; t < NSTAGE - 1 && t < nchunk; ++t) produce(t);
+    if (tid == 0)
+      for (int t = 0; t < NSTAGE - 1 && t < nchunk; ++t) produce(t);
     for (int t = 0; t < nchunk; ++t) {
-      if (t + NSTAGE - 1 < nchunk) produce(t + NSTAGE - 1);
+      if (tid == 0 && t + NSTAGE - 1 < nchunk) produce(t + NSTAGE - 1);
       const int st = ring_wait(ring);
-      const double* xa = Xs + (size_t)st * KC * pitchA;  // column 0 == state row 8t
-      const double* xb = Bs + (size_t)st * KC * pitchB;
+      const double* xa = Xs + (size_t)st * sdoubles;     // column 0 == state row 8t
+      const double* xb = Bs + (size_t)st * KC * BP_B;
       // output strip s = warp + NW*q receives S rows k <= its own: active slots are q >= qlo
       const int qlo = (t > warp) ? (t - warp + NW - 1) / NW : 0;
-      if (nt == NB / 8) mma_chunk_rt<NW, NB / 8>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, KC / 4, lane, warp);
-      else if (nt == 1) mma_chunk_rt<NW, 1>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, KC / 4, lane, warp);
-      else if (nt == 2) mma_chunk_rt<NW, 2>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, KC / 4, lane, warp);
-      else mma_chunk_rt<NW, 3>(acc, qlo, nq_w, xa, pitchA, 8 * t, xb, pitchB, KC / 4, lane, warp);
+      mma_chunk_any<NW>(acc, qlo, nq_w, nt, xa, KC * TP, t, xb, BP_B, KC / 4, lane, warp);
       ring_release(ring);
     }
     // epilogue: apply wi*gamma and si^-1 to each column pair, store Ut[c][f] (transposed), accumulate the shift
@@ -657,8 +663,6 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
 //   T  (one thread per row) rows below: C(i,j) -= sum_{k<j in sub} L(i,k) W(j,k), L(i,j) = C(i,j)/d_j
 // Afterwards Cp holds L; S_new(j, i) = sqrt(d_j) L(i, j) (:2321) is written by the caller.
 // -------------------------------------------------------------------------------------------------
-constexpr int WD_PITCH = NB + 1;
-
 template <int NW>
 __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm, double* sdsm, int R, int nbe, int J0,
                                              int n, double eps, uint32_t& flags) {
@@ -760,7 +764,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
 // the S_old and Ut sources) and compared at the end: on violation, or when a pivot is modified beyond the EPSILON
 // floor, the filter is queued for the reference-order fallback (k_downdate) which recomputes it from S_old.
 // -------------------------------------------------------------------------------------------------
-template <int NW>
+template <int NW, bool TIMING>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -769,14 +773,16 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   const int n = p.n, L = p.L, np = p.np, Lc = p.Lc;
   const double* Sold = q.S + (size_t)b * p.nbp;
   double* Snew = q.S2 + (size_t)b * p.nbp;
-  const double* Ut = q.U + (size_t)blockIdx.x * Lc * np;
-  const int stage_doubles = KC * x_pitch(np);
+  const CUtensorMap* tmOld = q.tmaps + (q.sbuf ? TM_S1 : TM_S0);
+  const CUtensorMap* tmNew = q.tmaps + (q.sbuf ? TM_S0 : TM_S1);
+  const CUtensorMap* tmUt = q.tmaps + TM_UT;
+  const int sdoubles = stage_doubles_for(np);
   size_t off = 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * NSTAGE * sizeof(uint64_t));
   double* Wd = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB * WD_PITCH;
   double* dsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;    // pivots d_j
   double* sdsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;   // sqrt(d_j)
-  double* red = reinterpret_cast<double*>(smraw + off); off = align16(off + sizeof(double) * 40);
+  double* red = reinterpret_cast<double*>(smraw + off); off = (off + sizeof(double) * 40 + 127) & ~(size_t)127;
   double* Xs = reinterpret_cast<double*>(smraw + off);  // ring: NSTAGE stages, aliased by the panel Cp
   double* Cp = Xs;
   uint32_t flags = 0;
@@ -791,29 +797,27 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   ring_init<NW>(ring, bars);
   double gmax = -1.0e300, zmax = 0.0, tmax = 0.0;
   // optional phase timing (thread 0 of every CTA): K loop / barrier skew / panel store / factor / write-out
-  const bool timing = (q.dbg != nullptr) && tid == 0;
+  const bool timing = TIMING && (q.dbg != nullptr) && tid == 0;
   long long tph[6] = {0, 0, 0, 0, 0, 0};
+  long long tkl[6] = {0, 0, 0, 0, 0, 0};
   long long tlast = timing ? clock64() : 0;
-#define SRUKF_TICK(i) if (timing) { long long tnow_ = clock64(); tph[i] += tnow_ - tlast; tlast = tnow_; }
+#define SRUKF_TICK(i) if (TIMING && timing) { long long tnow_ = clock64(); tph[i] += tnow_ - tlast; tlast = tnow_; }
 
   for (int J0 = 0; J0 < np; J0 += NB) {
     const int nbe = (np - J0 < NB) ? (np - J0) : NB;
     const int R = np - J0;
     const int nt = nbe / 8;
-    const int pitch = x_pitch(R);
+    const int nbx = ntiles(R);         // TMA boxes per chunk
     const int nstrip = R / 8;
     const int nq_w = (nstrip > warp) ? (nstrip - warp - 1) / NW + 1 : 0;
-    const bool regular = (nt == NB / 8);
     // K rows per pipeline stage: as many 8-row blocks as fit the fixed stage size (8 rows at full width), so the
     // DMMA work and the bytes in flight per mbarrier round trip stay roughly constant as the panel narrows
-    int rpc = (stage_doubles / pitch) & ~7;
+    int rpc = (sdoubles / (nbx * TP)) & ~7;
     if (rpc > 32) rpc = 32;
-    // chunk list: [A1: S_old rows 0..J0+7 | A2: S_old rows inside the diagonal block, 8 at a time |
-    //              B: Ut rows | C: finished S_new rows 0..J0-1]
-    const int rowsA1 = J0 + 8, rowsB = Lc, rowsC = J0;
-    const int cA1 = (rowsA1 + rpc - 1) / rpc, cA2 = nt - 1, cB = (rowsB + rpc - 1) / rpc, cC = (rowsC + rpc - 1) / rpc;
-    const int nA = cA1 + cA2;
-    const int nchunks = nA + cB + cC;
+    // chunk list: [A: S_old rows 0..J0+nbe-1 | B: Ut rows | C: finished S_new rows 0..J0-1]
+    const int rowsA = J0 + nbe, rowsB = Lc, rowsC = J0;
+    const int cA = (rowsA + rpc - 1) / rpc, cB = (rowsB + rpc - 1) / rpc, cC = (rowsC + rpc - 1) / rpc;
+    const int nchunks = cA + cB + cC;
     double acc[MAXQ][NB / 8][2];
 #pragma unroll
     for (int qq = 0; qq < MAXQ; ++qq)
@@ -822,51 +826,36 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
 
     // rows of chunk t: first row (within its source) and count
     auto chunk_rows = [&](int t, int& row0) -> int {
-      if (t < cA1) { row0 = t * rpc; return (rowsA1 - row0 < rpc) ? rowsA1 - row0 : rpc; }
-      if (t < nA) { row0 = rowsA1 + 8 * (t - cA1); return 8; }
-      if (t < nA + cB) { row0 = (t - nA) * rpc; return (rowsB - row0 < rpc) ? rowsB - row0 : rpc; }
-      row0 = (t - nA - cB) * rpc;
+      if (t < cA) { row0 = t * rpc; return (rowsA - row0 < rpc) ? rowsA - row0 : rpc; }
+      if (t < cA + cB) { row0 = (t - cA) * rpc; return (rowsB - row0 < rpc) ? rowsB - row0 : rpc; }
+      row0 = (t - cA - cB) * rpc;
       return (rowsC - row0 < rpc) ? rowsC - row0 : rpc;
     };
-    auto produce = [&](int t) {  // every warp copies rows warp, warp+NW, .. of the chunk
+    auto produce = [&](int t) {  // thread 0: nbx tensor copies of [nrows x 72] from column J0 + 64 j
       int row0;
       const int nrows = chunk_rows(t, row0);
-      const int st = ring_acquire(ring);
-      double* sdst = Xs + (size_t)st * stage_doubles;
-      for (int rr = warp; rr < nrows; rr += NW) {
-        const int k = row0 + rr;
-        const double* src;
-        int dcol = 0, len = R;
-        if (t < nA) {              // S_old row k (stored from column 8*floor(k/8))
-          const int kb = (k >> 3) << 3;
-          if (kb <= J0) src = Sold + bp_row_off(k, np) + (J0 - kb);
-          else { src = Sold + bp_row_off(k, np); dcol = kb - J0; len = np - kb; }  // left part is never read
-        } else if (t < nA + cB) {
-          src = Ut + (size_t)k * np + J0;
-        } else {
-          src = Snew + bp_row_off(k, np) + (J0 - ((k >> 3) << 3));
-        }
-        warp_copy_row(sdst + (size_t)rr * pitch + dcol, src, len, lane);
-      }
-      ring_commit(ring, st);
+      long long tk0 = (TIMING && timing) ? clock64() : 0;
+      const int st = ring_acquire(ring, (uint32_t)(nbx * nrows * TP * sizeof(double)));
+      if (TIMING && timing) { long long t1_ = clock64(); tkl[0] += t1_ - tk0; tk0 = t1_; }
+      const CUtensorMap* tm = ((t < cA) ? tmOld : (t < cA + cB) ? tmUt : tmNew) + (nrows / 8 - 1);
+      const int c2 = (t >= cA && t < cA + cB) ? (int)blockIdx.x : b;
+      double* dst = Xs + (size_t)st * sdoubles;
+      for (int j = 0; j < nbx; ++j) tma_load_3d(dst + (size_t)j * nrows * TP, tm, J0 + TW * j, row0, c2, ring.full + st);
+      if (TIMING && timing) { tkl[1] += clock64() - tk0; }
     };
     auto consume = [&](int t0, int t1) {
       for (int t = t0; t < t1; ++t) {
-        if (t + NSTAGE - 1 < nchunks) produce(t + NSTAGE - 1);
+        if (tid == 0 && t + NSTAGE - 1 < nchunks) produce(t + NSTAGE - 1);
         int row0;
         const int nrows = chunk_rows(t, row0);
+        long long tk0 = (TIMING && timing) ? clock64() : 0;
         const int st = ring_wait(ring);
-        const double* xs_ = Xs + (size_t)st * stage_doubles;
-        if (p.dbg_skip_mma) {
-        } else if (t >= cA1 && t < nA) {   // rows inside the diagonal block: only strips/tiles at or right of them
-          const int kq = t - cA1 + 1;
-          mma_chunk_pred<NW>(acc, xs_, pitch, nstrip, kq, kq, nt, 2, lane, warp);
-        } else if (regular) {
-          mma_chunk_rt<NW, NB / 8>(acc, 0, nq_w, xs_, pitch, 0, xs_, pitch, nrows / 4, lane, warp);
-        } else {
-          mma_chunk_pred<NW>(acc, xs_, pitch, nstrip, 0, 0, nt, nrows / 4, lane, warp);
-        }
+        if (TIMING && timing) { long long t1_ = clock64(); tkl[2] += t1_ - tk0; tk0 = t1_; }
+        const double* xs_ = Xs + (size_t)st * sdoubles;
+        if (!p.dbg_skip_mma) mma_chunk_any<NW>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nrows / 4, lane, warp);
+        if (TIMING && timing) { long long t1_ = clock64(); tkl[3] += t1_ - tk0; tk0 = t1_; }
         ring_release(ring);
+        if (TIMING && timing) { tkl[4] += clock64() - tk0; tkl[5] += 1; }
       }
     };
     auto negate = [&]() {
@@ -875,10 +864,13 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
 #pragma unroll
         for (int t = 0; t < NB / 8; ++t) { acc[qq][t][0] = -acc[qq][t][0]; acc[qq][t][1] = -acc[qq][t][1]; }
     };
-    for (int t = 0; t < NSTAGE - 1 && t < nchunks; ++t) produce(t);
-    consume(0, nA);          // + S_old^T S_old
+    if (tid == 0) {
+      fence_proxy_async();  // the ring aliases the previous panel's Cp (generic-proxy stores)
+      for (int t = 0; t < NSTAGE - 1 && t < nchunks; ++t) produce(t);
+    }
+    consume(0, cA);          // + S_old^T S_old
     negate();
-    consume(nA, nA + cB);    // acc = -(S^T S - U U^T) = -G(i, J)
+    consume(cA, cA + cB);    // acc = -(S^T S - U U^T) = -G(i, J)
     // track max diag / max off-diag of G for beta^2 (:2204-2205)
 #pragma unroll
     for (int qq = 0; qq < MAXQ; ++qq) {
@@ -901,7 +893,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
         }
       }
     }
-    consume(nA + cB, nchunks);  // + S_new^T S_new
+    consume(cA + cB, nchunks);  // + S_new^T S_new
     negate();                   // acc = C(i, J)
     SRUKF_TICK(0)
     __syncthreads();            // every warp is done with the ring: reuse it as the panel
@@ -924,29 +916,31 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     SRUKF_TICK(2)
     factor_panel<NW>(Cp, Wd, dsm, sdsm, R, nbe, J0, n, p.epsilon, flags);
     SRUKF_TICK(3)
-    // ---- rows J0.. of S_new: S_new(J0+j, J0+i) = sd_j L(i,j) for i > j, sd_j on the diagonal, explicit zeros
-    //      left of the diagonal inside the row's stored range (blocked-packed layout) ----
+    // ---- rows J0.. of S_new: S_new(J0+j, J0+i) = sd_j L(i,j) for i > j, sd_j on the diagonal
+    //      (entries left of the diagonal are zero in both S buffers and are never written) ----
     for (int i = tid; i < R; i += NTH) {
       const double* crow = Cp + (size_t)i * CP_PITCH;
-      const int col = J0 + i;
-      for (int j = 0; j < nbe; ++j) {
-        const int row = J0 + j, rb = (row >> 3) << 3;
-        if (col >= rb) {
-          const double sdj = sdsm[j];
-          const double v = (i == j) ? sdj : ((i > j) ? sdj * crow[j] : 0.0);
-          Snew[bp_row_off(row, np) + (col - rb)] = v;
-          if (i > j && col < n) tmax = fmax(tmax, v * v);
-        }
+      double* dcol = Snew + (size_t)J0 * np + J0 + i;
+      const int jmax = (i < nbe - 1) ? i : nbe - 1;
+      const bool real = (J0 + i < n);
+      for (int j = 0; j <= jmax; ++j) {
+        const double sdj = sdsm[j];
+        const double v = (i == j) ? sdj : sdj * crow[j];
+        dcol[(size_t)j * np] = v;
+        if (i > j && real) tmax = fmax(tmax, v * v);
       }
     }
     SRUKF_TICK(4)
-    __syncthreads();  // S_new rows of this panel are visible to the next panel's loads; Cp is free
+    fence_proxy_async();  // this panel's generic-proxy smem/global accesses precede the next panel's tensor copies
+    __syncthreads();      // S_new rows of this panel are visible to the next panel's loads; Cp is free
     SRUKF_TICK(5)
   }
-  if (timing) {
+  if (TIMING && timing) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) atomicAdd(q.dbg + i, (unsigned long long)tph[i]);
     atomicAdd(q.dbg + 7, 1ull);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) atomicAdd(q.dbg + 8 + i, (unsigned long long)tkl[i]);
   }
 #undef SRUKF_TICK
   // ---- GMW guard: theta_j^2/beta^2 would have raised a pivot iff max S_new(j,i)^2 > beta^2 -------------
@@ -1025,7 +1019,7 @@ __device__ void form_G(const DevParams& p, const double* __restrict__ S, const d
     for (int i = j + lane; i < n; i += 32) {
       double acc = 0.0;
       for (int k = 0; k <= j; ++k) {
-        const double* row = S + bp_row_off(k, np) - ((k >> 3) << 3);
+        const double* row = S + (size_t)k * np;
         acc += row[j] * row[i];
       }
       double sub = 0.0;
@@ -1091,21 +1085,20 @@ __global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mo
 // -------------------------------------------------------------------------------------------------
 // auxiliary kernels
 // -------------------------------------------------------------------------------------------------
-// external formats <-> internal blocked-packed S.  fmt 0: dense [nb][n][n] row-major, fmt 1: upper-packed [nb][ntri]
+// external formats <-> internal square S.  fmt 0: dense [nb][n][n] row-major, fmt 1: upper-packed [nb][ntri]
 __global__ void k_import(int n, int np, int ntri, int nbp, int fmt, const double* __restrict__ ext,
                          double* __restrict__ bp) {
   const int b = blockIdx.x;
   double* dst = bp + (size_t)b * nbp;
   for (int k = 0; k < np; ++k) {
-    const int rb = (k >> 3) << 3;
-    double* row = dst + bp_row_off(k, np);
-    for (int c = rb + threadIdx.x; c < np; c += blockDim.x) {
+    double* row = dst + (size_t)k * np;
+    for (int c = threadIdx.x; c < np; c += blockDim.x) {
       double v = 0.0;
       if (k < n && c < n && c >= k)
         v = fmt ? ext[(size_t)b * ntri + tri_off(k, n) + (c - k)] : ext[((size_t)b * n + k) * n + c];
       else if (k >= n && c == k)
         v = 1.0;
-      row[c - rb] = v;
+      row[c] = v;
     }
   }
 }
@@ -1210,14 +1203,14 @@ size_t predict_smem_bytes(const DevParams& p) {
 size_t gain_smem_bytes(const DevParams& p) {
   size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
   off += sizeof(double) * 8 * (p.Lc / 2);
-  off = align16(off + sizeof(int) * (p.L + 1));
-  return off + sizeof(double) * (size_t)NSTAGE * KC * (x_pitch(p.np) + NB + 8);
+  off = (off + sizeof(int) * (p.L + 1) + 127) & ~(size_t)127;
+  return off + sizeof(double) * (size_t)NSTAGE * (stage_doubles_for(p.np) + KC * BP_B);
 }
 size_t update_smem_bytes(const DevParams& p) {
   size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
-  off += sizeof(double) * (NB * (NB + 1) + 2 * NB);
-  off = align16(off + sizeof(double) * 40);
-  size_t ring = (size_t)NSTAGE * KC * x_pitch(p.np);  // stage size is fixed: 8 rows at full width
+  off += sizeof(double) * (NB * WD_PITCH + 2 * NB);
+  off = (off + sizeof(double) * 40 + 127) & ~(size_t)127;
+  size_t ring = (size_t)NSTAGE * stage_doubles_for(p.np);  // stage size is fixed: 8 rows at full width
   size_t panel = (size_t)p.np * CP_PITCH;
   return off + sizeof(double) * (ring > panel ? ring : panel);
 }
@@ -1232,8 +1225,10 @@ cudaError_t configure_kernels(const DevParams& p) {
   int gs = (int)gain_smem_bytes(p), us = (int)update_smem_bytes(p);
   if ((e = cudaFuncSetAttribute(k_gain<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
   if ((e = cudaFuncSetAttribute(k_gain<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
-  if ((e = cudaFuncSetAttribute(k_update<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
-  if ((e = cudaFuncSetAttribute(k_update<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
+  if ((e = cudaFuncSetAttribute(k_update<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
+  if ((e = cudaFuncSetAttribute(k_update<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
+  if ((e = cudaFuncSetAttribute(k_update<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
+  if ((e = cudaFuncSetAttribute(k_update<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
   if ((e = cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)downdate_smem_bytes(p))))
     return e;
   return cudaSuccess;
@@ -1251,8 +1246,14 @@ void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_
   else k_gain<16><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q);
 }
 void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
-  if (tile_warps(p) == 8) k_update<8><<<nblocks, 256, update_smem_bytes(p), st>>>(p, q);
-  else k_update<16><<<nblocks, 512, update_smem_bytes(p), st>>>(p, q);
+  const bool timing = q.dbg != nullptr;
+  if (tile_warps(p) == 8) {
+    if (timing) k_update<8, true><<<nblocks, 256, update_smem_bytes(p), st>>>(p, q);
+    else k_update<8, false><<<nblocks, 256, update_smem_bytes(p), st>>>(p, q);
+  } else {
+    if (timing) k_update<16, true><<<nblocks, 512, update_smem_bytes(p), st>>>(p, q);
+    else k_update<16, false><<<nblocks, 512, update_smem_bytes(p), st>>>(p, q);
+  }
 }
 void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, int use_worklist, cudaStream_t st) {
   k_downdate<<<nblocks, NT, downdate_smem_bytes(p), st>>>(p, q, mode, use_worklist);

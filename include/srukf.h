@@ -113,8 +113,9 @@ int srukf_launch_count(srukf_t *h, uint64_t *count);
 int srukf_set_profiling(srukf_t *h, int on);
 int srukf_get_kernel_times(srukf_t *h, double *ms3, uint64_t *launches3);
 /* Diagnostics: cumulative SM cycles spent by k_update's CTAs in {K loop, post-K barrier, panel store, diagonal
- * block, solve, end barrier, -, #CTAs}; only when the handle was created with SRUKF_PHASE_TIMING=1 in the env. */
-int srukf_get_phase_cycles(srukf_t *h, uint64_t *out8);
+ * block, solve, end barrier, -, #CTAs} and, in out[8..13], inside the K loop {stage acquire, copy issue, data wait,
+ * DMMA, release, #chunks}; only when the handle was created with SRUKF_PHASE_TIMING=1 in the env.  out has 16 slots. */
+int srukf_get_phase_cycles(srukf_t *h, uint64_t *out16);
 const char *srukf_last_error(void);
 const char *srukf_version(void);
 

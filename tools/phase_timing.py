@@ -12,7 +12,7 @@ g.set_state(sc.x0, sc.S0)
 for s in range(3):
     g.SLAM(sc.u[s], sc.z[s], sc.matched[s])
 g.sync()
-out = np.zeros(8, dtype=np.uint64)
+out = np.zeros(16, dtype=np.uint64)
 capi.check(g._lib.srukf_get_phase_cycles(g._h, capi.ptr(out)))
 n = float(out[7])
 names = ["K loop", "post-K barrier", "panel store+sync", "factor panel", "write S_new", "end barrier"]
@@ -20,3 +20,8 @@ tot = float(out[:6].sum())
 for nm, v in zip(names, out[:6]):
     print(f"{nm:18s} {float(v)/n:12.0f} cycles/filter  {100*float(v)/tot:5.1f}%")
 print(f"total {tot/n:.0f} cycles per filter-update ({int(n)} CTAs)")
+kn = ["acquire (empty wait)", "copy issue", "data wait (full)", "DMMA", "release"]
+nch = float(out[13]) / n
+for nm, v in zip(kn, out[8:13]):
+    print(f"  K loop / {nm:22s} {float(v)/n:12.0f} cycles/filter   {float(v)/max(float(out[13]),1):8.0f} per chunk")
+print(f"  chunks per filter {nch:.0f}")
