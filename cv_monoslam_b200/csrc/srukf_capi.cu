@@ -139,6 +139,7 @@ static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
   d.cam_dx = s.cam_dx; d.cam_dy = s.cam_dy; d.cam_cx = s.cam_cx; d.cam_cy = s.cam_cy;
   d.cam_k1 = s.cam_k1; d.cam_k2 = s.cam_k2;
   d.f1 = s.cam_f / s.cam_dx; d.f2 = s.cam_f / s.cam_dy;  // SLAM.cpp:336-337
+  d.inv_dx = 1.0 / s.cam_dx; d.inv_dy = 1.0 / s.cam_dy;
   d.img_w = s.image_width; d.img_h = s.image_height;
   d.a1 = s.a1; d.a2 = s.a2; d.a3 = s.a3; d.a4 = s.a4; d.sigma_measure = s.sigma_measure;
   d.epsilon = s.epsilon; d.newton_iters = s.newton_iters;

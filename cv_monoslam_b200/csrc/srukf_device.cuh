@@ -19,6 +19,7 @@ struct DevParams {
   int nbp;   // doubles per filter in the internal layout of S (np * np)
   // camera (SLAM.cpp:329-337)
   double cam_dx, cam_dy, cam_cx, cam_cy, cam_k1, cam_k2, f1, f2;
+  double inv_dx, inv_dy;  // 1/cam_dx, 1/cam_dy
   double img_w, img_h;
   // noise (SLAM.cpp:195-198, 238)
   double a1, a2, a3, a4, sigma_measure;
@@ -107,33 +108,34 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// distortOnePointRW, SLAM.cpp:3177-3213.  The Newton loop (fixed 100 iterations in the reference)
-// exits once the step no longer changes rd; the fixed point is the same to < 1 ulp.
+// distortOnePointRW, SLAM.cpp:3177-3213.
+// The reference solves rd + k1 rd^3 + k2 rd^5 = ru by 100 Newton steps and returns c + (xu/d)/dx with
+// d = 1 + k1 rd^2 + k2 rd^4.  The same root is found here for t = rd/ru = 1/d directly:
+//     t (1 + a t^2 + b t^4) = 1,   a = k1 ru^2,  b = k2 ru^4
+// which needs no square root and no division (Newton with the derivative's reciprocal replaced by its
+// first-order expansion 2 - f'; it converges to the same fixed point, to rounding).  The loop stops when the
+// step is below one ulp (the reference's fixed 100 iterations sit on that fixed point).  |result - reference|
+// is a few ulp of the pixel coordinate.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void distort_point(const DevParams& p, double ux, double uy, double& ox, double& oy,
                                               uint32_t& flags) {
-  const double k1 = p.cam_k1, k2 = p.cam_k2;
-  double xu = (ux - p.cam_cx) * p.cam_dx;
-  double yu = (uy - p.cam_cy) * p.cam_dy;
-  double ru = sqrt(xu * xu + yu * yu);
-  double ru2 = ru * ru;
-  double rd = ru / (1 + k1 * ru2 + k2 * (ru2 * ru2));
+  const double xu = (ux - p.cam_cx) * p.cam_dx;
+  const double yu = (uy - p.cam_cy) * p.cam_dy;
+  const double ru2 = xu * xu + yu * yu;
+  const double a = p.cam_k1 * ru2, bq = p.cam_k2 * (ru2 * ru2);
+  double t = 1.0 - a - bq;
   for (int it = 0; it < p.newton_iters; ++it) {
-    double rd2 = rd * rd;
-    double f = rd + k1 * (rd2 * rd) + k2 * (rd2 * rd2 * rd) - ru;
-    double ff = 1.0 + 3.0 * k1 * rd2 + 5.0 * k2 * (rd2 * rd2);
-    double nrd = rd - f / ff;
-    bool done = (nrd == rd);
-    rd = nrd;
+    const double t2 = t * t;
+    const double g = a * t2 + bq * (t2 * t2);
+    const double f = fma(t, g, t - 1.0);
+    const double ff = 1.0 + 3.0 * a * t2 + 5.0 * bq * (t2 * t2);
+    const double nt = fma(-f, 2.0 - ff, t);
+    const bool done = fabs(nt - t) <= 1.2e-16;
+    t = nt;
     if (done) break;
   }
-  double rd2 = rd * rd;
-  double d = 1 + k1 * rd2 + k2 * (rd2 * rd2);
-  if (d == 0) d = p.epsilon;
-  double xd = xu / d;
-  double yd = yu / d;
-  ox = p.cam_cx + xd / p.cam_dx;
-  oy = p.cam_cy + yd / p.cam_dy;
+  ox = p.cam_cx + (xu * t) * p.inv_dx;
+  oy = p.cam_cy + (yu * t) * p.inv_dy;
   bool vis = (ox >= 0) && (ox <= p.img_w) && (oy >= 0) && (oy <= p.img_h);
   if (!vis) {
     ox = 0;
@@ -143,34 +145,25 @@ __device__ __forceinline__ void distort_point(const DevParams& p, double ux, dou
 }
 
 // ---------------------------------------------------------------------------------------------
-// One sigma-point projection of one feature:
-//   coordinatesState2World :3250-3276, World2Camera :3289-3292 with Rcw = Rwc.inv() (:1642-1643,
-//   OpenCV closed-form 3x3 inverse = adj/det), Camera2Image :3324-3347 (x/y swap kept), distortion.
-// (cth, sth) = cos/sin of the robot heading of this sigma point; (e0, e1) its pixel-noise components.
+// World-frame ray (hx,hy,hz) = feature point - robot position  ->  distorted pixel:
+//   World2Camera :3289-3292 with Rcw = Rwc.inv() (:1642-1643, OpenCV closed-form 3x3 inverse = adj/det; the
+//   three distinct entries cd = c/det, sd = s/det, zd = det/det are precomputed per sigma point),
+//   Camera2Image :3324-3347 (x/y swap kept), distortion.  (e0, e1) = pixel-noise components of the sigma point.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void project_feature(const DevParams& p, double xi, double yi, double zi, double theta,
-                                                double phi, double rho, double rx, double ry, double rz, double cth,
-                                                double sth, double e0, double e1, double& ox, double& oy,
-                                                uint32_t& flags) {
-  double sphi, cphi, sthe, cthe;
-  sincos(phi, &sphi, &cphi);
-  sincos(theta, &sthe, &cthe);
-  double ir = 1 / rho;
-  double hx = xi + ir * cphi * sthe - rx;
-  double hy = yi - ir * sphi - ry;
-  double hz = zi + ir * cphi * cthe - rz;
-  double det = cth * cth + sth * sth;
-  double dinv = 1.0 / det;
-  double rxx = (cth * dinv) * hx + (sth * dinv) * hy;
-  double ryy = (-sth * dinv) * hx + (cth * dinv) * hy;
-  double rzz = (det * dinv) * hz;
+__device__ __forceinline__ void pixel_from_ray(const DevParams& p, double hx, double hy, double hz, double cd,
+                                               double sd, double zd, double e0, double e1, double& ox, double& oy,
+                                               uint32_t& flags) {
+  const double rxx = cd * hx + sd * hy;
+  const double ryy = -sd * hx + cd * hy;
+  const double rzz = zd * hz;
   double ux, uy;
   if (rzz == 0) {
     ux = 0;
     uy = 0;
   } else {
-    uy = p.cam_cx + p.f1 * rxx / rzz + e0;
-    ux = p.cam_cy + p.f2 * ryy / rzz + e1;
+    const double r = 1.0 / rzz;
+    uy = p.cam_cx + (p.f1 * rxx) * r + e0;
+    ux = p.cam_cy + (p.f2 * ryy) * r + e1;
     if (ux < 10 || ux > p.img_w - 10 || uy < 10 || uy > p.img_h - 10) {
       ux = 0;
       uy = 0;
@@ -178,6 +171,33 @@ __device__ __forceinline__ void project_feature(const DevParams& p, double xi, d
     }
   }
   distort_point(p, ux, uy, ox, oy, flags);
+}
+
+// sin/cos of (a0 + d) and (a0 - d) from sin/cos(a0): angle addition with a degree-11/12 Taylor series of the
+// small perturbation d = gamma * S(k, col) (the +- sigma points share it); full sincos for |d| >= 1/8.
+__device__ __forceinline__ void sincos_pm(double a0, double s0, double c0, double d, double& sp, double& cp, double& sm,
+                                          double& cm) {
+  if (fabs(d) < 0.125) {
+    const double d2 = d * d;
+    double sd = fma(d2, -1.0 / 110.0, 1.0);
+    sd = fma(d2 * (-1.0 / 72.0), sd, 1.0);
+    sd = fma(d2 * (-1.0 / 42.0), sd, 1.0);
+    sd = fma(d2 * (-1.0 / 20.0), sd, 1.0);
+    sd = fma(d2 * (-1.0 / 6.0), sd, 1.0) * d;
+    double cd = fma(d2, -1.0 / 132.0, 1.0);
+    cd = fma(d2 * (-1.0 / 90.0), cd, 1.0);
+    cd = fma(d2 * (-1.0 / 56.0), cd, 1.0);
+    cd = fma(d2 * (-1.0 / 30.0), cd, 1.0);
+    cd = fma(d2 * (-1.0 / 12.0), cd, 1.0);
+    cd = fma(d2 * (-0.5), cd, 1.0);
+    sp = fma(s0, cd, c0 * sd);
+    cp = fma(c0, cd, -s0 * sd);
+    sm = fma(s0, cd, -c0 * sd);
+    cm = fma(c0, cd, s0 * sd);
+  } else {
+    sincos(a0 + d, &sp, &cp);
+    sincos(a0 - d, &sm, &cm);
+  }
 }
 
 // deterministic block reductions (fixed tree order => run-to-run and 1-vs-N-GPU bit identical)

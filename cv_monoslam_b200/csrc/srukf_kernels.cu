@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
   const int b = q.chunk0 + blockIdx.x;
   const int n = p.n, nf = p.nf, Na = p.Na, P = p.P, L = p.L;
   double* xs = sm;                 // n
-  double* rs = xs + n;             // P x 6 : rx ry rz rtheta cos sin
-  double* z0 = rs + (size_t)P * 6; // 2L
+  double* rs = xs + n;             // P x 8 : rx ry rz rtheta c/det s/det det/det -
+  double* z0 = rs + (size_t)P * 8; // 2L
   double* red = z0 + 2 * L;        // 40
   double* work = red + 40;         // max((n+10)*4, slots*13)
   double* xg = q.x + (size_t)b * n;
@@ -143,16 +143,17 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
       double ry = by + trans * sn;
       double rz = bz + 0;
       double rt = bt + (rot1 + rot2);
-      double* r = rs + (size_t)i * 6;
+      double* r = rs + (size_t)i * 8;
       r[0] = rx; r[1] = ry; r[2] = rz; r[3] = rt;
       sincos(rt, &sn, &cs);
-      r[4] = cs; r[5] = sn;
+      const double det = cs * cs + sn * sn, dinv = 1.0 / det;  // Rwc.inv() = adj/det, :1643
+      r[4] = cs * dinv; r[5] = sn * dinv; r[6] = det * dinv;
     }
     __syncthreads();
     // robot mean, :1526-1531: wm0*r0 + wi*sum r_i == Wsum*r0 + wi*sum (r_i - r0)
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     for (int i = 1 + tid; i < P; i += NT) {
-      const double* r = rs + (size_t)i * 6;
+      const double* r = rs + (size_t)i * 8;
       a0 += r[0] - rs[0]; a1 += r[1] - rs[1]; a2 += r[2] - rs[2]; a3 += r[3] - rs[3];
     }
     a0 = block_sum<NT>(a0, red); a1 = block_sum<NT>(a1, red);
@@ -169,8 +170,8 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
     double* T = work;  // (n + 10) x 4
     const double hs = p.wi_sr * 0.70710678118654752440;  // wi_sr / sqrt(2)
     for (int k = tid; k < n; k += NT) {
-      const double* rp = rs + (size_t)(k + 1) * 6;
-      const double* rm = rs + (size_t)(Na + k + 1) * 6;
+      const double* rp = rs + (size_t)(k + 1) * 8;
+      const double* rm = rs + (size_t)(Na + k + 1) * 8;
       double e[4], s[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
     }
     if (tid < 6) {  // control-noise pairs n..n+2 (pixel-noise pairs have zero robot deviation)
       int k = n + tid / 2;
-      const double* r = rs + (size_t)((tid & 1) ? (Na + k + 1) : (k + 1)) * 6;
+      const double* r = rs + (size_t)((tid & 1) ? (Na + k + 1) : (k + 1)) * 8;
 #pragma unroll
       for (int c = 0; c < 4; ++c) T[(4 + n + tid) * 4 + c] = p.wi_sr * (r[c] - rs[c]);
     }
@@ -202,33 +203,27 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
     }
     if (save_rsig) {
       double* rg = q.rsig + (size_t)b * P * 4;
-      for (int i = tid; i < P * 4; i += NT) rg[i] = rs[(size_t)(i >> 2) * 6 + (i & 3)];
+      for (int i = tid; i < P * 4; i += NT) rg[i] = rs[(size_t)(i >> 2) * 8 + (i & 3)];
     }
     __syncthreads();
   } else {
     const double* rg = q.rsig + (size_t)b * P * 4;
     for (int i = tid; i < P; i += NT) {
-      double* r = rs + (size_t)i * 6;
+      double* r = rs + (size_t)i * 8;
       r[0] = rg[i * 4 + 0]; r[1] = rg[i * 4 + 1]; r[2] = rg[i * 4 + 2]; r[3] = rg[i * 4 + 3];
       double sn, cs;
       sincos(r[3], &sn, &cs);
-      r[4] = cs; r[5] = sn;
+      const double det = cs * cs + sn * sn, dinv = 1.0 / det;
+      r[4] = cs * dinv; r[5] = sn * dinv; r[6] = det * dinv;
     }
     __syncthreads();
   }
 
   if (MEAS) {
     const double gsm = p.gamma * p.sigma_measure;  // Qt = I2*sigma_measure enters as a sqrt block (:1462)
-    // sigma point 0
-    for (int j = tid; j < L; j += NT) {
-      const double* f = xs + 6 * j;
-      double ox, oy;
-      project_feature(p, f[0], f[1], f[2], f[3], f[4], f[5], rs[0], rs[1], rs[2], rs[4], rs[5], 0.0, 0.0, ox, oy,
-                      flags);
-      z0[2 * j] = ox;
-      z0[2 * j + 1] = oy;
-    }
-    __syncthreads();
+    // per slot (g, j): feature j's mean direction and world point (State2World :3250-3276), sigma point 0,
+    // then the sigma pairs k = g, g+G, ..  For pairs that do not touch feature j's own six entries
+    // (k > 6j+5: S is upper triangular) only the robot pose moves and the world point is reused.
     const int G = (L <= NT) ? NT / L : 1;
     double* acc = work;  // [G*L][13]
     const int Lc = p.Lc;
@@ -236,25 +231,38 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
     for (int slot = tid; slot < G * L; slot += NT) {
       const int g = slot / L, j = slot - g * L;
       const double* f = xs + 6 * j;
-      const double zx0 = z0[2 * j], zy0 = z0[2 * j + 1];
+      double sth0, cth0, sph0, cph0;
+      sincos(f[3], &sth0, &cth0);
+      sincos(f[4], &sph0, &cph0);
+      const double ir0 = 1 / f[5];
+      const double pwx = f[0] + ir0 * cph0 * sth0, pwy = f[1] - ir0 * sph0, pwz = f[2] + ir0 * cph0 * cth0;
+      double zx0, zy0;
+      pixel_from_ray(p, pwx - rs[0], pwy - rs[1], pwz - rs[2], rs[4], rs[5], rs[6], 0.0, 0.0, zx0, zy0, flags);
+      if (g == 0) { z0[2 * j] = zx0; z0[2 * j + 1] = zy0; }
       double sb0 = 0, sb1 = 0, s00 = 0, s01 = 0, s11 = 0;
       double sa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int k = g; k < Na; k += G) {
-        double s[6] = {0, 0, 0, 0, 0, 0};
-        if (k < nf && k <= 6 * j + 5) {
-#pragma unroll
-          for (int c = 0; c < 6; ++c) s[c] = S_at(Sg, np, k, 6 * j + c);
-        }
-        double e0 = (k == n + 3) ? gsm : 0.0, e1 = (k == n + 4) ? gsm : 0.0;
-        const double* rp = rs + (size_t)(k + 1) * 6;
-        const double* rm = rs + (size_t)(Na + k + 1) * 6;
+        const double e0 = (k == n + 3) ? gsm : 0.0, e1 = (k == n + 4) ? gsm : 0.0;
+        const double* rp = rs + (size_t)(k + 1) * 8;
+        const double* rm = rs + (size_t)(Na + k + 1) * 8;
         double px, py, mx, my;
-        project_feature(p, f[0] * 1 + s[0] * p.gamma, f[1] * 1 + s[1] * p.gamma, f[2] * 1 + s[2] * p.gamma,
-                        f[3] * 1 + s[3] * p.gamma, f[4] * 1 + s[4] * p.gamma, f[5] * 1 + s[5] * p.gamma, rp[0], rp[1],
-                        rp[2], rp[4], rp[5], e0, e1, px, py, flags);
-        project_feature(p, f[0] * 1 - s[0] * p.gamma, f[1] * 1 - s[1] * p.gamma, f[2] * 1 - s[2] * p.gamma,
-                        f[3] * 1 - s[3] * p.gamma, f[4] * 1 - s[4] * p.gamma, f[5] * 1 - s[5] * p.gamma, rm[0], rm[1],
-                        rm[2], rm[4], rm[5], -e0, -e1, mx, my, flags);
+        if (k <= 6 * j + 5) {   // (k < nf is implied) feature j's own entries are perturbed by +-gamma*S(k, 6j..6j+5)
+          const double* srow = Sg + (size_t)k * np + 6 * j;  // entries left of the diagonal are stored zeros
+          double dlt[6];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) dlt[c] = srow[c] * p.gamma;
+          double stp, ctp, stm, ctm, spp, cpp, spm, cpm;
+          sincos_pm(f[3], sth0, cth0, dlt[3], stp, ctp, stm, ctm);
+          sincos_pm(f[4], sph0, cph0, dlt[4], spp, cpp, spm, cpm);
+          const double irp = 1 / (f[5] * 1 + dlt[5]), irm = 1 / (f[5] * 1 - dlt[5]);
+          pixel_from_ray(p, (f[0] * 1 + dlt[0]) + irp * cpp * stp - rp[0], (f[1] * 1 + dlt[1]) - irp * spp - rp[1],
+                         (f[2] * 1 + dlt[2]) + irp * cpp * ctp - rp[2], rp[4], rp[5], rp[6], e0, e1, px, py, flags);
+          pixel_from_ray(p, (f[0] * 1 - dlt[0]) + irm * cpm * stm - rm[0], (f[1] * 1 - dlt[1]) - irm * spm - rm[1],
+                         (f[2] * 1 - dlt[2]) + irm * cpm * ctm - rm[2], rm[4], rm[5], rm[6], -e0, -e1, mx, my, flags);
+        } else {
+          pixel_from_ray(p, pwx - rp[0], pwy - rp[1], pwz - rp[2], rp[4], rp[5], rp[6], e0, e1, px, py, flags);
+          pixel_from_ray(p, pwx - rm[0], pwy - rm[1], pwz - rm[2], rm[4], rm[5], rm[6], -e0, -e1, mx, my, flags);
+        }
         if (k < nf) {
           dZ[(size_t)k * Lc + 2 * j] = px - mx;
           dZ[(size_t)k * Lc + 2 * j + 1] = py - my;
@@ -1198,7 +1206,7 @@ size_t predict_smem_bytes(const DevParams& p) {
   size_t work = slots * 13;
   size_t t4 = (size_t)(p.n + 10) * 4;
   if (t4 > work) work = t4;
-  return sizeof(double) * ((size_t)p.n + (size_t)p.P * 6 + 2 * (size_t)p.L + 40 + work);
+  return sizeof(double) * ((size_t)p.n + (size_t)p.P * 8 + 2 * (size_t)p.L + 40 + work);
 }
 size_t gain_smem_bytes(const DevParams& p) {
   size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
