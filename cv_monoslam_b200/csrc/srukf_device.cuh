@@ -96,6 +96,17 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, in
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// 1/d for d > 0 well inside the normal range: MUFU.RCP64H seed + two Newton steps (5 dependent FP64 ops instead of
+// the ~15 of an IEEE division), accurate to ~1 ulp.  Used on the pivot chain of the panel factorisation.
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
 // orders this thread's earlier generic-proxy accesses (shared AND global) before later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // 16-byte asynchronous global->shared copy (LDGSTS, L2 only) and its completion hook onto an mbarrier:

@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
 //   U  (all warps, DMMA)   C(:, sub) -= L(:, <sub) * W(sub rows, <sub)^T,  W = unscaled C of the diagonal rows
 //   D  (one warp, 8 lanes) 8x8 diagonal block: pivots, L = C/d (:2232), in-block updates (:2253) -- the only
 //                          sequential chain (8 pivots); 28 shuffle-FMAs in registers
-//   T  (one thread per row) rows below: C(i,j) -= sum_{k<j in sub} L(i,k) W(j,k), L(i,j) = C(i,j)/d_j
+//   T  (one thread per row) rows below: C(i,j) -= sum_{k<j in sub} L(i,k) W(j,k), L(i,j) = C(i,j) * (1/d_j)
 // Afterwards Cp holds L; S_new(j, i) = sqrt(d_j) L(i, j) (:2321) is written by the caller.
 // -------------------------------------------------------------------------------------------------
 template <int NW>
@@ -700,7 +700,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
       const double* myrow = Cp + (size_t)(c0 + li) * CP_PITCH + c0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) r[k] = myrow[k];
-      double dmine = 1.0, w[8];
+      double dmine = 1.0, rmine = 1.0, w[8];
       bool modified = false;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -708,7 +708,9 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
         const double d = fmax(eps, fabs(cjj));
         if (li == j) { dmine = d; modified = (d != cjj); }
         w[j] = r[j];
-        const double lij = r[j] / d;
+        const double rinv = fast_rcp(d);
+        if (li == j) rmine = rinv;
+        const double lij = r[j] * rinv;   // L(i,j) = C(i,j)/d_j (:2232), as a multiplication by 1/d_j
 #pragma unroll
         for (int k = j + 1; k < 8; ++k) {
           const double ckj = __shfl_sync(0xffffffffu, r[j], k);  // C(k,j), unscaled
@@ -718,7 +720,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
       }
       if (lane < 8) {
         const double sd = sqrt(dmine);
-        dsm[c0 + lane] = dmine;
+        dsm[c0 + lane] = rmine;   // 1/d_j for the solve of the rows below
         sdsm[c0 + lane] = sd;
         if (modified && J0 + c0 + lane < n) flags |= (dmine > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
         if (!isfinite(sd)) flags |= SRUKF_FLAG_NAN;
@@ -743,7 +745,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
 #pragma unroll
         for (int k = 0; k < j; ++k) a = fma(-l[k], wj[k], a);
         cf[j] = a;
-        l[j] = a / dsm[c0 + j];
+        l[j] = a * dsm[c0 + j];
       }
       if (i < nbe) {   // rows of the panel's own diagonal block feed later sub-panels as W
         double* wrow = Wd + (size_t)i * WD_PITCH + c0;
@@ -788,7 +790,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   size_t off = 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * NSTAGE * sizeof(uint64_t));
   double* Wd = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB * WD_PITCH;
-  double* dsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;    // pivots d_j
+  double* dsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;    // 1 / pivot d_j
   double* sdsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;   // sqrt(d_j)
   double* red = reinterpret_cast<double*>(smraw + off); off = (off + sizeof(double) * 40 + 127) & ~(size_t)127;
   double* Xs = reinterpret_cast<double*>(smraw + off);  // ring: NSTAGE stages, aliased by the panel Cp
