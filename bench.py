@@ -35,9 +35,10 @@ FP64_PEAK_TFLOPS = 37.2   # measured DMMA peak on this pool's B200 (profiles/r01
 # work model (DESIGN.md "Work per filter-step"): flops of the formulation that is actually executed
 # ------------------------------------------------------------------------------------------------------
 def flops_downdate(n: int, L: int) -> float:
-    """k_update: multiply-adds of G = S^T S - U U^T on the lower triangle plus its modified Cholesky (the fused
-    left-looking kernel performs the same products in panel order; padding and masked tiles are not counted)."""
-    form = sum((n - j) * ((j + 1) + 2 * L) * 2.0 for j in range(n))
+    """k_update: multiply-adds of G = P - U U^T on the lower triangle (P = S^T S is carried between steps, so the
+    reference's dense S^T S product is NOT counted) plus the modified Cholesky of G.  The fused left-looking kernel
+    performs these products in panel order; padding and masked tiles are not counted."""
+    form = n * (n + 1) / 2.0 * (2 * L) * 2.0
     mchol = sum((n - j - 1) * (n - j) / 2.0 * 2.0 + 3.0 * (n - j) for j in range(n))
     return form + mchol
 
@@ -50,7 +51,9 @@ def flops_gain(n: int, L: int) -> float:
 def flops_predict(n: int, L: int) -> float:
     Na = n + 5
     P = 2 * Na + 1
-    return 100.0 * P * L + 40.0 * P + 26.0 * 2 * Na * L   # projections (~100 flop each incl. sincos) + sums
+    nf = n - 4
+    # projections (~100 flop each incl. sincos) + sums + robot rows of the carried covariance (S_ff^T E_f)
+    return 100.0 * P * L + 40.0 * P + 26.0 * 2 * Na * L + nf * (nf + 1) / 2.0 * 4 * 2.0
 
 
 def algorithmic_bytes(n: int, L: int) -> float:

@@ -20,6 +20,7 @@ struct StepPtrs {
   double* dZ; double* U; double* G; uint32_t* flags; int chunk0;
   double* S2; int* worklist; int rel0; unsigned long long* dbg;
   const CUtensorMap* tmaps; int sbuf; int tm_dz; int dz_filter0;
+  double* Pd; double* Pd2; int carry_p;
 };
 // tensor-map table layout and box geometry (must match srukf_kernels.cu)
 constexpr int TM_S0 = 0, TM_S1 = 4, TM_UT = 8, TM_DZ = 12, TM_DZ_ALL = 13, TM_COUNT = 14;
@@ -36,6 +37,7 @@ void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStrea
 void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, int use_worklist, cudaStream_t st);
 void launch_import(const DevParams& p, int nb, int fmt, const double* ext, double* bp, cudaStream_t st);
 void launch_export(const DevParams& p, int nb, int fmt, const double* bp, double* ext, cudaStream_t st);
+void launch_form_P(const DevParams& p, int b0, int nb, double* S, double* Pd, cudaStream_t st);
 void launch_cov_block(const DevParams& p, const double* S, int r0, int nr, double* out, cudaStream_t st);
 void launch_stats(const DevParams& p, const double* x, const double* S, const double* truth, double* perf,
                   const uint32_t* flags, double* out, cudaStream_t st);
@@ -59,6 +61,7 @@ struct srukf_handle {
   // state: S lives in the internal square layout; k_update ping-pongs between the two buffers
   double *x = nullptr, *S = nullptr, *S2 = nullptr;   // S = current, S2 = the other one
   int sbuf = 0;                                       // index of the current buffer in the tensor-map table
+  double *Pd = nullptr, *Pd2 = nullptr;               // diagonals of the carried covariance (fused mode)
   CUtensorMap* tmaps = nullptr;                       // device table of TMA tensor maps
   // per-step inputs (device copies for the host-pointer API)
   double *u = nullptr, *z = nullptr; uint8_t* matched = nullptr;
@@ -244,6 +247,10 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   if (prm.downdate_mode == 0) {
     CUH(cudaMalloc(&h->S2, sizeof(double) * (size_t)B * p.nbp));
     CUH(cudaMemsetAsync(h->S2, 0, sizeof(double) * (size_t)B * p.nbp, h->stream));
+    CUH(cudaMalloc(&h->Pd, sizeof(double) * (size_t)B * p.np));
+    CUH(cudaMalloc(&h->Pd2, sizeof(double) * (size_t)B * p.np));
+    CUH(cudaMemsetAsync(h->Pd, 0, sizeof(double) * (size_t)B * p.np, h->stream));
+    CUH(cudaMemsetAsync(h->Pd2, 0, sizeof(double) * (size_t)B * p.np, h->stream));
   }
   CUH(cudaMalloc(&h->u, sizeof(double) * B * 3));
   CUH(cudaMalloc(&h->z, sizeof(double) * B * L2));
@@ -297,7 +304,7 @@ int srukf_destroy(srukf_t* h) {
   if (!h) return SRUKF_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+  void* ptrs[] = {h->Pd, h->Pd2, h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -313,6 +320,7 @@ static StepPtrs base_ptrs(srukf_t* h) {
   q.rsig = h->rsig; q.dZ = h->dZ; q.U = h->U; q.G = h->G; q.flags = h->flags; q.chunk0 = 0;
   q.S2 = h->S2; q.worklist = h->worklist; q.rel0 = 0; q.dbg = h->dbg;
   q.tmaps = h->tmaps; q.sbuf = h->sbuf; q.tm_dz = TM_DZ; q.dz_filter0 = 0;
+  q.Pd = h->Pd; q.Pd2 = h->Pd2; q.carry_p = (h->prm.downdate_mode == 0) ? 1 : 0;
   return q;
 }
 
@@ -330,7 +338,10 @@ static int transfer_S(srukf_t* h, int fmt, const double* src_host, double* dst_h
     cudaError_t e = cudaSuccess;
     if (src_host) {
       e = cudaMemcpyAsync(tmp, (const char*)src_host + per * b0, per * nb, cudaMemcpyHostToDevice, h->stream);
-      if (e == cudaSuccess) launch_import(p, nb, fmt, tmp, h->S + (size_t)b0 * p.nbp, h->stream);
+      if (e == cudaSuccess) {
+        launch_import(p, nb, fmt, tmp, h->S + (size_t)b0 * p.nbp, h->stream);
+        if (h->Pd) { launch_form_P(p, b0, nb, h->S, h->Pd, h->stream); h->launches++; }
+      }
     } else {
       launch_export(p, nb, fmt, h->S + (size_t)b0 * p.nbp, tmp, h->stream);
       e = cudaMemcpyAsync((char*)dst_host + per * b0, tmp, per * nb, cudaMemcpyDeviceToHost, h->stream);
@@ -459,7 +470,10 @@ static void run_update(srukf_t* h, StepPtrs q, int b0, int nb) {
 
 // after a fused update over the whole batch the roles of the two S buffers swap
 static void flip_buffers(srukf_t* h) {
-  if (h->prm.downdate_mode == 0) { double* t = h->S; h->S = h->S2; h->S2 = t; h->sbuf ^= 1; }
+  if (h->prm.downdate_mode == 0) {
+    double* t = h->S; h->S = h->S2; h->S2 = t; h->sbuf ^= 1;
+    t = h->Pd; h->Pd = h->Pd2; h->Pd2 = t;
+  }
 }
 
 int srukf_kalman_update(srukf_t* h, const double* z, const uint8_t* matched) {
@@ -522,6 +536,7 @@ int srukf_set_state_dev(srukf_t* h, int b0, int nb, const double* d_x, const dou
   if (d_S_packed) {
     launch_import(h->p, nb, 1, d_S_packed, h->S + (size_t)b0 * h->p.nbp, h->stream);
     h->launches++;
+    if (h->Pd) { launch_form_P(h->p, b0, nb, h->S, h->Pd, h->stream); h->launches++; }
   }
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());

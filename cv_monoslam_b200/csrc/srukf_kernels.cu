@@ -45,6 +45,12 @@ struct StepPtrs {
   int sbuf;                // which S buffer is "current" (q.S): 0 or 1
   int tm_dz;               // TM_DZ (chunk scratch) or TM_DZ_ALL (split API)
   int dz_filter0;          // first filter of this launch inside the dZ tensor
+  // Carried covariance (fused mode only): P = S^T S lives next to S -- strictly-lower part in the lower triangle
+  // of the same square buffer, diagonal in Pd -- so k_update starts each panel from P instead of re-forming
+  // S_old^T S_old (the motion step leaves the feature block of P unchanged and rewrites only the robot rows).
+  double* Pd;              // [B][np] diagonal of P belonging to q.S
+  double* Pd2;             // [B][np] ... belonging to q.S2
+  int carry_p;
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -167,7 +173,8 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
       xg[n - 4] = xs[n - 4]; xg[n - 3] = xs[n - 3]; xg[n - 2] = xs[n - 2]; xg[n - 1] = xs[n - 1];
     }
     // square-root factor: E rows and the stacked robot-only rows
-    double* T = work;  // (n + 10) x 4
+    double* T = work;                    // (n + 10) x 4
+    double* Ef = T + (size_t)(n + 10) * 4;  // nf x 4: new robot columns of the feature rows
     const double hs = p.wi_sr * 0.70710678118654752440;  // wi_sr / sqrt(2)
     for (int k = tid; k < n; k += NT) {
       const double* rp = rs + (size_t)(k + 1) * 8;
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
       if (k < nf) {
         double* row = Sg + bp_idx(k, nf, np);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) row[c] = e[c];
+        for (int c = 0; c < 4; ++c) { row[c] = e[c]; Ef[k * 4 + c] = e[c]; }
       } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) T[(k - nf) * 4 + c] = e[c];
@@ -200,6 +207,32 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
     householder4(T, n + 10, red);
     if (tid < 4) {
       for (int c = tid; c < 4; ++c) Sg[bp_idx(nf + tid, nf + c, np)] = T[tid * 4 + c];
+    }
+    if (q.carry_p) {
+      // robot rows of the carried covariance P = S^T S for the new factor [[S_ff, E_f], [0, R_rr]]:
+      //   P(robot r, feature i) = sum_{k <= i} S(k,i) E_f(k,r),   P_rr = E_f^T E_f + R_rr^T R_rr
+      for (int i = tid; i < nf; i += NT) {
+        double a0_ = 0, a1_ = 0, a2_ = 0, a3_ = 0;
+        const double* scol = Sg + i;
+#pragma unroll 4
+        for (int k = 0; k <= i; ++k) {
+          const double sv = scol[(size_t)k * np];
+          a0_ = fma(sv, Ef[k * 4 + 0], a0_); a1_ = fma(sv, Ef[k * 4 + 1], a1_);
+          a2_ = fma(sv, Ef[k * 4 + 2], a2_); a3_ = fma(sv, Ef[k * 4 + 3], a3_);
+        }
+        Sg[(size_t)(nf + 0) * np + i] = a0_; Sg[(size_t)(nf + 1) * np + i] = a1_;
+        Sg[(size_t)(nf + 2) * np + i] = a2_; Sg[(size_t)(nf + 3) * np + i] = a3_;
+      }
+      if (tid < 16) {
+        const int r = tid >> 2, c = tid & 3;
+        if (r >= c) {
+          double a = 0.0;
+          for (int k = 0; k < nf; ++k) a = fma(Ef[k * 4 + r], Ef[k * 4 + c], a);
+          for (int m = 0; m <= c; ++m) a = fma(T[m * 4 + r], T[m * 4 + c], a);
+          if (r == c) q.Pd[(size_t)b * np + nf + r] = a;
+          else Sg[(size_t)(nf + r) * np + nf + c] = a;
+        }
+      }
     }
     if (save_rsig) {
       double* rg = q.rsig + (size_t)b * P * 4;
@@ -247,10 +280,10 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
         const double* rm = rs + (size_t)(Na + k + 1) * 8;
         double px, py, mx, my;
         if (k <= 6 * j + 5) {   // (k < nf is implied) feature j's own entries are perturbed by +-gamma*S(k, 6j..6j+5)
-          const double* srow = Sg + (size_t)k * np + 6 * j;  // entries left of the diagonal are stored zeros
+          const double* srow = Sg + (size_t)k * np + 6 * j;  // S is upper triangular: columns < k are zero
           double dlt[6];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) dlt[c] = srow[c] * p.gamma;
+          for (int c = 0; c < 6; ++c) dlt[c] = (6 * j + c >= k) ? srow[c] * p.gamma : 0.0;
           double stp, ctp, stm, ctm, spp, cpp, spm, cpm;
           sincos_pm(f[3], sth0, cth0, dlt[3], stp, ctp, stm, ctm);
           sincos_pm(f[4], sph0, cph0, dlt[4], spp, cpp, spm, cpm);
@@ -416,7 +449,9 @@ __device__ __forceinline__ void ring_release(Ring& r) {
 // DMMA over one chunk held as boxes [tile][row][TP]: strip slots [QLO, QHI) of this warp x NTT column tiles.
 //   The chunk's column 0 is output row/column `c0` of the panel; strip s covers chunk columns 8*(s-s0)..+7,
 //   i.e. box (8*(s-s0)) / 64 at offset (8*(s-s0)) % 64.  B fragments come from `bbase` (pitch bpitch).
-template <int NW, int QLO, int QHI, int NTT>
+//   MASK: the strip on the chunk's own diagonal (s == s0) only takes A(k, col) with col >= k (the entries left of
+//   the diagonal of S's square buffer hold the carried covariance, not zeros).
+template <int NW, int QLO, int QHI, int NTT, bool MASK>
 __device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const double* abase, int tstride, int s0,
                                           const double* bbase, int bpitch, int nks, int lane, int warp) {
   int aoff[QHI > QLO ? QHI - QLO : 1];
@@ -435,19 +470,20 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const 
     for (int tt = 0; tt < NTT; ++tt) bf[tt] = br[8 * tt];
 #pragma unroll
     for (int q = QLO; q < QHI; ++q) {
-      const double a = ar[aoff[q - QLO]];
+      double a = ar[aoff[q - QLO]];
+      if (MASK && (warp + NW * q == s0) && (lane >> 2) < kk) a = 0.0;
 #pragma unroll
       for (int tt = 0; tt < NTT; ++tt) dmma(acc[q][tt][0], acc[q][tt][1], a, bf[tt]);
     }
   }
 }
 // runtime (qlo, qhi) -> compile-time instantiation (warp-uniform switch)
-template <int NW, int NTT>
+template <int NW, int NTT, bool MASK>
 __device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int qlo, int qhi, const double* abase,
                                              int tstride, int s0, const double* bbase, int bpitch, int nks, int lane,
                                              int warp) {
 #define SRUKF_CASE(LO, HI) \
-  case LO * 8 + HI: mma_chunk<NW, LO, HI, NTT>(acc, abase, tstride, s0, bbase, bpitch, nks, lane, warp); break;
+  case LO * 8 + HI: mma_chunk<NW, LO, HI, NTT, MASK>(acc, abase, tstride, s0, bbase, bpitch, nks, lane, warp); break;
   switch (qlo * 8 + qhi) {
     SRUKF_CASE(0, 1) SRUKF_CASE(0, 2) SRUKF_CASE(0, 3) SRUKF_CASE(0, 4) SRUKF_CASE(0, 5)
     SRUKF_CASE(1, 2) SRUKF_CASE(1, 3) SRUKF_CASE(1, 4) SRUKF_CASE(1, 5)
@@ -458,14 +494,14 @@ __device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int
   }
 #undef SRUKF_CASE
 }
-template <int NW>
+template <int NW, bool MASK>
 __device__ __forceinline__ void mma_chunk_any(double (&acc)[MAXQ][NB / 8][2], int qlo, int qhi, int nt,
                                               const double* abase, int tstride, int s0, const double* bbase, int bpitch,
                                               int nks, int lane, int warp) {
-  if (nt == NB / 8) mma_chunk_rt<NW, NB / 8>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
-  else if (nt == 1) mma_chunk_rt<NW, 1>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
-  else if (nt == 2) mma_chunk_rt<NW, 2>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
-  else mma_chunk_rt<NW, 3>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
+  if (nt == NB / 8) mma_chunk_rt<NW, NB / 8, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
+  else if (nt == 1) mma_chunk_rt<NW, 1, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
+  else if (nt == 2) mma_chunk_rt<NW, 2, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
+  else mma_chunk_rt<NW, 3, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -565,7 +601,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
       const double* xb = Bs + (size_t)st * KC * BP_B;
       // output strip s = warp + NW*q receives S rows k <= its own: active slots are q >= qlo
       const int qlo = (t > warp) ? (t - warp + NW - 1) / NW : 0;
-      mma_chunk_any<NW>(acc, qlo, nq_w, nt, xa, KC * TP, t, xb, BP_B, KC / 4, lane, warp);
+      mma_chunk_any<NW, true>(acc, qlo, nq_w, nt, xa, KC * TP, t, xb, BP_B, KC / 4, lane, warp);
       ring_release(ring);
     }
     // epilogue: apply wi*gamma and si^-1 to each column pair, store Ut[c][f] (transposed), accumulate the shift
@@ -672,8 +708,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
 // Afterwards Cp holds L; S_new(j, i) = sqrt(d_j) L(i, j) (:2321) is written by the caller.
 // -------------------------------------------------------------------------------------------------
 template <int NW>
-__device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm, double* sdsm, int R, int nbe, int J0,
-                                             int n, double eps, uint32_t& flags) {
+__device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm, double* sdsm, double* esm, int R,
+                                             int nbe, int J0, int n, double eps, uint32_t& flags) {
   constexpr int NTH = NW * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nsub = nbe / 8;
@@ -700,13 +736,13 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
       const double* myrow = Cp + (size_t)(c0 + li) * CP_PITCH + c0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) r[k] = myrow[k];
-      double dmine = 1.0, rmine = 1.0, w[8];
+      double dmine = 1.0, rmine = 1.0, emine = 0.0, w[8];
       bool modified = false;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const double cjj = __shfl_sync(0xffffffffu, r[j], j);
         const double d = fmax(eps, fabs(cjj));
-        if (li == j) { dmine = d; modified = (d != cjj); }
+        if (li == j) { dmine = d; emine = d - cjj; modified = (d != cjj); }   // E_j = D_j - C_jj, :2288
         w[j] = r[j];
         const double rinv = fast_rcp(d);
         if (li == j) rmine = rinv;
@@ -722,6 +758,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
         const double sd = sqrt(dmine);
         dsm[c0 + lane] = rmine;   // 1/d_j for the solve of the rows below
         sdsm[c0 + lane] = sd;
+        esm[c0 + lane] = emine;
         if (modified && J0 + c0 + lane < n) flags |= (dmine > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
         if (!isfinite(sd)) flags |= SRUKF_FLAG_NAN;
         double* wrow = Wd + (size_t)(c0 + lane) * WD_PITCH + c0;
@@ -764,11 +801,14 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
 // features at once: S_new = modifiedCholesky(S_old^T S_old - U U^T)  (SLAM.cpp:2197-2327).
 //
 // Left-looking, 32 columns per panel; G is never formed.  For panel columns J = [J0, J0+32) and rows i >= J0
-//     C(i, J) = sum_{k < J0+32} S_old(k,i) S_old(k,J) - sum_c Ut(c,i) Ut(c,J) - sum_{k < J0} S_new(k,i) S_new(k,J)
-// is one DMMA contraction over K = [S_old rows | Ut rows | S_new rows]; all three are K-major in HBM, so the
-// same smem chunk feeds the A fragment (rows i) and the B fragment (its first 32 columns).  The two negative
-// sources are folded in by flipping the sign of the accumulators between sources.  The panel is then factorised
-// in shared memory (factor_panel) and rows J of S_new = sqrt(d_j) * L(:, j) are written (:2321).
+//     C(i, J) = P(i, J) - sum_c Ut(c,i) Ut(c,J) - sum_{k < J0} S_new(k,i) S_new(k,J)
+// where P = S_old^T S_old is CARRIED between steps (strictly-lower part in the lower triangle of the S buffer,
+// diagonal in Pd; the reference re-forms it with a dense product at :2118): after this update P_new = G + E
+// (:2288), and the next motion step only rewrites its robot rows (k_predict).  The two sums are one DMMA
+// contraction over K = [Ut rows | S_new rows]; both are K-major in HBM, so the same smem chunk feeds the A
+// fragment (rows i) and the B fragment (its first 32 columns).  The accumulators start at -P(i,J), the sign is
+// flipped at the end.  The panel is then factorised in shared memory (factor_panel) and rows J of
+// S_new = sqrt(d_j) * L(:, j) are written (:2321).
 // GMW's third pivot candidate theta_j^2/beta^2 exceeds d_j iff max_i S_new(j,i)^2 > beta^2, where beta^2 needs
 // max diag / max off-diag of G (:2204-2211).  Both maxima are accumulated on the fly (G's panel is visible after
 // the S_old and Ut sources) and compared at the end: on violation, or when a pivot is modified beyond the EPSILON
@@ -783,8 +823,9 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   const int n = p.n, L = p.L, np = p.np, Lc = p.Lc;
   const double* Sold = q.S + (size_t)b * p.nbp;
   double* Snew = q.S2 + (size_t)b * p.nbp;
-  const CUtensorMap* tmOld = q.tmaps + (q.sbuf ? TM_S1 : TM_S0);
   const CUtensorMap* tmNew = q.tmaps + (q.sbuf ? TM_S0 : TM_S1);
+  const double* PdOld = q.Pd + (size_t)b * np;
+  double* PdNew = q.Pd2 + (size_t)b * np;
   const CUtensorMap* tmUt = q.tmaps + TM_UT;
   const int sdoubles = stage_doubles_for(np);
   size_t off = 0;
@@ -792,6 +833,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   double* Wd = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB * WD_PITCH;
   double* dsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;    // 1 / pivot d_j
   double* sdsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;   // sqrt(d_j)
+  double* esm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;    // E_j = d_j - c_jj
+  double* gdiag = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;  // G(j,j) of the panel
   double* red = reinterpret_cast<double*>(smraw + off); off = (off + sizeof(double) * 40 + 127) & ~(size_t)127;
   double* Xs = reinterpret_cast<double*>(smraw + off);  // ring: NSTAGE stages, aliased by the panel Cp
   double* Cp = Xs;
@@ -799,8 +842,9 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
 
   int nact = 0;
   for (int j = 0; j < L; ++j) nact += (q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j]) ? 1 : 0;
-  if (nact == 0) {  // KalmanUpdate returned early (:2050): the factor is carried over unchanged
+  if (nact == 0) {  // KalmanUpdate returned early (:2050): factor and covariance are carried over unchanged
     for (int i = tid; i < p.nbp; i += NTH) Snew[i] = Sold[i];
+    for (int i = tid; i < np; i += NTH) PdNew[i] = PdOld[i];
     return;
   }
   Ring ring;
@@ -824,19 +868,38 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     // DMMA work and the bytes in flight per mbarrier round trip stay roughly constant as the panel narrows
     int rpc = (sdoubles / (nbx * TP)) & ~7;
     if (rpc > 32) rpc = 32;
-    // chunk list: [A: S_old rows 0..J0+nbe-1 | B: Ut rows | C: finished S_new rows 0..J0-1]
-    const int rowsA = J0 + nbe, rowsB = Lc, rowsC = J0;
-    const int cA = (rowsA + rpc - 1) / rpc, cB = (rowsB + rpc - 1) / rpc, cC = (rowsC + rpc - 1) / rpc;
-    const int nchunks = cA + cB + cC;
+    // chunk list: [B: Ut rows | C: finished S_new rows 0..J0-1]
+    const int rowsB = Lc, rowsC = J0;
+    const int cA = 0, cB = (rowsB + rpc - 1) / rpc, cC = (rowsC + rpc - 1) / rpc;
+    const int nchunks = cB + cC;
+    // accumulators start at -P_old(i, J): tiles below the panel's diagonal come straight from the lower triangle
+    // of the old buffer, diagonal tiles mix lower entries and Pd, tiles above the diagonal are never used
     double acc[MAXQ][NB / 8][2];
 #pragma unroll
-    for (int qq = 0; qq < MAXQ; ++qq)
+    for (int qq = 0; qq < MAXQ; ++qq) {
+      const int rs = warp + NW * qq;
+      const int i = J0 + 8 * rs + (lane >> 2);
+      const double* prow = Sold + (size_t)i * np;
 #pragma unroll
-      for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
+      for (int tt = 0; tt < NB / 8; ++tt) {
+        double v0 = 0.0, v1 = 0.0;
+        if (rs < nstrip && tt < nt) {
+          const int j = J0 + 8 * tt + 2 * (lane & 3);
+          if (rs > tt) {
+            const double2 v = *reinterpret_cast<const double2*>(prow + j);
+            v0 = v.x; v1 = v.y;
+          } else if (rs == tt) {
+            v0 = (i > j) ? prow[j] : ((i == j) ? PdOld[i] : 0.0);
+            v1 = (i > j + 1) ? prow[j + 1] : ((i == j + 1) ? PdOld[i] : 0.0);
+          }
+        }
+        acc[qq][tt][0] = -v0;
+        acc[qq][tt][1] = -v1;
+      }
+    }
 
     // rows of chunk t: first row (within its source) and count
     auto chunk_rows = [&](int t, int& row0) -> int {
-      if (t < cA) { row0 = t * rpc; return (rowsA - row0 < rpc) ? rowsA - row0 : rpc; }
       if (t < cA + cB) { row0 = (t - cA) * rpc; return (rowsB - row0 < rpc) ? rowsB - row0 : rpc; }
       row0 = (t - cA - cB) * rpc;
       return (rowsC - row0 < rpc) ? rowsC - row0 : rpc;
@@ -847,8 +910,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
       long long tk0 = (TIMING && timing) ? clock64() : 0;
       const int st = ring_acquire(ring, (uint32_t)(nbx * nrows * TP * sizeof(double)));
       if (TIMING && timing) { long long t1_ = clock64(); tkl[0] += t1_ - tk0; tk0 = t1_; }
-      const CUtensorMap* tm = ((t < cA) ? tmOld : (t < cA + cB) ? tmUt : tmNew) + (nrows / 8 - 1);
-      const int c2 = (t >= cA && t < cA + cB) ? (int)blockIdx.x : b;
+      const CUtensorMap* tm = ((t < cB) ? tmUt : tmNew) + (nrows / 8 - 1);
+      const int c2 = (t < cB) ? (int)blockIdx.x : b;
       double* dst = Xs + (size_t)st * sdoubles;
       for (int j = 0; j < nbx; ++j) tma_load_3d(dst + (size_t)j * nrows * TP, tm, J0 + TW * j, row0, c2, ring.full + st);
       if (TIMING && timing) { tkl[1] += clock64() - tk0; }
@@ -862,7 +925,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
         const int st = ring_wait(ring);
         if (TIMING && timing) { long long t1_ = clock64(); tkl[2] += t1_ - tk0; tk0 = t1_; }
         const double* xs_ = Xs + (size_t)st * sdoubles;
-        if (!p.dbg_skip_mma) mma_chunk_any<NW>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nrows / 4, lane, warp);
+        if (!p.dbg_skip_mma) mma_chunk_any<NW, false>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nrows / 4, lane, warp);
         if (TIMING && timing) { long long t1_ = clock64(); tkl[3] += t1_ - tk0; tk0 = t1_; }
         ring_release(ring);
         if (TIMING && timing) { tkl[4] += clock64() - tk0; tkl[5] += 1; }
@@ -878,10 +941,30 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
       fence_proxy_async();  // the ring aliases the previous panel's Cp (generic-proxy stores)
       for (int t = 0; t < NSTAGE - 1 && t < nchunks; ++t) produce(t);
     }
-    consume(0, cA);          // + S_old^T S_old
-    negate();
-    consume(cA, cA + cB);    // acc = -(S^T S - U U^T) = -G(i, J)
-    // track max diag / max off-diag of G for beta^2 (:2204-2205)
+    consume(0, cB);          // acc = -(P - U U^T) = -G(i, J)
+    // G(i, J) is visible now: store the carried covariance of the new factor, P_new = G (+ E on the diagonal,
+    // added after the pivots are known), and track max diag / max off-diag of G for beta^2 (:2204-2205)
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq) {
+      const int rs = warp + NW * qq;
+      if (rs < nstrip) {
+        const int i = J0 + 8 * rs + (lane >> 2);
+        double* prow = Snew + (size_t)i * np;
+#pragma unroll
+        for (int tt = 0; tt < NB / 8; ++tt) {
+          if (tt < nt) {
+            const int j = J0 + 8 * tt + 2 * (lane & 3);
+            const double g0 = -acc[qq][tt][0], g1 = -acc[qq][tt][1];
+            if (rs > tt) {
+              *reinterpret_cast<double2*>(prow + j) = make_double2(g0, g1);
+            } else if (rs == tt) {
+              if (i > j) prow[j] = g0; else if (i == j) gdiag[i - J0] = g0;
+              if (i > j + 1) prow[j + 1] = g1; else if (i == j + 1) gdiag[i - J0] = g1;
+            }
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int qq = 0; qq < MAXQ; ++qq) {
       const int rs = warp + NW * qq;
@@ -924,7 +1007,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     }
     __syncthreads();
     SRUKF_TICK(2)
-    factor_panel<NW>(Cp, Wd, dsm, sdsm, R, nbe, J0, n, p.epsilon, flags);
+    factor_panel<NW>(Cp, Wd, dsm, sdsm, esm, R, nbe, J0, n, p.epsilon, flags);
+    if (tid < nbe) PdNew[J0 + tid] = gdiag[tid] + esm[tid];   // diag(P_new) = diag(G) + E, :2288
     SRUKF_TICK(3)
     // ---- rows J0.. of S_new: S_new(J0+j, J0+i) = sd_j L(i,j) for i > j, sd_j on the diagonal
     //      (entries left of the diagonal are zero in both S buffers and are never written) ----
@@ -1039,6 +1123,26 @@ __device__ void form_G(const DevParams& p, const double* __restrict__ S, const d
   }
 }
 
+// carried covariance of a factor, from scratch: strictly-lower part of P = S^T S into the lower triangle of the
+// same square buffer, diagonal into Pd (set_state and the fallback path; the fused path maintains it)
+__device__ void form_P(const DevParams& p, double* S, double* Pd) {
+  const int n = p.n, np = p.np;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < n; j += nw) {
+    for (int i = j + lane; i < n; i += 32) {
+      double acc = 0.0;
+      for (int k = 0; k <= j; ++k) acc = fma(S[(size_t)k * np + j], S[(size_t)k * np + i], acc);
+      if (i == j) Pd[j] = acc;
+      else S[(size_t)i * np + j] = acc;
+    }
+  }
+  for (int i = n + threadIdx.x; i < np; i += blockDim.x) Pd[i] = 1.0;
+}
+__global__ void __launch_bounds__(NT) k_form_P(DevParams p, double* S, double* Pd, int b0) {
+  const int b = b0 + blockIdx.x;
+  form_P(p, S + (size_t)b * p.nbp, Pd + (size_t)b * p.np);
+}
+
 // -------------------------------------------------------------------------------------------------
 // k_downdate -- GSLCholeskyUpdate, DOWNDATING / NEEDNOT_REORDER (SLAM.cpp:2106-2121,2139-2153), reference order.
 //   mode 1: the reference's sequence: for every matched feature, for each of its 2 U columns,
@@ -1089,6 +1193,10 @@ __global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mo
     flags = __reduce_or_sync(0xffffffffu, flags);
     if ((tid & 31) == 0 && flags) atomicOr(q.flags + b, flags);
     __syncthreads();
+    if (use_worklist && q.carry_p) {   // the redone filter needs its carried covariance rebuilt as well
+      form_P(p, Sg, q.Pd2 + (size_t)b * np);
+      __syncthreads();
+    }
   }
 }
 
@@ -1206,7 +1314,7 @@ int tile_warps(const DevParams& p) {  // warps per CTA of the DMMA kernels; 0 = 
 size_t predict_smem_bytes(const DevParams& p) {
   size_t slots = (p.L <= NT) ? (size_t)(NT / p.L) * p.L : (size_t)p.L;
   size_t work = slots * 13;
-  size_t t4 = (size_t)(p.n + 10) * 4;
+  size_t t4 = (size_t)(p.n + 10) * 4 + (size_t)p.nf * 4;
   if (t4 > work) work = t4;
   return sizeof(double) * ((size_t)p.n + (size_t)p.P * 8 + 2 * (size_t)p.L + 40 + work);
 }
@@ -1218,7 +1326,7 @@ size_t gain_smem_bytes(const DevParams& p) {
 }
 size_t update_smem_bytes(const DevParams& p) {
   size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
-  off += sizeof(double) * (NB * WD_PITCH + 2 * NB);
+  off += sizeof(double) * (NB * WD_PITCH + 4 * NB);
   off = (off + sizeof(double) * 40 + 127) & ~(size_t)127;
   size_t ring = (size_t)NSTAGE * stage_doubles_for(p.np);  // stage size is fixed: 8 rows at full width
   size_t panel = (size_t)p.np * CP_PITCH;
@@ -1270,6 +1378,9 @@ void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mod
 }
 void launch_import(const DevParams& p, int nb, int fmt, const double* ext, double* bp, cudaStream_t st) {
   k_import<<<nb, 256, 0, st>>>(p.n, p.np, p.ntri, p.nbp, fmt, ext, bp);
+}
+void launch_form_P(const DevParams& p, int b0, int nb, double* S, double* Pd, cudaStream_t st) {
+  k_form_P<<<nb, NT, 0, st>>>(p, S, Pd, b0);
 }
 void launch_export(const DevParams& p, int nb, int fmt, const double* bp, double* ext, cudaStream_t st) {
   k_export<<<nb, 256, 0, st>>>(p.n, p.np, p.ntri, p.nbp, fmt, bp, ext);
