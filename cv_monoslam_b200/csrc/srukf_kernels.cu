@@ -209,20 +209,8 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
       for (int c = tid; c < 4; ++c) Sg[bp_idx(nf + tid, nf + c, np)] = T[tid * 4 + c];
     }
     if (q.carry_p) {
-      // robot rows of the carried covariance P = S^T S for the new factor [[S_ff, E_f], [0, R_rr]]:
-      //   P(robot r, feature i) = sum_{k <= i} S(k,i) E_f(k,r),   P_rr = E_f^T E_f + R_rr^T R_rr
-      for (int i = tid; i < nf; i += NT) {
-        double a0_ = 0, a1_ = 0, a2_ = 0, a3_ = 0;
-        const double* scol = Sg + i;
-#pragma unroll 4
-        for (int k = 0; k <= i; ++k) {
-          const double sv = scol[(size_t)k * np];
-          a0_ = fma(sv, Ef[k * 4 + 0], a0_); a1_ = fma(sv, Ef[k * 4 + 1], a1_);
-          a2_ = fma(sv, Ef[k * 4 + 2], a2_); a3_ = fma(sv, Ef[k * 4 + 3], a3_);
-        }
-        Sg[(size_t)(nf + 0) * np + i] = a0_; Sg[(size_t)(nf + 1) * np + i] = a1_;
-        Sg[(size_t)(nf + 2) * np + i] = a2_; Sg[(size_t)(nf + 3) * np + i] = a3_;
-      }
+      // robot block of the carried covariance P = S^T S for the new factor [[S_ff, E_f], [0, R_rr]]:
+      //   P_rr = E_f^T E_f + R_rr^T R_rr   (the robot-feature rows S_ff^T E_f are formed by k_gain on the tensor pipe)
       if (tid < 16) {
         const int r = tid >> 2, c = tid & 3;
         if (r >= c) {
@@ -451,9 +439,11 @@ __device__ __forceinline__ void ring_release(Ring& r) {
 //   i.e. box (8*(s-s0)) / 64 at offset (8*(s-s0)) % 64.  B fragments come from `bbase` (pitch bpitch).
 //   MASK: the strip on the chunk's own diagonal (s == s0) only takes A(k, col) with col >= k (the entries left of
 //   the diagonal of S's square buffer hold the carried covariance, not zeros).
+//   b2base != nullptr: the LAST of the NTT column tiles takes its B fragment from b2base (pitch TP) instead.
 template <int NW, int QLO, int QHI, int NTT, bool MASK>
 __device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const double* abase, int tstride, int s0,
-                                          const double* bbase, int bpitch, int nks, int lane, int warp) {
+                                          const double* bbase, int bpitch, const double* b2base, int nks, int lane,
+                                          int warp) {
   int aoff[QHI > QLO ? QHI - QLO : 1];
 #pragma unroll
   for (int q = QLO; q < QHI; ++q) {
@@ -468,6 +458,7 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const 
     double bf[NTT];
 #pragma unroll
     for (int tt = 0; tt < NTT; ++tt) bf[tt] = br[8 * tt];
+    if (MASK && b2base) bf[NTT - 1] = b2base[kk * TP + (lane >> 2)];
 #pragma unroll
     for (int q = QLO; q < QHI; ++q) {
       double a = ar[aoff[q - QLO]];
@@ -480,10 +471,10 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const 
 // runtime (qlo, qhi) -> compile-time instantiation (warp-uniform switch)
 template <int NW, int NTT, bool MASK>
 __device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int qlo, int qhi, const double* abase,
-                                             int tstride, int s0, const double* bbase, int bpitch, int nks, int lane,
-                                             int warp) {
+                                             int tstride, int s0, const double* bbase, int bpitch,
+                                             const double* b2base, int nks, int lane, int warp) {
 #define SRUKF_CASE(LO, HI) \
-  case LO * 8 + HI: mma_chunk<NW, LO, HI, NTT, MASK>(acc, abase, tstride, s0, bbase, bpitch, nks, lane, warp); break;
+  case LO * 8 + HI: mma_chunk<NW, LO, HI, NTT, MASK>(acc, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp); break;
   switch (qlo * 8 + qhi) {
     SRUKF_CASE(0, 1) SRUKF_CASE(0, 2) SRUKF_CASE(0, 3) SRUKF_CASE(0, 4) SRUKF_CASE(0, 5)
     SRUKF_CASE(1, 2) SRUKF_CASE(1, 3) SRUKF_CASE(1, 4) SRUKF_CASE(1, 5)
@@ -497,11 +488,11 @@ __device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int
 template <int NW, bool MASK>
 __device__ __forceinline__ void mma_chunk_any(double (&acc)[MAXQ][NB / 8][2], int qlo, int qhi, int nt,
                                               const double* abase, int tstride, int s0, const double* bbase, int bpitch,
-                                              int nks, int lane, int warp) {
-  if (nt == NB / 8) mma_chunk_rt<NW, NB / 8, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
-  else if (nt == 1) mma_chunk_rt<NW, 1, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
-  else if (nt == 2) mma_chunk_rt<NW, 2, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
-  else mma_chunk_rt<NW, 3, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, nks, lane, warp);
+                                              const double* b2base, int nks, int lane, int warp) {
+  if (nt == NB / 8) mma_chunk_rt<NW, NB / 8, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp);
+  else if (nt == 1) mma_chunk_rt<NW, 1, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp);
+  else if (nt == 2) mma_chunk_rt<NW, 2, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp);
+  else mma_chunk_rt<NW, 3, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -530,13 +521,16 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
   double* sii = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 4 * (Lc / 2);   // per column pair
   double* gv = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 2 * (Lc / 2);    // si^-T (z - hbar)
   double* ct = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 2 * (Lc / 2);    // c^T si^-1
+  double* dxs = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * np;             // state shift U g
   int* act = reinterpret_cast<int*>(smraw + off); off = (off + sizeof(int) * (L + 1) + 127) & ~(size_t)127;
   double* Xs = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NSTAGE * sdoubles;
   double* Bs = reinterpret_cast<double*>(smraw + off);
   int* nact = act + L;
+  for (int i = tid; i < np; i += NTH) dxs[i] = 0.0;
   const CUtensorMap* tmS = q.tmaps + (q.sbuf ? TM_S1 : TM_S0);   // 8-row boxes
   const CUtensorMap* tmZ = q.tmaps + q.tm_dz;
   double* Ut = q.U + (size_t)blockIdx.x * Lc * np;
+  double* Sgw = q.S + (size_t)b * p.nbp;   // robot rows of the carried covariance are written here
   if (tid == 0) *nact = 0;
   __syncthreads();
   for (int j = tid; j < Lc / 2; j += NTH) {
@@ -566,18 +560,26 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
   }
   Ring ring;
   ring_init<NW>(ring, bars);
-  if (*nact == 0) return;  // KalmanUpdate returns early, :2050 (k_update copies S through)
+  // KalmanUpdate returns early without matches, :2050 (k_update copies S through); the carried covariance still
+  // needs its new robot-feature rows
+  const bool none = (*nact == 0);
+  if (none && !q.carry_p) return;
   const bool seq_shift = (p.wc0 != p.wm0);
   const double wg = p.wi * p.gamma;
   const int nblk = np / 8;                            // 8-row blocks of S == K chunks == output strips
   const int nq_w = (nblk > warp) ? (nblk - warp - 1) / NW + 1 : 0;
-  double dxp[MAXQ];
-#pragma unroll
-  for (int qq = 0; qq < MAXQ; ++qq) dxp[qq] = 0.0;
-
-  for (int cg = 0; cg < Lc; cg += NB) {
-    const int ncol = (Lc - cg < NB) ? (Lc - cg) : NB;
-    const int nt = ncol / 8;
+  // With a carried covariance the robot-feature rows P(robot r, feature f) = sum_{k<=f} S(k,f) S(k, nf+r) (the new
+  // robot columns of S, written by k_predict) are the same triangular product with 8 more B columns taken from the
+  // S chunk itself: they ride along as one extra column tile of the last pass (or a pass of their own).
+  const int ncg = (Lc + NB - 1) / NB;
+  const bool last_full = (Lc - (ncg - 1) * NB) == NB;
+  const int npass = ncg + ((q.carry_p && last_full) ? 1 : 0);
+  for (int pass = none ? npass - 1 : 0; pass < npass; ++pass) {
+    const int cg = pass * NB;
+    const int ncol = (none || cg >= Lc) ? 0 : ((Lc - cg < NB) ? (Lc - cg) : NB);
+    const bool xtile = q.carry_p && (pass == npass - 1);
+    const int ntm = ncol / 8;              // measurement-column tiles of this pass
+    const int nt = ntm + (xtile ? 1 : 0);  // + the P_fr tile
     double acc[MAXQ][NB / 8][2];
 #pragma unroll
     for (int qq = 0; qq < MAXQ; ++qq)
@@ -587,10 +589,10 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
     const int nchunk = (nf + 7) / 8;
     auto produce = [&](int t) {  // thread 0: S rows 8t..8t+7 from column 8t on (boxes of 64+8 columns) + dZ rows
       const int nbx = ntiles(np - 8 * t);
-      const int st = ring_acquire(ring, (uint32_t)((nbx * KC * TP + KC * BP_B) * sizeof(double)));
+      const int st = ring_acquire(ring, (uint32_t)((nbx * KC * TP + (ncol ? KC * BP_B : 0)) * sizeof(double)));
       double* xd = Xs + (size_t)st * sdoubles;
       for (int j = 0; j < nbx; ++j) tma_load_3d(xd + (size_t)j * KC * TP, tmS, 8 * t + TW * j, 8 * t, b, ring.full + st);
-      tma_load_3d(Bs + (size_t)st * KC * BP_B, tmZ, cg, 8 * t, q.dz_filter0 + blockIdx.x, ring.full + st);
+      if (ncol) tma_load_3d(Bs + (size_t)st * KC * BP_B, tmZ, cg, 8 * t, q.dz_filter0 + blockIdx.x, ring.full + st);
     };
     if (tid == 0)
       for (int t = 0; t < NSTAGE - 1 && t < nchunk; ++t) produce(t);
@@ -601,7 +603,9 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
       const double* xb = Bs + (size_t)st * KC * BP_B;
       // output strip s = warp + NW*q receives S rows k <= its own: active slots are q >= qlo
       const int qlo = (t > warp) ? (t - warp + NW - 1) / NW : 0;
-      mma_chunk_any<NW, true>(acc, qlo, nq_w, nt, xa, KC * TP, t, xb, BP_B, KC / 4, lane, warp);
+      const int xrel = nf - 8 * t;  // chunk column of S(:, nf): new robot columns (columns >= n are zero)
+      const double* b2 = xtile ? xa + (size_t)(xrel >> 6) * (KC * TP) + (xrel & 63) : nullptr;
+      mma_chunk_any<NW, true>(acc, qlo, nq_w, nt, xa, KC * TP, t, xb, BP_B, b2, KC / 4, lane, warp);
       ring_release(ring);
     }
     // epilogue: apply wi*gamma and si^-1 to each column pair, store Ut[c][f] (transposed), accumulate the shift
@@ -610,9 +614,10 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
       const int s = warp + NW * qq;
       if (s < nblk) {
         const int f = 8 * s + (lane >> 2);
+        double dxp = 0.0;
 #pragma unroll
         for (int tt = 0; tt < NB / 8; ++tt) {
-          if (tt < nt) {
+          if (tt < ntm) {
             const int c = cg + 8 * tt + 2 * (lane & 3);
             const int j = c >> 1;
             const double a0 = wg * acc[qq][tt][0], a1 = wg * acc[qq][tt][1];
@@ -622,27 +627,35 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
               Ut[(size_t)c * np + f] = u0;
               Ut[(size_t)(c + 1) * np + f] = u1;
             }
-            dxp[qq] += u0 * gv[2 * j] + u1 * gv[2 * j + 1];
+            dxp += u0 * gv[2 * j] + u1 * gv[2 * j + 1];
           }
         }
+        if (xtile && f < nf && (lane & 3) < 2) {   // P(nf + r, f), r = 2*(lane&3) + {0,1} < 4: tile ntm
+          double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+          for (int tt = 0; tt < NB / 8; ++tt)
+            if (tt == ntm) { p0 = acc[qq][tt][0]; p1 = acc[qq][tt][1]; }
+          const int r = 2 * (lane & 3);
+          Sgw[(size_t)(nf + r) * np + f] = p0;
+          Sgw[(size_t)(nf + r + 1) * np + f] = p1;
+        }
+        // the 4 lanes that share state row f; each row has exactly one owner across all passes
+        dxp += __shfl_xor_sync(0xffffffffu, dxp, 1);
+        dxp += __shfl_xor_sync(0xffffffffu, dxp, 2);
+        if ((lane & 3) == 0) dxs[f] += dxp;
       }
     }
   }
+  if (none) return;
   double* xg = q.x + (size_t)b * n;
   uint32_t flags = 0;
   if (!seq_shift) {
-    // x_f += U_f g  (sum over the 4 lanes that share a state row)
-#pragma unroll
-    for (int qq = 0; qq < MAXQ; ++qq) {
-      double v = dxp[qq];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      const int f = 8 * (warp + NW * qq) + (lane >> 2);
-      if ((lane & 3) == 0 && f < nf) {
-        const double xn = xg[f] + v;
-        xg[f] = xn;
-        if (!isfinite(xn)) flags |= SRUKF_FLAG_NAN;
-      }
+    // x_f += U_f g
+    __syncthreads();
+    for (int f = tid; f < nf; f += NTH) {
+      const double xn = xg[f] + dxs[f];
+      xg[f] = xn;
+      if (!isfinite(xn)) flags |= SRUKF_FLAG_NAN;
     }
   }
   // robot rows: U_r = Pxy_r sii ; padding rows/columns of Ut are zero
@@ -925,7 +938,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
         const int st = ring_wait(ring);
         if (TIMING && timing) { long long t1_ = clock64(); tkl[2] += t1_ - tk0; tk0 = t1_; }
         const double* xs_ = Xs + (size_t)st * sdoubles;
-        if (!p.dbg_skip_mma) mma_chunk_any<NW, false>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nrows / 4, lane, warp);
+        if (!p.dbg_skip_mma) mma_chunk_any<NW, false>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nullptr, nrows / 4, lane, warp);
         if (TIMING && timing) { long long t1_ = clock64(); tkl[3] += t1_ - tk0; tk0 = t1_; }
         ring_release(ring);
         if (TIMING && timing) { tkl[4] += clock64() - tk0; tkl[5] += 1; }
@@ -1320,7 +1333,7 @@ size_t predict_smem_bytes(const DevParams& p) {
 }
 size_t gain_smem_bytes(const DevParams& p) {
   size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
-  off += sizeof(double) * 8 * (p.Lc / 2);
+  off += sizeof(double) * (8 * (p.Lc / 2) + p.np);
   off = (off + sizeof(int) * (p.L + 1) + 127) & ~(size_t)127;
   return off + sizeof(double) * (size_t)NSTAGE * (stage_doubles_for(p.np) + KC * BP_B);
 }
