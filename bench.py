@@ -126,7 +126,7 @@ def cpu_reference_run(L: int, filters: int, steps: int, warmup: int, threads: in
     return times
 
 
-def run_reference(args, ctx):
+def run_reference(args, ctx, out):
     """--impl reference: the reference's CPU algorithm (oracle port; oracle/_ref is unbuildable: MFC + OpenCV 2.4.3
     + GSL 1.8) with all host threads, each step a bounded sample of the workload."""
     if ctx.rank != 0:
@@ -150,10 +150,38 @@ def run_reference(args, ctx):
         "e2e": {"value": value, "unit": "filter-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
+
+
+class StdoutGuard:
+    """Everything written to fd 1 while the benchmark runs (e.g. NCCL's version banner, written from C) goes to
+    stderr; only the final JSON line reaches stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
+    with StdoutGuard() as out:
+        run(out)
+
+
+def run(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -171,7 +199,7 @@ def main():
     from cv_monoslam_b200 import dist
     if args.impl == "reference":
         ctx = dist.Ctx(int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), 0, None)
-        run_reference(args, ctx)
+        run_reference(args, ctx, out)
         return
 
     import torch
@@ -271,7 +299,7 @@ def main():
     cpu = None
     if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        times = cpu_reference_run(L, cores, 2, 0, cores)
+        times = cpu_reference_run(L, cores, 6, 0, cores)
         cpu = {"value": cores * len(times) / sum(times), "unit": "filter-steps/s", "cores": cores, "kind": "port",
                "sample": f"{cores} filters (one per host thread) x {len(times)} steps at L={L}, oracle literal mode "
                          f"(dense S^T S + GMW per U column), gcc -O2, {sum(times):.1f} s"}
@@ -312,7 +340,7 @@ def main():
             "cpu_baseline": cpu,
             "stats": stats,
         }
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     g.close()
     dist.finalize(ctx)
 
