@@ -268,9 +268,10 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   CUH(cudaMemsetAsync(h->x, 0, sizeof(double) * B * n, h->stream));
   CUH(cudaMemsetAsync(h->S, 0, sizeof(double) * (size_t)B * p.nbp, h->stream));
   CUH(cudaMemsetAsync(h->visible, 0, (size_t)B * L, h->stream));
-  // scratch: chunk sized so the pipeline scratch (V and Ut per filter) stays <= 2 GiB
+  // scratch: chunk sized so the pipeline scratch (dZ and Ut per filter) stays <= 6 GiB: few, long launches keep
+  // the idle tail of each kernel (the last wave of CTAs) small against its run time
   size_t per = sizeof(double) * 2 * (size_t)p.np * p.Lc;
-  size_t budget = (size_t)2 << 30;
+  size_t budget = (size_t)6 << 30;
   long chunk = (long)(budget / per);
   if (chunk < 1) chunk = 1;
   if (chunk > B) chunk = B;

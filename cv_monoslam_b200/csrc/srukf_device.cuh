@@ -96,17 +96,6 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, in
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// 1/d for d > 0 well inside the normal range: MUFU.RCP64H seed + two Newton steps (5 dependent FP64 ops instead of
-// the ~15 of an IEEE division), accurate to ~1 ulp.  Used on the pivot chain of the panel factorisation.
-__device__ __forceinline__ double fast_rcp(double d) {
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-  double e = fma(-d, x, 1.0);
-  x = fma(x, e, x);
-  e = fma(-d, x, 1.0);
-  x = fma(x, e, x);
-  return x;
-}
 // orders this thread's earlier generic-proxy accesses (shared AND global) before later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // 16-byte asynchronous global->shared copy (LDGSTS, L2 only) and its completion hook onto an mbarrier:
@@ -116,6 +105,18 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 1/d for |d| well inside the normal range: MUFU.RCP64H seed + two Newton steps (5 dependent FP64 ops instead of
+// the ~15 of an IEEE division), accurate to ~1 ulp.  Used on the pivot chain of the panel factorisation.
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  return x;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -172,7 +173,7 @@ __device__ __forceinline__ void pixel_from_ray(const DevParams& p, double hx, do
     ux = 0;
     uy = 0;
   } else {
-    const double r = 1.0 / rzz;
+    const double r = fast_rcp(rzz);   // rzz ~ ceiling height: well inside the normal range
     uy = p.cam_cx + (p.f1 * rxx) * r + e0;
     ux = p.cam_cy + (p.f2 * ryy) * r + e1;
     if (ux < 10 || ux > p.img_w - 10 || uy < 10 || uy > p.img_h - 10) {

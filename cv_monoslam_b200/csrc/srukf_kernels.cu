@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
           double stp, ctp, stm, ctm, spp, cpp, spm, cpm;
           sincos_pm(f[3], sth0, cth0, dlt[3], stp, ctp, stm, ctm);
           sincos_pm(f[4], sph0, cph0, dlt[4], spp, cpp, spm, cpm);
-          const double irp = 1 / (f[5] * 1 + dlt[5]), irm = 1 / (f[5] * 1 - dlt[5]);
+          const double irp = fast_rcp(f[5] * 1 + dlt[5]), irm = fast_rcp(f[5] * 1 - dlt[5]);
           pixel_from_ray(p, (f[0] * 1 + dlt[0]) + irp * cpp * stp - rp[0], (f[1] * 1 + dlt[1]) - irp * spp - rp[1],
                          (f[2] * 1 + dlt[2]) + irp * cpp * ctp - rp[2], rp[4], rp[5], rp[6], e0, e1, px, py, flags);
           pixel_from_ray(p, (f[0] * 1 - dlt[0]) + irm * cpm * stm - rm[0], (f[1] * 1 - dlt[1]) - irm * spm - rm[1],
