@@ -24,7 +24,10 @@ struct StepPtrs {
 };
 // tensor-map table layout and box geometry (must match srukf_kernels.cu)
 constexpr int TM_S0 = 0, TM_S1 = 4, TM_UT = 8, TM_DZ = 12, TM_DZ_ALL = 13, TM_COUNT = 14;
-constexpr int TP = 72, BP_B = 40;
+#ifndef SRUKF_TW
+#define SRUKF_TW 64
+#endif
+constexpr int TP = SRUKF_TW + 8, BP_B = 40;
 int tile_warps(const DevParams& p);
 cudaError_t configure_kernels(const DevParams& p);
 size_t predict_smem_bytes(const DevParams& p);

@@ -96,6 +96,11 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, in
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a box (no shared-memory destination): hides the DRAM latency of chunks further ahead than the ring
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // orders this thread's earlier generic-proxy accesses (shared AND global) before later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // 16-byte asynchronous global->shared copy (LDGSTS, L2 only) and its completion hook onto an mbarrier:

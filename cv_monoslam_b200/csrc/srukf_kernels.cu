@@ -373,8 +373,11 @@ constexpr int KC = 8;       // K rows per pipeline stage at full width
 #endif
 constexpr int NSTAGE = SRUKF_NSTAGE;   // ring depth
 constexpr int MAXQ = 5;     // strips per warp: np <= 8 * NW * MAXQ
-constexpr int TW = 64;      // payload columns per TMA box
-constexpr int TP = 72;      // box width == smem row pitch inside a box (doubles)
+#ifndef SRUKF_TW
+#define SRUKF_TW 64
+#endif
+constexpr int TW = SRUKF_TW;   // payload columns per TMA box (64 or 128)
+constexpr int TP = TW + 8;     // box width == smem row pitch inside a box (doubles), == 8 mod 16
 constexpr int BP_B = 40;    // box width of the dZ operand of k_gain (32 payload columns + 8)
 constexpr int CP_PITCH = NB + 1;  // odd pitch: one row per lane/thread is bank-conflict free
 constexpr int WD_PITCH = NB + 1;
@@ -392,7 +395,7 @@ __host__ __device__ __forceinline__ int stage_doubles_for(int np) { return KC * 
 struct Ring {
   uint64_t* full;    // [NSTAGE]  expect_tx by the producer thread + TMA complete_tx
   uint64_t* empty;   // [NSTAGE]  one arrival per warp: the warp is done reading the chunk
-  uint32_t produced; // chunks issued so far (meaningful in thread 0 only)
+  uint32_t produced; // chunks issued so far (kept in step by every thread)
   uint32_t consumed; // chunks consumed so far by this warp
 };
 
@@ -411,15 +414,23 @@ __device__ __forceinline__ void ring_init(Ring& r, uint64_t* bars) {
   }
   __syncthreads();
 }
-// thread 0: claim the next stage (waits until every warp released its previous occupant) and post the byte count
+// Producer election: chunk g (global count) is issued by lane 0 of warp g % NW, so the serial cost of issuing
+// (stage wait + expect_tx + a few tensor copies) rotates over the warps instead of sitting on one of them.
+// Every thread calls ring_next() once per produced chunk to keep the counter in step.
+template <int NW>
+__device__ __forceinline__ bool ring_my_turn(const Ring& r) {
+  return ((threadIdx.x & 31) == 0) && ((int)(r.produced % NW) == (int)(threadIdx.x >> 5));
+}
+// elected thread: claim the next stage (waits until every warp released its previous occupant), post the byte count
 __device__ __forceinline__ int ring_acquire(Ring& r, uint32_t bytes) {
-  const uint32_t g = r.produced++;
+  const uint32_t g = r.produced;
   const int st = g % NSTAGE;
   const uint32_t use = g / NSTAGE;
   if (use > 0) mbar_wait(r.empty + st, (use - 1) & 1);
   mbar_expect_tx(r.full + st, bytes);
   return st;
 }
+__device__ __forceinline__ void ring_next(Ring& r) { r.produced++; }
 // all threads of a warp: wait for the next chunk, returns its stage
 __device__ __forceinline__ int ring_wait(Ring& r) {
   const uint32_t g = r.consumed;
@@ -448,7 +459,7 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const 
 #pragma unroll
   for (int q = QLO; q < QHI; ++q) {
     const int rel = 8 * (warp + NW * q - s0);
-    aoff[q - QLO] = (rel >> 6) * tstride + (rel & 63);
+    aoff[q - QLO] = (rel / TW) * tstride + (rel % TW);
   }
 #pragma unroll 2
   for (int ks = 0; ks < nks; ++ks) {
@@ -587,24 +598,29 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
       for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
     // only blocks whose rows can touch a feature row matter: S rows >= nf (robot) have zero dZ
     const int nchunk = (nf + 7) / 8;
-    auto produce = [&](int t) {  // thread 0: S rows 8t..8t+7 from column 8t on (boxes of 64+8 columns) + dZ rows
+    auto produce = [&](int t) {  // elected thread: S rows 8t..8t+7 from column 8t on (boxes of 64+8 columns) + dZ rows
       const int nbx = ntiles(np - 8 * t);
       const int st = ring_acquire(ring, (uint32_t)((nbx * KC * TP + (ncol ? KC * BP_B : 0)) * sizeof(double)));
       double* xd = Xs + (size_t)st * sdoubles;
       for (int j = 0; j < nbx; ++j) tma_load_3d(xd + (size_t)j * KC * TP, tmS, 8 * t + TW * j, 8 * t, b, ring.full + st);
       if (ncol) tma_load_3d(Bs + (size_t)st * KC * BP_B, tmZ, cg, 8 * t, q.dz_filter0 + blockIdx.x, ring.full + st);
     };
-    if (tid == 0)
-      for (int t = 0; t < NSTAGE - 1 && t < nchunk; ++t) produce(t);
+    for (int t = 0; t < NSTAGE - 1 && t < nchunk; ++t) {
+      if (ring_my_turn<NW>(ring)) produce(t);
+      ring_next(ring);
+    }
     for (int t = 0; t < nchunk; ++t) {
-      if (tid == 0 && t + NSTAGE - 1 < nchunk) produce(t + NSTAGE - 1);
+      if (t + NSTAGE - 1 < nchunk) {
+        if (ring_my_turn<NW>(ring)) produce(t + NSTAGE - 1);
+        ring_next(ring);
+      }
       const int st = ring_wait(ring);
       const double* xa = Xs + (size_t)st * sdoubles;     // column 0 == state row 8t
       const double* xb = Bs + (size_t)st * KC * BP_B;
       // output strip s = warp + NW*q receives S rows k <= its own: active slots are q >= qlo
       const int qlo = (t > warp) ? (t - warp + NW - 1) / NW : 0;
       const int xrel = nf - 8 * t;  // chunk column of S(:, nf): new robot columns (columns >= n are zero)
-      const double* b2 = xtile ? xa + (size_t)(xrel >> 6) * (KC * TP) + (xrel & 63) : nullptr;
+      const double* b2 = xtile ? xa + (size_t)(xrel / TW) * (KC * TP) + (xrel % TW) : nullptr;
       mma_chunk_any<NW, true>(acc, qlo, nq_w, nt, xa, KC * TP, t, xb, BP_B, b2, KC / 4, lane, warp);
       ring_release(ring);
     }
@@ -864,7 +880,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   ring_init<NW>(ring, bars);
   double gmax = -1.0e300, zmax = 0.0, tmax = 0.0;
   // optional phase timing (thread 0 of every CTA): K loop / barrier skew / panel store / factor / write-out
-  const bool timing = TIMING && (q.dbg != nullptr) && tid == 0;
+  const bool timing = TIMING && (q.dbg != nullptr) && tid == 0;  // (sees only the chunks warp 0 issues)
   long long tph[6] = {0, 0, 0, 0, 0, 0};
   long long tkl[6] = {0, 0, 0, 0, 0, 0};
   long long tlast = timing ? clock64() : 0;
@@ -917,7 +933,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
       row0 = (t - cA - cB) * rpc;
       return (rowsC - row0 < rpc) ? rowsC - row0 : rpc;
     };
-    auto produce = [&](int t) {  // thread 0: nbx tensor copies of [nrows x 72] from column J0 + 64 j
+    auto produce = [&](int t) {  // elected thread: nbx tensor copies of [nrows x 72] from column J0 + 64 j
       int row0;
       const int nrows = chunk_rows(t, row0);
       long long tk0 = (TIMING && timing) ? clock64() : 0;
@@ -931,7 +947,10 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     };
     auto consume = [&](int t0, int t1) {
       for (int t = t0; t < t1; ++t) {
-        if (tid == 0 && t + NSTAGE - 1 < nchunks) produce(t + NSTAGE - 1);
+        if (t + NSTAGE - 1 < nchunks) {
+          if (ring_my_turn<NW>(ring)) produce(t + NSTAGE - 1);
+          ring_next(ring);
+        }
         int row0;
         const int nrows = chunk_rows(t, row0);
         long long tk0 = (TIMING && timing) ? clock64() : 0;
@@ -950,9 +969,12 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
 #pragma unroll
         for (int t = 0; t < NB / 8; ++t) { acc[qq][t][0] = -acc[qq][t][0]; acc[qq][t][1] = -acc[qq][t][1]; }
     };
-    if (tid == 0) {
-      fence_proxy_async();  // the ring aliases the previous panel's Cp (generic-proxy stores)
-      for (int t = 0; t < NSTAGE - 1 && t < nchunks; ++t) produce(t);
+    for (int t = 0; t < NSTAGE - 1 && t < nchunks; ++t) {
+      if (ring_my_turn<NW>(ring)) {
+        fence_proxy_async();  // the ring aliases the previous panel's Cp (generic-proxy stores)
+        produce(t);
+      }
+      ring_next(ring);
     }
     consume(0, cB);          // acc = -(P - U U^T) = -G(i, J)
     // G(i, J) is visible now: store the carried covariance of the new factor, P_new = G (+ E on the diagonal,
