@@ -27,7 +27,9 @@ constexpr int TM_S0 = 0, TM_S1 = 4, TM_UT = 8, TM_DZ = 12, TM_DZ_ALL = 13, TM_CO
 #ifndef SRUKF_TW
 #define SRUKF_TW 64
 #endif
-constexpr int TP = SRUKF_TW + 8, BP_B = 40;
+constexpr int TP = SRUKF_TW + 8;
+int gain_dz_box(const DevParams& p);
+int gain_variant(const DevParams& p);
 int tile_warps(const DevParams& p);
 cudaError_t configure_kernels(const DevParams& p);
 size_t predict_smem_bytes(const DevParams& p);
@@ -149,7 +151,7 @@ static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
   d.img_w = s.image_width; d.img_h = s.image_height;
   d.a1 = s.a1; d.a2 = s.a2; d.a3 = s.a3; d.a4 = s.a4; d.sigma_measure = s.sigma_measure;
   d.epsilon = s.epsilon; d.newton_iters = s.newton_iters;
-  { const char* e_ = getenv("SRUKF_DBG_SKIP_MMA"); d.dbg_skip_mma = (e_ && e_[0] == '1') ? 1 : 0; }
+  { const char* e_ = getenv("SRUKF_DBG_SKIP_MMA"); d.dbg_skip_mma = e_ ? atoi(e_) : 0; }  // bit 0: skip DMMAs, bit 1: skip k_gain's loads
   // calculateSampleParameter, SLAM.cpp:1050-1103 (operation order kept)
   const int Na = d.Na;
   double wm0, wc0, wi, wi_sr, gamma;
@@ -209,8 +211,9 @@ static int build_tensor_maps(srukf_handle* h, double* sbuf0, double* sbuf1) {
     if ((rc = encode_map(&hm[TM_S1 + r], sbuf1 ? sbuf1 : sbuf0, p.np, p.np, p.B, TP, 8 * (r + 1)))) return rc;
     if ((rc = encode_map(&hm[TM_UT + r], h->U, p.np, p.Lc, h->chunk, TP, 8 * (r + 1)))) return rc;
   }
-  if ((rc = encode_map(&hm[TM_DZ], h->dZ, p.Lc, p.np, h->chunk, BP_B, 8))) return rc;
-  if ((rc = encode_map(&hm[TM_DZ_ALL], h->dZ_all ? h->dZ_all : h->dZ, p.Lc, p.np, h->dZ_all ? p.B : h->chunk, BP_B, 8)))
+  const uint32_t bpb = (uint32_t)gain_dz_box(p);
+  if ((rc = encode_map(&hm[TM_DZ], h->dZ, p.Lc, p.np, h->chunk, bpb, 8))) return rc;
+  if ((rc = encode_map(&hm[TM_DZ_ALL], h->dZ_all ? h->dZ_all : h->dZ, p.Lc, p.np, h->dZ_all ? p.B : h->chunk, bpb, 8)))
     return rc;
   if (!h->tmaps) CU(cudaMalloc(&h->tmaps, sizeof(hm)));
   CU(cudaMemcpyAsync(h->tmaps, hm, sizeof(hm), cudaMemcpyHostToDevice, h->stream));

@@ -29,7 +29,7 @@ struct DevParams {
   double cpair;  // sqrt(2) * wi_sr * gamma (== 1 analytically for all three weight types)
   double epsilon;
   int newton_iters;
-  int dbg_skip_mma;  // diagnostics only: stream the K chunks but skip the DMMAs (SRUKF_DBG_SKIP_MMA=1)
+  int dbg_skip_mma;  // diagnostics only (SRUKF_DBG_SKIP_MMA): bit 0 stream the K chunks but skip the DMMAs, bit 1 k_gain without loads
 };
 
 // packed upper-triangular row-major: row i holds columns i..n-1
@@ -73,7 +73,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
+      #ifdef SRUKF_TEST_WAIT
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#endif
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
@@ -102,6 +106,26 @@ __device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1
                : "memory");
 }
 // orders this thread's earlier generic-proxy accesses (shared AND global) before later async-proxy (TMA) accesses
+// same with an L2 eviction-priority hint (createpolicy): evict_last for operands that are re-streamed several times,
+// evict_first for data read once
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, "
+      "%5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // 16-byte asynchronous global->shared copy (LDGSTS, L2 only) and its completion hook onto an mbarrier:
 // the executing thread arrives on `bar` once all of its earlier cp.async operations have landed.

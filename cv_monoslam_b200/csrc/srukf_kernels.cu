@@ -14,6 +14,8 @@
 //                and for downdate_mode 1/2.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "srukf_device.cuh"
 
 namespace srukf {
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
 constexpr int NB = 32;      // panel width (columns per contraction pass)
 constexpr int KC = 8;       // K rows per pipeline stage at full width
 #ifndef SRUKF_NSTAGE
-#define SRUKF_NSTAGE 4
+#define SRUKF_NSTAGE 3
 #endif
 constexpr int NSTAGE = SRUKF_NSTAGE;   // ring depth
 constexpr int MAXQ = 5;     // strips per warp: np <= 8 * NW * MAXQ
@@ -378,7 +380,6 @@ constexpr int MAXQ = 5;     // strips per warp: np <= 8 * NW * MAXQ
 #endif
 constexpr int TW = SRUKF_TW;   // payload columns per TMA box (64 or 128)
 constexpr int TP = TW + 8;     // box width == smem row pitch inside a box (doubles), == 8 mod 16
-constexpr int BP_B = 40;    // box width of the dZ operand of k_gain (32 payload columns + 8)
 constexpr int CP_PITCH = NB + 1;  // odd pitch: one row per lane/thread is bank-conflict free
 constexpr int WD_PITCH = NB + 1;
 
@@ -451,8 +452,8 @@ __device__ __forceinline__ void ring_release(Ring& r) {
 //   MASK: the strip on the chunk's own diagonal (s == s0) only takes A(k, col) with col >= k (the entries left of
 //   the diagonal of S's square buffer hold the carried covariance, not zeros).
 //   b2base != nullptr: the LAST of the NTT column tiles takes its B fragment from b2base (pitch TP) instead.
-template <int NW, int QLO, int QHI, int NTT, bool MASK>
-__device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const double* abase, int tstride, int s0,
+template <int NW, int MQ, int NTM, int QLO, int QHI, int NTT, bool MASK>
+__device__ __forceinline__ void mma_chunk(double (&acc)[MQ][NTM][2], const double* abase, int tstride, int s0,
                                           const double* bbase, int bpitch, const double* b2base, int nks, int lane,
                                           int warp) {
   int aoff[QHI > QLO ? QHI - QLO : 1];
@@ -480,12 +481,15 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MAXQ][NB / 8][2], const 
   }
 }
 // runtime (qlo, qhi) -> compile-time instantiation (warp-uniform switch)
-template <int NW, int NTT, bool MASK>
-__device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int qlo, int qhi, const double* abase,
+template <int NW, int MQ, int NTM, int NTT, bool MASK>
+__device__ __forceinline__ void mma_chunk_rt(double (&acc)[MQ][NTM][2], int qlo, int qhi, const double* abase,
                                              int tstride, int s0, const double* bbase, int bpitch,
                                              const double* b2base, int nks, int lane, int warp) {
-#define SRUKF_CASE(LO, HI) \
-  case LO * 8 + HI: mma_chunk<NW, LO, HI, NTT, MASK>(acc, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp); break;
+#define SRUKF_CASE(LO, HI)                                                                                          \
+  case LO * 8 + HI:                                                                                               \
+    if constexpr (HI <= MQ)                                                                                       \
+      mma_chunk<NW, MQ, NTM, LO, HI, NTT, MASK>(acc, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp); \
+    break;
   switch (qlo * 8 + qhi) {
     SRUKF_CASE(0, 1) SRUKF_CASE(0, 2) SRUKF_CASE(0, 3) SRUKF_CASE(0, 4) SRUKF_CASE(0, 5)
     SRUKF_CASE(1, 2) SRUKF_CASE(1, 3) SRUKF_CASE(1, 4) SRUKF_CASE(1, 5)
@@ -496,14 +500,18 @@ __device__ __forceinline__ void mma_chunk_rt(double (&acc)[MAXQ][NB / 8][2], int
   }
 #undef SRUKF_CASE
 }
-template <int NW, bool MASK>
-__device__ __forceinline__ void mma_chunk_any(double (&acc)[MAXQ][NB / 8][2], int qlo, int qhi, int nt,
-                                              const double* abase, int tstride, int s0, const double* bbase, int bpitch,
+template <int NW, int MQ, int NTM, bool MASK>
+__device__ __forceinline__ void mma_chunk_any(double (&acc)[MQ][NTM][2], int qlo, int qhi, int nt, const double* abase,
+                                              int tstride, int s0, const double* bbase, int bpitch,
                                               const double* b2base, int nks, int lane, int warp) {
-  if (nt == NB / 8) mma_chunk_rt<NW, NB / 8, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp);
-  else if (nt == 1) mma_chunk_rt<NW, 1, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp);
-  else if (nt == 2) mma_chunk_rt<NW, 2, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp);
-  else mma_chunk_rt<NW, 3, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp);
+#define SRUKF_NT(N)                                                                                                   \
+  if constexpr (N <= NTM)                                                                                             \
+    if (nt == N) {                                                                                                    \
+      mma_chunk_rt<NW, MQ, NTM, N, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp); \
+      return;                                                                                                         \
+    }
+  SRUKF_NT(NTM) SRUKF_NT(1) SRUKF_NT(2) SRUKF_NT(3) SRUKF_NT(4) SRUKF_NT(5) SRUKF_NT(6) SRUKF_NT(7)
+#undef SRUKF_NT
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -519,9 +527,13 @@ __device__ __forceinline__ void mma_chunk_any(double (&acc)[MAXQ][NB / 8][2], in
 // The triangular product runs on the FP64 tensor pipe: output strips of 8 state rows x 32 measurement
 // columns, K = 8-row blocks of S, each fetched from column 8t on by TMA.
 // -------------------------------------------------------------------------------------------------
-template <int NW>
+// Tile shapes: <8 warps, 5 strips, 4 tiles> (32 columns per pass, 2 CTAs/SM) or <16 warps, 3 strips, 7 tiles>
+// (56 columns per pass, 1 CTA/SM: half as many passes over S -- the kernel is bound by streaming S, not by DMMA).
+template <int NW, int MQ, int NTM>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
+  constexpr int NBG = 8 * NTM;                       // measurement columns per pass
+  constexpr int BPB = (NBG % 16 == 0) ? NBG + 8 : NBG + 16;  // dZ box width == smem pitch, == 8 mod 16
   extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = q.chunk0 + blockIdx.x;
@@ -571,6 +583,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
   }
   Ring ring;
   ring_init<NW>(ring, bars);
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_once = l2_policy_evict_first();
   // KalmanUpdate returns early without matches, :2050 (k_update copies S through); the carried covariance still
   // needs its new robot-feature rows
   const bool none = (*nact == 0);
@@ -582,57 +595,60 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
   // With a carried covariance the robot-feature rows P(robot r, feature f) = sum_{k<=f} S(k,f) S(k, nf+r) (the new
   // robot columns of S, written by k_predict) are the same triangular product with 8 more B columns taken from the
   // S chunk itself: they ride along as one extra column tile of the last pass (or a pass of their own).
-  const int ncg = (Lc + NB - 1) / NB;
-  const bool last_full = (Lc - (ncg - 1) * NB) == NB;
+  const int ncg = (Lc + NBG - 1) / NBG;
+  const bool last_full = (Lc - (ncg - 1) * NBG) == NBG;
   const int npass = ncg + ((q.carry_p && last_full) ? 1 : 0);
   for (int pass = none ? npass - 1 : 0; pass < npass; ++pass) {
-    const int cg = pass * NB;
-    const int ncol = (none || cg >= Lc) ? 0 : ((Lc - cg < NB) ? (Lc - cg) : NB);
+    const int cg = pass * NBG;
+    const int ncol = (none || cg >= Lc) ? 0 : ((Lc - cg < NBG) ? (Lc - cg) : NBG);
     const bool xtile = q.carry_p && (pass == npass - 1);
     const int ntm = ncol / 8;              // measurement-column tiles of this pass
     const int nt = ntm + (xtile ? 1 : 0);  // + the P_fr tile
-    double acc[MAXQ][NB / 8][2];
+    double acc[MQ][NTM][2];
 #pragma unroll
-    for (int qq = 0; qq < MAXQ; ++qq)
+    for (int qq = 0; qq < MQ; ++qq)
 #pragma unroll
-      for (int t = 0; t < NB / 8; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
+      for (int t = 0; t < NTM; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
     // only blocks whose rows can touch a feature row matter: S rows >= nf (robot) have zero dZ
     const int nchunk = (nf + 7) / 8;
     auto produce = [&](int t) {  // elected thread: S rows 8t..8t+7 from column 8t on (boxes of 64+8 columns) + dZ rows
       const int nbx = ntiles(np - 8 * t);
-      const int st = ring_acquire(ring, (uint32_t)((nbx * KC * TP + (ncol ? KC * BP_B : 0)) * sizeof(double)));
+      const int st = ring_acquire(ring, (uint32_t)((nbx * KC * TP + (ncol ? KC * BPB : 0)) * sizeof(double)));
       double* xd = Xs + (size_t)st * sdoubles;
-      for (int j = 0; j < nbx; ++j) tma_load_3d(xd + (size_t)j * KC * TP, tmS, 8 * t + TW * j, 8 * t, b, ring.full + st);
-      if (ncol) tma_load_3d(Bs + (size_t)st * KC * BP_B, tmZ, cg, 8 * t, q.dz_filter0 + blockIdx.x, ring.full + st);
+      // S is streamed once per pass: ask L2 to keep it; dZ is read once
+      for (int j = 0; j < nbx; ++j)
+        tma_load_3d_hint(xd + (size_t)j * KC * TP, tmS, 8 * t + TW * j, 8 * t, b, ring.full + st, pol_keep);
+      if (ncol)
+        tma_load_3d_hint(Bs + (size_t)st * KC * BPB, tmZ, cg, 8 * t, q.dz_filter0 + blockIdx.x, ring.full + st, pol_once);
     };
-    for (int t = 0; t < NSTAGE - 1 && t < nchunk; ++t) {
+    for (int t = 0; t < NSTAGE - 1 && t < nchunk && !(p.dbg_skip_mma & 2); ++t) {
       if (ring_my_turn<NW>(ring)) produce(t);
       ring_next(ring);
     }
     for (int t = 0; t < nchunk; ++t) {
-      if (t + NSTAGE - 1 < nchunk) {
+      if (t + NSTAGE - 1 < nchunk && !(p.dbg_skip_mma & 2)) {
         if (ring_my_turn<NW>(ring)) produce(t + NSTAGE - 1);
         ring_next(ring);
       }
-      const int st = ring_wait(ring);
+      const int st = (p.dbg_skip_mma & 2) ? (t % NSTAGE) : ring_wait(ring);
       const double* xa = Xs + (size_t)st * sdoubles;     // column 0 == state row 8t
-      const double* xb = Bs + (size_t)st * KC * BP_B;
+      const double* xb = Bs + (size_t)st * KC * BPB;
       // output strip s = warp + NW*q receives S rows k <= its own: active slots are q >= qlo
       const int qlo = (t > warp) ? (t - warp + NW - 1) / NW : 0;
       const int xrel = nf - 8 * t;  // chunk column of S(:, nf): new robot columns (columns >= n are zero)
       const double* b2 = xtile ? xa + (size_t)(xrel / TW) * (KC * TP) + (xrel % TW) : nullptr;
-      mma_chunk_any<NW, true>(acc, qlo, nq_w, nt, xa, KC * TP, t, xb, BP_B, b2, KC / 4, lane, warp);
-      ring_release(ring);
+      if (!(p.dbg_skip_mma & 1)) mma_chunk_any<NW, MQ, NTM, true>(acc, qlo, nq_w, nt, xa, KC * TP, t, xb, BPB, b2, KC / 4, lane, warp);
+      if (!(p.dbg_skip_mma & 2)) ring_release(ring);
     }
     // epilogue: apply wi*gamma and si^-1 to each column pair, store Ut[c][f] (transposed), accumulate the shift
 #pragma unroll
-    for (int qq = 0; qq < MAXQ; ++qq) {
+    for (int qq = 0; qq < MQ; ++qq) {
       const int s = warp + NW * qq;
       if (s < nblk) {
         const int f = 8 * s + (lane >> 2);
         double dxp = 0.0;
 #pragma unroll
-        for (int tt = 0; tt < NB / 8; ++tt) {
+        for (int tt = 0; tt < NTM; ++tt) {
           if (tt < ntm) {
             const int c = cg + 8 * tt + 2 * (lane & 3);
             const int j = c >> 1;
@@ -649,7 +665,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
         if (xtile && f < nf && (lane & 3) < 2) {   // P(nf + r, f), r = 2*(lane&3) + {0,1} < 4: tile ntm
           double p0 = 0.0, p1 = 0.0;
 #pragma unroll
-          for (int tt = 0; tt < NB / 8; ++tt)
+          for (int tt = 0; tt < NTM; ++tt)
             if (tt == ntm) { p0 = acc[qq][tt][0]; p1 = acc[qq][tt][1]; }
           const int r = 2 * (lane & 3);
           Sgw[(size_t)(nf + r) * np + f] = p0;
@@ -957,7 +973,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
         const int st = ring_wait(ring);
         if (TIMING && timing) { long long t1_ = clock64(); tkl[2] += t1_ - tk0; tk0 = t1_; }
         const double* xs_ = Xs + (size_t)st * sdoubles;
-        if (!p.dbg_skip_mma) mma_chunk_any<NW, false>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nullptr, nrows / 4, lane, warp);
+        if (!(p.dbg_skip_mma & 1)) mma_chunk_any<NW, MAXQ, NB / 8, false>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nullptr, nrows / 4, lane, warp);
         if (TIMING && timing) { long long t1_ = clock64(); tkl[3] += t1_ - tk0; tk0 = t1_; }
         ring_release(ring);
         if (TIMING && timing) { tkl[4] += clock64() - tk0; tkl[5] += 1; }
@@ -1083,7 +1099,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   flags = __reduce_or_sync(0xffffffffu, flags);
   if (lane == 0 && flags) {
     atomicOr(q.flags + b, flags);
-    if (flags & SRUKF_FLAG_GMW_MODIFIED) {  // only warp 0 can raise it: one queue entry per filter and step
+    if ((flags & SRUKF_FLAG_GMW_MODIFIED) && !p.dbg_skip_mma) {  // only warp 0 can raise it: one queue entry per filter and step
       atomicOr(q.flags + b, SRUKF_FLAG_FALLBACK);
       int slot = atomicAdd(q.worklist, 1);
       q.worklist[1 + slot] = blockIdx.x;
@@ -1341,11 +1357,19 @@ __global__ void __launch_bounds__(256) k_stats_reduce(int B, const double* __res
 // -------------------------------------------------------------------------------------------------
 // host-side launchers (called from srukf_capi.cu)
 // -------------------------------------------------------------------------------------------------
-int tile_warps(const DevParams& p) {  // warps per CTA of the DMMA kernels; 0 = unsupported size
+int tile_warps(const DevParams& p) {  // warps per CTA of k_update; 0 = unsupported size
   if (p.np <= 8 * 8 * MAXQ) return 8;
   if (p.np <= 8 * 16 * MAXQ) return 16;
   return 0;
 }
+// k_gain variant: 0 = <8,5,4> (np <= 320, 2 CTAs/SM), 1 = <16,3,7> (np <= 384, 1 CTA/SM, half the passes),
+// 2 = <16,5,4> (np <= 640)
+int gain_variant(const DevParams& p) {
+  if (const char* e = getenv("SRUKF_GAIN_VARIANT")) return atoi(e);
+  if (p.np <= 8 * 16 * 3) return 1;
+  return 2;
+}
+int gain_dz_box(const DevParams& p) { return gain_variant(p) == 1 ? 72 : 40; }
 size_t predict_smem_bytes(const DevParams& p) {
   size_t slots = (p.L <= NT) ? (size_t)(NT / p.L) * p.L : (size_t)p.L;
   size_t work = slots * 13;
@@ -1357,7 +1381,7 @@ size_t gain_smem_bytes(const DevParams& p) {
   size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
   off += sizeof(double) * (8 * (p.Lc / 2) + p.np);
   off = (off + sizeof(int) * (p.L + 1) + 127) & ~(size_t)127;
-  return off + sizeof(double) * (size_t)NSTAGE * (stage_doubles_for(p.np) + KC * BP_B);
+  return off + sizeof(double) * (size_t)NSTAGE * (stage_doubles_for(p.np) + KC * gain_dz_box(p));
 }
 size_t update_smem_bytes(const DevParams& p) {
   size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
@@ -1376,8 +1400,9 @@ cudaError_t configure_kernels(const DevParams& p) {
   if ((e = cudaFuncSetAttribute(k_predict<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
   if ((e = cudaFuncSetAttribute(k_predict<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
   int gs = (int)gain_smem_bytes(p), us = (int)update_smem_bytes(p);
-  if ((e = cudaFuncSetAttribute(k_gain<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
-  if ((e = cudaFuncSetAttribute(k_gain<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
+  if ((e = cudaFuncSetAttribute(k_gain<8, 5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
+  if ((e = cudaFuncSetAttribute(k_gain<16, 3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
+  if ((e = cudaFuncSetAttribute(k_gain<16, 5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
   if ((e = cudaFuncSetAttribute(k_update<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
   if ((e = cudaFuncSetAttribute(k_update<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
   if ((e = cudaFuncSetAttribute(k_update<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
@@ -1395,8 +1420,11 @@ void launch_predict(const DevParams& p, const StepPtrs& q, int nblocks, bool mot
   else k_predict<false, true><<<nblocks, NT, smem, st>>>(p, q, 0);
 }
 void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
-  if (tile_warps(p) == 8) k_gain<8><<<nblocks, 256, gain_smem_bytes(p), st>>>(p, q);
-  else k_gain<16><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q);
+  switch (gain_variant(p)) {
+    case 0: k_gain<8, 5, 4><<<nblocks, 256, gain_smem_bytes(p), st>>>(p, q); break;
+    case 1: k_gain<16, 3, 7><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
+    default: k_gain<16, 5, 4><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
+  }
 }
 void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
   const bool timing = q.dbg != nullptr;
