@@ -276,6 +276,12 @@ def test_headline_size_single_filter_against_oracle(gpu, oracle):
     run_against_oracle(gpu, oracle, 50, 2, 2, unique=1)
 
 
+@pytest.mark.parametrize("L", [56, 70])
+def test_wide_state_variants_against_oracle(gpu, oracle, L):
+    """n = 340 / 424: k_update with 16 warps per CTA; k_gain variants <16,3,7> and <16,5,4>."""
+    run_against_oracle(gpu, oracle, L, 2, 1, unique=1)
+
+
 def test_stats_match_numpy(gpu):
     from cv_monoslam_b200 import CSLAMBatch
     L, B = 6, 9
