@@ -1358,6 +1358,7 @@ __global__ void __launch_bounds__(256) k_stats_reduce(int B, const double* __res
 // host-side launchers (called from srukf_capi.cu)
 // -------------------------------------------------------------------------------------------------
 int tile_warps(const DevParams& p) {  // warps per CTA of k_update; 0 = unsupported size
+  if (const char* e = getenv("SRUKF_UPDATE_WARPS")) { if (atoi(e) == 16 && p.np <= 8 * 16 * MAXQ) return 16; }
   if (p.np <= 8 * 8 * MAXQ) return 8;
   if (p.np <= 8 * 16 * MAXQ) return 16;
   return 0;
