@@ -272,8 +272,11 @@ def test_properties_at_headline_size(gpu):
 
 
 def test_headline_size_single_filter_against_oracle(gpu, oracle):
-    """One L=50 filter, two steps, against the oracle (about 3 s of CPU)."""
-    run_against_oracle(gpu, oracle, 50, 2, 2, unique=1)
+    """L=50 (n=304) filters from two different worlds, 12 steps each, against the oracle step by step
+    (about 1.2 s of CPU per filter-step)."""
+    worst, flags, _ = run_against_oracle(gpu, oracle, 50, 4, 12, unique=2)
+    assert worst[0] <= 1e-10 and worst[1] <= 1e-10
+    assert not (flags & (gpu.FLAG_NAN | gpu.FLAG_GMW_MODIFIED)).any()
 
 
 @pytest.mark.parametrize("L", [56, 70])

@@ -294,3 +294,43 @@ def test_golden_inputs_are_reproducible_from_seeds():
     sc = synth.make_scenario(3, 4, 6)
     assert np.array_equal(sc.u, g["u"]) and np.array_equal(sc.z, g["z"])
     assert relmax(sc.x0, g["x0"]) < 1e-13 and relmax(sc.S0, g["S0"]) < 1e-9
+
+
+# ---- property tests (hypothesis): size-independent identities of the restated building blocks -------------
+from hypothesis import given, settings, strategies as hst  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None)
+@given(hst.integers(2, 12), hst.integers(0, 10), hst.integers(0, 2 ** 31 - 1))
+def test_property_qr_gram_identity(n, extra, seed):
+    import oracle as O
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n + extra, n)) * rng.uniform(1e-3, 1e3)
+    R = O.qr_R(A)
+    assert np.allclose(np.tril(R, -1), 0)
+    assert relmax(R.T @ R, A.T @ A) < 1e-12
+
+
+@settings(max_examples=25, deadline=None)
+@given(hst.integers(1, 14), hst.integers(0, 2 ** 31 - 1))
+def test_property_mchol_is_cholesky_on_pd_and_always_reconstructs(n, seed):
+    import oracle as O
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n + 3, n))
+    G = A.T @ A + 1e-3 * np.eye(n)
+    S, E, nmod = O.mchol(G)
+    assert nmod == 0 and relmax(S.T @ S, G) < 1e-12
+    H = G - 2.0 * np.outer(A[0], A[0])              # may be indefinite: G + E = S^T S must still hold
+    S2, E2, _ = O.mchol(H)
+    assert relmax(S2.T @ S2, H + np.diag(E2)) < 1e-10
+    assert (np.diag(S2) >= np.sqrt(1e-13) * (1 - 1e-12)).all()
+
+
+@settings(max_examples=20, deadline=None)
+@given(hst.integers(9, 400))
+def test_property_weights_sum_to_one_and_pair_scale_is_one(Na):
+    import oracle as O
+    for wt in (0, 2):
+        w = O.sample_parameters(Na, O.default_params(weight_type=wt))
+        assert abs(w["wm0"] + 2 * Na * w["wi"] - 1.0) < 1e-12
+        assert abs(np.sqrt(2.0) * w["wi_sr"] * w["gamma"] - 1.0) < 1e-14
