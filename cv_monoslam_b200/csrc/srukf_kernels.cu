@@ -917,32 +917,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     const int rowsB = Lc, rowsC = J0;
     const int cA = 0, cB = (rowsB + rpc - 1) / rpc, cC = (rowsC + rpc - 1) / rpc;
     const int nchunks = cB + cC;
-    // accumulators start at -P_old(i, J): tiles below the panel's diagonal come straight from the lower triangle
-    // of the old buffer, diagonal tiles mix lower entries and Pd, tiles above the diagonal are never used
     double acc[MAXQ][NB / 8][2];
-#pragma unroll
-    for (int qq = 0; qq < MAXQ; ++qq) {
-      const int rs = warp + NW * qq;
-      const int i = J0 + 8 * rs + (lane >> 2);
-      const double* prow = Sold + (size_t)i * np;
-#pragma unroll
-      for (int tt = 0; tt < NB / 8; ++tt) {
-        double v0 = 0.0, v1 = 0.0;
-        if (rs < nstrip && tt < nt) {
-          const int j = J0 + 8 * tt + 2 * (lane & 3);
-          if (rs > tt) {
-            const double2 v = *reinterpret_cast<const double2*>(prow + j);
-            v0 = v.x; v1 = v.y;
-          } else if (rs == tt) {
-            v0 = (i > j) ? prow[j] : ((i == j) ? PdOld[i] : 0.0);
-            v1 = (i > j + 1) ? prow[j + 1] : ((i == j + 1) ? PdOld[i] : 0.0);
-          }
-        }
-        acc[qq][tt][0] = -v0;
-        acc[qq][tt][1] = -v1;
-      }
-    }
-
     // rows of chunk t: first row (within its source) and count
     auto chunk_rows = [&](int t, int& row0) -> int {
       if (t < cA + cB) { row0 = (t - cA) * rpc; return (rowsB - row0 < rpc) ? rowsB - row0 : rpc; }
@@ -992,6 +967,32 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
       }
       ring_next(ring);
     }
+    // (the first chunk loads are in flight while the accumulators are initialised from global memory)
+    // accumulators start at -P_old(i, J): tiles below the panel's diagonal come straight from the lower triangle
+    // of the old buffer, diagonal tiles mix lower entries and Pd, tiles above the diagonal are never used
+#pragma unroll
+    for (int qq = 0; qq < MAXQ; ++qq) {
+      const int rs = warp + NW * qq;
+      const int i = J0 + 8 * rs + (lane >> 2);
+      const double* prow = Sold + (size_t)i * np;
+#pragma unroll
+      for (int tt = 0; tt < NB / 8; ++tt) {
+        double v0 = 0.0, v1 = 0.0;
+        if (rs < nstrip && tt < nt) {
+          const int j = J0 + 8 * tt + 2 * (lane & 3);
+          if (rs > tt) {
+            const double2 v = *reinterpret_cast<const double2*>(prow + j);
+            v0 = v.x; v1 = v.y;
+          } else if (rs == tt) {
+            v0 = (i > j) ? prow[j] : ((i == j) ? PdOld[i] : 0.0);
+            v1 = (i > j + 1) ? prow[j + 1] : ((i == j + 1) ? PdOld[i] : 0.0);
+          }
+        }
+        acc[qq][tt][0] = -v0;
+        acc[qq][tt][1] = -v1;
+      }
+    }
+
     consume(0, cB);          // acc = -(P - U U^T) = -G(i, J)
     // G(i, J) is visible now: store the carried covariance of the new factor, P_new = G (+ E on the diagonal,
     // added after the pivots are known), and track max diag / max off-diag of G for beta^2 (:2204-2205)
