@@ -44,6 +44,8 @@ void launch_import(const DevParams& p, int nb, int fmt, const double* ext, doubl
 void launch_export(const DevParams& p, int nb, int fmt, const double* bp, double* ext, cudaStream_t st);
 void launch_form_P(const DevParams& p, int b0, int nb, double* S, double* Pd, cudaStream_t st);
 void launch_cov_block(const DevParams& p, const double* S, int r0, int nr, double* out, cudaStream_t st);
+void launch_gate(const DevParams& p, const double* z, const double* hbar, const double* si, const uint8_t* visible,
+                 double threshold, uint8_t* accept, double* d2, cudaStream_t st);
 void launch_stats(const DevParams& p, const double* x, const double* S, const double* truth, double* perf,
                   const uint32_t* flags, double* out, cudaStream_t st);
 }  // namespace srukf
@@ -448,6 +450,26 @@ int srukf_get_prediction(srukf_t* h, double* hbar, double* si, uint8_t* visible)
   if (si) CU(cudaMemcpyAsync(si, h->si, sizeof(double) * B * 4 * L, cudaMemcpyDeviceToHost, h->stream));
   if (visible) CU(cudaMemcpyAsync(visible, h->visible, B * L, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return SRUKF_OK;
+}
+
+int srukf_chi2_gate(srukf_t* h, const double* z, double threshold, uint8_t* accept, double* d2) {
+  if (!h || !z || !accept) return fail(SRUKF_EINVAL, "srukf_chi2_gate: null argument");
+  if (h->phase != 2) return fail(SRUKF_ESTATE, "srukf_chi2_gate: call srukf_predict_measurement first");
+  CU(cudaSetDevice(h->device));
+  const DevParams& p = h->p;
+  const size_t BL = (size_t)p.B * p.L;
+  CU(cudaMemcpyAsync(h->z, z, sizeof(double) * BL * 2, cudaMemcpyHostToDevice, h->stream));
+  double* d_d2 = nullptr;
+  if (d2) CU(cudaMalloc(&d_d2, sizeof(double) * BL));
+  launch_gate(p, h->z, h->hbar, h->si, h->visible, threshold, h->matched, d_d2, h->stream);
+  h->launches++;
+  cudaError_t e = cudaMemcpyAsync(accept, h->matched, BL, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && d2) e = cudaMemcpyAsync(d2, d_d2, sizeof(double) * BL, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (d_d2) cudaFree(d_d2);
+  if (e != cudaSuccess) return fail(SRUKF_ECUDA, "srukf_chi2_gate", e);
   return SRUKF_OK;
 }
 

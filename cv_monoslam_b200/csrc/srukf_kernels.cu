@@ -1299,6 +1299,31 @@ __global__ void k_cov_block(int n, int np, int nbp, const double* __restrict__ S
   }
 }
 
+// chi-square gate of dataAssociation (SLAM.cpp:1946-1977): one thread per (filter, feature)
+__global__ void k_gate(int total, const double* __restrict__ z, const double* __restrict__ hbar,
+                       const double* __restrict__ si, const uint8_t* __restrict__ visible, double threshold,
+                       uint8_t* accept, double* d2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  uint8_t a = 0;
+  double pii = -1.0;
+  if (visible[i]) {
+    const double* s = si + 4 * (size_t)i;
+    const double p00 = s[0] * s[0] + s[2] * s[2], p01 = s[0] * s[1] + s[2] * s[3], p11 = s[1] * s[1] + s[3] * s[3];
+    const double det = p00 * p11 - p01 * p01;
+    double i00 = 0, i01 = 0, i11 = 0;
+    if (det != 0.) {
+      const double d = 1. / det;
+      i00 = p11 * d; i01 = -p01 * d; i11 = p00 * d;
+    }
+    const double e0 = z[2 * (size_t)i] - hbar[2 * (size_t)i], e1 = z[2 * (size_t)i + 1] - hbar[2 * (size_t)i + 1];
+    pii = (e0 * i00 + e1 * i01) * e0 + (e0 * i01 + e1 * i11) * e1;
+    a = pii < threshold ? 1 : 0;
+  }
+  accept[i] = a;
+  if (d2) d2[i] = pii;
+}
+
 // per-filter squared errors and NEES of (rx, ry, rtheta) -> perf[b][4]
 __global__ void __launch_bounds__(128) k_stats(int n, int np, int nbp, const double* __restrict__ x,
                                                const double* __restrict__ S, const double* __restrict__ truth,
@@ -1449,6 +1474,11 @@ void launch_form_P(const DevParams& p, int b0, int nb, double* S, double* Pd, cu
 }
 void launch_export(const DevParams& p, int nb, int fmt, const double* bp, double* ext, cudaStream_t st) {
   k_export<<<nb, 256, 0, st>>>(p.n, p.np, p.ntri, p.nbp, fmt, bp, ext);
+}
+void launch_gate(const DevParams& p, const double* z, const double* hbar, const double* si, const uint8_t* visible,
+                 double threshold, uint8_t* accept, double* d2, cudaStream_t st) {
+  const int total = p.B * p.L;
+  k_gate<<<(total + 255) / 256, 256, 0, st>>>(total, z, hbar, si, visible, threshold, accept, d2);
 }
 void launch_cov_block(const DevParams& p, const double* S, int r0, int nr, double* out, cudaStream_t st) {
   k_cov_block<<<p.B, 128, 0, st>>>(p.n, p.np, p.nbp, S, r0, nr, out);

@@ -103,6 +103,16 @@ class CSLAMBatch:
         capi.check(self._lib.srukf_get_prediction(self._h, capi.ptr(hbar), capi.ptr(si), capi.ptr(vis)))
         return hbar, si, vis
 
+    CHI2INV_95_2 = 5.99146454710798   # CHI2INV_TABLE(0,2), SLAM.cpp:54
+
+    def chi2Gate(self, candidates: np.ndarray, threshold: float = CHI2INV_95_2):
+        """Chi-square gate of dataAssociation (SLAM.cpp:1946-1977): (isMatching mask [B,L], Mahalanobis d2 [B,L])."""
+        z = np.ascontiguousarray(candidates, dtype=np.float64).reshape(self.B, self.L, 2)
+        acc = np.empty((self.B, self.L), dtype=np.uint8)
+        d2 = np.empty((self.B, self.L))
+        capi.check(self._lib.srukf_chi2_gate(self._h, capi.ptr(z), float(threshold), capi.ptr(acc), capi.ptr(d2)))
+        return acc, d2
+
     def KalmanUpdate(self, matchLocation: np.ndarray, isMatching: np.ndarray):
         z = np.ascontiguousarray(matchLocation, dtype=np.float64).reshape(self.B, self.L, 2)
         m = np.ascontiguousarray(isMatching, dtype=np.uint8).reshape(self.B, self.L)

@@ -81,6 +81,12 @@ int srukf_predict_measurement(srukf_t *h);
 /* m_allPredictSet / map_p->predictLocation, map_p->Si, map_p->isVisible (SLAM.cpp:1724-1738):
  * hbar [B][L][2], si [B][L][4] (2x2 row-major upper triangular), visible [B][L]; any may be NULL. */
 int srukf_get_prediction(srukf_t *h, double *hbar, double *si, uint8_t *visible);
+/* Chi-square gate of CSLAM::dataAssociation (SLAM.cpp:1946-1977, CHI2INV_TABLE(0,2) = 5.99146454710798 at :54):
+ * candidate pixels z [B][L][2] are accepted when (z - predictLocation) (Si^T Si)^-1 (z - predictLocation)^T < threshold
+ * and the feature is visible.  accept [B][L] (the isMatching mask for srukf_kalman_update), d2 [B][L] or NULL.
+ * Call between srukf_predict_measurement and srukf_kalman_update.  (The image-patch correlation that proposes the
+ * candidates in the reference is outside this path.) */
+int srukf_chi2_gate(srukf_t *h, const double *z, double threshold, uint8_t *accept, double *d2);
 /* CSLAM::KalmanUpdate (SLAM.cpp:2048-2096): z [B][L][2] = matchLocation (x,y); matched [B][L] = isMatching. */
 int srukf_kalman_update(srukf_t *h, const double *z, const uint8_t *matched);
 /* predictMotion + predictMeasurement + KalmanUpdate of one CSLAM::SLAM() frame (SLAM.cpp:91,93,99). */

@@ -73,6 +73,7 @@ def lib():
         L.oracle_predict_measurement.argtypes = [C.c_void_p]
         L.oracle_kalman_update.argtypes = [C.c_void_p, _dp, _bp]
         L.oracle_step.argtypes = [C.c_void_p, _dp, _dp, _bp]
+        L.oracle_chi2_gate.argtypes = [C.c_void_p, _dp, C.c_double, _bp, _dp]
         L.oracle_init_features.argtypes = [C.POINTER(OracleParams), _dp, _dp, C.c_int, _dp, C.c_double,
                                            C.c_double, _dp, _dp]
         L.oracle_batch_step.argtypes = [C.c_int, C.c_int, C.POINTER(OracleParams), _dp, _dp, _dp, _dp, _bp,
@@ -183,6 +184,12 @@ class Filter:
     def kalman_update(self, z, matched):
         lib().oracle_kalman_update(self._h, np.ascontiguousarray(z, dtype=np.float64),
                                    np.ascontiguousarray(matched, dtype=np.uint8))
+
+    def chi2_gate(self, z, threshold=5.99146454710798):
+        acc = np.zeros(self.L, dtype=np.uint8)
+        d2 = np.zeros(self.L)
+        lib().oracle_chi2_gate(self._h, np.ascontiguousarray(z, dtype=np.float64), float(threshold), acc, d2)
+        return acc, d2
 
     def step(self, u, z, matched):
         lib().oracle_step(self._h, np.ascontiguousarray(u, dtype=np.float64),

@@ -609,6 +609,30 @@ void oracle_kalman_update(OracleFilter *f, const double *z, const unsigned char 
   }
 }
 
+/* Chi-square gate of dataAssociation, SLAM.cpp:1946-1977: pi = Si^T Si, pii = err * pi^-1 * err^T with
+ * err = candidate - predictLocation, accepted when pii < CHI2INV_TABLE(0,2) (:54).  cv::Mat::inv on a 2x2 is the
+ * determinant closed form.  d2 (may be NULL) receives pii; unvisible features are rejected with d2 = -1. */
+void oracle_chi2_gate(const OracleFilter *f, const double *z, double threshold, unsigned char *accept, double *d2) {
+  for (int id = 0; id < f->L; id++) {
+    accept[id] = 0;
+    if (d2) d2[id] = -1.0;
+    if (!f->visible[id]) continue;
+    const double *si = f->si + 4 * id;
+    double p00 = si[0] * si[0] + si[2] * si[2], p01 = si[0] * si[1] + si[2] * si[3];
+    double p10 = p01, p11 = si[1] * si[1] + si[3] * si[3];
+    double det = p00 * p11 - p01 * p10;
+    double i00 = 0, i01 = 0, i10 = 0, i11 = 0;
+    if (det != 0.) {
+      double d = 1. / det;
+      i00 = p11 * d; i01 = -p01 * d; i10 = -p10 * d; i11 = p00 * d;
+    }
+    double e0 = z[2 * id] - f->hbar[2 * id], e1 = z[2 * id + 1] - f->hbar[2 * id + 1];
+    double pii = (e0 * i00 + e1 * i10) * e0 + (e0 * i01 + e1 * i11) * e1;
+    if (d2) d2[id] = pii;
+    accept[id] = pii < threshold ? 1 : 0;
+  }
+}
+
 void oracle_step(OracleFilter *f, const double *u3, const double *z, const unsigned char *matched) {
   oracle_predict_motion(f, u3);
   oracle_predict_measurement(f);

@@ -121,6 +121,31 @@ def test_prediction_matches_oracle(gpu, oracle):
     assert relmax(hbar[0], hb_ref) < 1e-11
 
 
+def test_chi2_gate_matches_oracle(gpu, oracle):
+    """the chi-square gate of dataAssociation (SLAM.cpp:1946-1977) on the prediction of the device."""
+    from cv_monoslam_b200 import CSLAMBatch
+    L, B = 9, 3
+    sc = synth.make_scenario(L, B, 1)
+    rng = np.random.default_rng(3)
+    z = sc.z[0] + rng.normal(0, 6.0, sc.z[0].shape)        # some candidates far from the prediction
+    g = CSLAMBatch(B, L)
+    g.set_state(sc.x0, sc.S0)
+    g.predictMotion(sc.u[0])
+    g.predictMeasurement()
+    acc, d2 = g.chi2Gate(z)
+    assert 0 < acc.sum() < B * L
+    for b in range(B):
+        f = oracle.Filter(L)
+        f.set_state(sc.x0[b], sc.S0[b])
+        f.predict_motion(sc.u[0, b])
+        f.predict_measurement()
+        a_ref, d_ref = f.chi2_gate(z[b])
+        assert np.array_equal(acc[b], a_ref)
+        assert relmax(d2[b], d_ref) < 1e-9
+    g.KalmanUpdate(z, acc)                                  # the mask feeds the update directly
+    assert np.isfinite(g.get_x()).all()
+
+
 def test_sequential_downdate_mode_matches_oracle(gpu, oracle):
     run_against_oracle(gpu, oracle, 5, 4, 5, mode_gpu=1)
 
