@@ -44,6 +44,9 @@ void launch_import(const DevParams& p, int nb, int fmt, const double* ext, doubl
 void launch_export(const DevParams& p, int nb, int fmt, const double* bp, double* ext, cudaStream_t st);
 void launch_form_P(const DevParams& p, int b0, int nb, double* S, double* Pd, cudaStream_t st);
 void launch_cov_block(const DevParams& p, const double* S, int r0, int nr, double* out, cudaStream_t st);
+void launch_init_features(const DevParams& p, int nblocks, const double* x4, const double* S4, const double* kp,
+                          double rho0, double sigma_rho, double gamma, double wi, double* x, double* S, double* Pd,
+                          double* G, uint32_t* flags, cudaStream_t st);
 void launch_gate(const DevParams& p, const double* z, const double* hbar, const double* si, const uint8_t* visible,
                  double threshold, uint8_t* accept, double* d2, cudaStream_t st);
 void launch_stats(const DevParams& p, const double* x, const double* S, const double* truth, double* perf,
@@ -140,23 +143,9 @@ void srukf_default_params(SrukfParams* p) {
 const char* srukf_last_error(void) { return g_err.c_str(); }
 const char* srukf_version(void) { return "srukf-b200 0.1 (sm_100a, fp64)"; }
 
-static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
-  d.B = B; d.L = L; d.n = 6 * L + 4; d.nf = 6 * L; d.Na = d.n + 5; d.P = 2 * d.Na + 1;
-  d.ntri = d.n * (d.n + 1) / 2;
-  d.np = (d.n + 7) & ~7;
-  d.Lc = (2 * L + 7) & ~7;
-  d.nbp = d.np * d.np;
-  d.cam_dx = s.cam_dx; d.cam_dy = s.cam_dy; d.cam_cx = s.cam_cx; d.cam_cy = s.cam_cy;
-  d.cam_k1 = s.cam_k1; d.cam_k2 = s.cam_k2;
-  d.f1 = s.cam_f / s.cam_dx; d.f2 = s.cam_f / s.cam_dy;  // SLAM.cpp:336-337
-  d.inv_dx = 1.0 / s.cam_dx; d.inv_dy = 1.0 / s.cam_dy;
-  d.img_w = s.image_width; d.img_h = s.image_height;
-  d.a1 = s.a1; d.a2 = s.a2; d.a3 = s.a3; d.a4 = s.a4; d.sigma_measure = s.sigma_measure;
-  d.epsilon = s.epsilon; d.newton_iters = s.newton_iters;
-  { const char* e_ = getenv("SRUKF_DBG_SKIP_MMA"); d.dbg_skip_mma = e_ ? atoi(e_) : 0; }  // bit 0: skip DMMAs, bit 1: skip k_gain's loads
-  // calculateSampleParameter, SLAM.cpp:1050-1103 (operation order kept)
-  const int Na = d.Na;
-  double wm0, wc0, wi, wi_sr, gamma;
+// calculateSampleParameter, SLAM.cpp:1050-1103 (operation order kept)
+static void sample_weights(const SrukfParams& s, int Na, double& wm0, double& wc0, double& wi, double& wi_sr,
+                           double& gamma) {
   if (s.weight_type == 0) {
     wm0 = 1.0 - Na / 3.0; wc0 = 1.0 - Na / 3.0;
     wi = (1.0 - wc0) / (2 * Na); wi_sr = std::sqrt(wi);
@@ -173,6 +162,25 @@ static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
     wm0 = 1.0 / 3.0; wc0 = 1.0 / 3.0;
     wi = 1.0 / (3.0 * Na); wi_sr = std::sqrt(wi);
   }
+}
+
+static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
+  d.B = B; d.L = L; d.n = 6 * L + 4; d.nf = 6 * L; d.Na = d.n + 5; d.P = 2 * d.Na + 1;
+  d.ntri = d.n * (d.n + 1) / 2;
+  d.np = (d.n + 7) & ~7;
+  d.Lc = (2 * L + 7) & ~7;
+  d.nbp = d.np * d.np;
+  d.cam_dx = s.cam_dx; d.cam_dy = s.cam_dy; d.cam_cx = s.cam_cx; d.cam_cy = s.cam_cy;
+  d.cam_k1 = s.cam_k1; d.cam_k2 = s.cam_k2;
+  d.f1 = s.cam_f / s.cam_dx; d.f2 = s.cam_f / s.cam_dy;  // SLAM.cpp:336-337
+  d.inv_dx = 1.0 / s.cam_dx; d.inv_dy = 1.0 / s.cam_dy;
+  d.img_w = s.image_width; d.img_h = s.image_height;
+  d.a1 = s.a1; d.a2 = s.a2; d.a3 = s.a3; d.a4 = s.a4; d.sigma_measure = s.sigma_measure;
+  d.epsilon = s.epsilon; d.newton_iters = s.newton_iters;
+  { const char* e_ = getenv("SRUKF_DBG_SKIP_MMA"); d.dbg_skip_mma = e_ ? atoi(e_) : 0; }  // bit 0: skip DMMAs, bit 1: skip k_gain's loads
+  double wm0, wc0, wi, wi_sr, gamma;
+  sample_weights(s, d.Na, wm0, wc0, wi, wi_sr, gamma);
+  const int Na = d.Na;
   d.gamma = gamma; d.wm0 = wm0; d.wc0 = wc0; d.wi = wi; d.wi_sr = wi_sr;
   d.Wsum = wm0 + 2.0 * Na * wi;
   d.cpair = std::sqrt(2.0) * wi_sr * gamma;
@@ -384,6 +392,36 @@ static int get_state_any(srukf_t* h, double* x, double* S, int fmt, const char* 
   }
   if (x) CU(cudaMemcpyAsync(x, h->x, sizeof(double) * (size_t)h->p.B * h->p.n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return SRUKF_OK;
+}
+
+int srukf_init_features(srukf_t* h, const double* x4, const double* S4, const double* keypoints, double rho0,
+                        double sigma_rho) {
+  if (!h || !x4 || !S4 || !keypoints) return fail(SRUKF_EINVAL, "srukf_init_features: null argument");
+  CU(cudaSetDevice(h->device));
+  const DevParams& p = h->p;
+  const size_t B = (size_t)p.B;
+  double wm0, wc0, wi, wi_sr, gamma;
+  sample_weights(h->prm, 4 + 3 * p.L, wm0, wc0, wi, wi_sr, gamma);   // Na of the initialisation, SLAM.cpp:827,867
+  double* d_in = nullptr;
+  CU(cudaMalloc(&d_in, sizeof(double) * B * (20 + 2 * (size_t)p.L)));
+  double *d_x4 = d_in, *d_S4 = d_in + 4 * B, *d_kp = d_in + 20 * B;
+  cudaError_t e = cudaMemcpyAsync(d_x4, x4, sizeof(double) * 4 * B, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_S4, S4, sizeof(double) * 16 * B, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_kp, keypoints, sizeof(double) * 2 * p.L * B, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    double* Pd = h->Pd;   // null in downdate modes 1 / 2 (no carried covariance)
+    const int nblocks = (int)(B < (size_t)h->gslots ? B : (size_t)h->gslots);
+    launch_init_features(p, nblocks, d_x4, d_S4, d_kp, rho0, sigma_rho, gamma, wi, h->x, h->S, Pd, h->G, h->flags,
+                         h->stream);
+    h->launches++;
+    e = cudaStreamSynchronize(h->stream);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(d_in);
+  if (e != cudaSuccess) return fail(SRUKF_ECUDA, "srukf_init_features", e);
+  h->phase = 0;
   return SRUKF_OK;
 }
 

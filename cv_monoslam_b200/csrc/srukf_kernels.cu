@@ -1253,6 +1253,169 @@ __global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mo
 }
 
 // -------------------------------------------------------------------------------------------------
+// k_init_features -- feature initialisation at frame 1 (CSLAM::addFeatures with dimOld = 4, SLAM.cpp:818-871;
+// passSigmaThroughMapingFunction :1177-1250; QrAndCholeskyForInitilization :1260-1300; getPermutationMatrix
+// :1303-1334).  The reference draws 2Na+1 sigma points of [robot(4) | (u, v, rho) per key-point], Na = 4 + 3L,
+// from sr = blockdiag(S4, diag(sigma_pix, sigma_pix, sigma_rho)...), maps every key-point to (theta, phi, rho)
+// through undistortion and the robot heading, stacks [robot | angles | anchor = robot xyz], takes R of the QR of
+// the weighted deviations from the image of sigma_0 and permutes to the canonical order.
+// sr is block diagonal, so only 14 sigma points move a given key-point (8 robot points through the heading, 6 of
+// its own); all other deviations are exactly zero.  One CTA per filter forms the covariance those deviations
+// define, directly in canonical order, and factorises it with the reference's modified Cholesky (mchol_inplace);
+// the factor equals the reference's permuted QR factor up to row signs and the EPSILON floor on the 3L anchor
+// directions (P has rank 4 + 3L).  The carried covariance is rebuilt from the factor (form_P).
+// -------------------------------------------------------------------------------------------------
+struct InitArgs {
+  const double* x4;   // [B][4]     robot prior mean (x, y, z, theta)
+  const double* S4;   // [B][4][4]  robot prior factor (rows are used as the reference uses them, :851-857)
+  const double* kp;   // [B][L][2]  key-points, distorted pixels (pt.x, pt.y) (:859-861)
+  double rho0, sigma_rho, gamma, wi;
+  int nb;
+};
+
+// undistortOnePoint (:3224-3236) -> camera ray (:3360-3363, image axes crossed as in the reference) -> world
+// (getTransferMatrix :1031) -> (theta, phi) (:3411-3412)
+__device__ __forceinline__ void init_angles(const DevParams& p, double px, double py, double heading, double& th,
+                                            double& ph) {
+  const double xd = (px - p.cam_cx) * p.cam_dx, yd = (py - p.cam_cy) * p.cam_dy;
+  const double rd = sqrt(xd * xd + yd * yd);
+  const double rd2 = rd * rd;
+  const double d = 1 + p.cam_k1 * rd2 + p.cam_k2 * (rd2 * rd2);
+  const double ux = p.cam_cx + (xd * d) / p.cam_dx, uy = p.cam_cy + (yd * d) / p.cam_dy;
+  const double h0 = (uy - p.cam_cx) / p.f1, h1 = (ux - p.cam_cy) / p.f2;
+  double s, c;
+  sincos(heading, &s, &c);
+  const double w0 = c * h0 - s * h1, w1 = s * h0 + c * h1;
+  th = atan2(w0, 1.0);
+  ph = atan2(-w1, sqrt(w0 * w0 + 1.0));
+}
+
+__global__ void __launch_bounds__(NT) k_init_features(DevParams p, InitArgs a, double* x, double* S, double* Pd,
+                                                      double* G, uint32_t* flagsg) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, n = p.n, L = p.L, np = p.np;
+  double* wcol = sm;             // n     (mchol_inplace)
+  double* red = wcol + n;        // 40
+  double* av = red + 40;         // [L][8][2]  (theta, phi) deviations under the 8 robot sigma points
+  double* Bj = av + 16 * L;      // [L][3][3]  covariance contribution of the key-point's own 6 sigma points
+  double* Ar = Bj + 9 * L;       // [L][2][4]  cross covariance angles x robot
+  double* Prr = Ar + 8 * L;      // [4][4]
+  double* dr = Prr + 16;         // [8][4]     robot deviations, q = 2k + (0: +gamma, 1: -gamma)
+  double* Gb = G + (size_t)blockIdx.x * p.ntri;
+  for (int item = blockIdx.x; item < a.nb; item += gridDim.x) {
+    const int b = item;
+    const double* x4 = a.x4 + 4 * (size_t)b;
+    const double* S4 = a.S4 + 16 * (size_t)b;
+    const double* kp = a.kp + 2 * (size_t)L * b;
+    double* xb = x + (size_t)b * n;
+    double* Sb = S + (size_t)b * p.nbp;
+    if (tid < 32) {   // sigma = mu*1 + e*(+-gamma) + 0 (:1159-1160), deviation from sigma_0 = mu
+      const int q = tid >> 2, c = tid & 3, k = q >> 1;
+      const double e = S4[4 * k + c];
+      const double v = x4[c] * 1 + e * ((q & 1) ? (-1) * a.gamma : a.gamma) + 0;
+      dr[4 * q + c] = v - x4[c];
+    }
+    for (int i = tid; i < p.nbp; i += NT) {   // the factor's buffer: zero, identity on the padding diagonal
+      const int r = i / np, c = i - r * np;
+      Sb[i] = (r == c && r >= n) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int j = tid; j < L; j += NT) {
+      const double px = kp[2 * j], py = kp[2 * j + 1], h0 = x4[3];
+      double t0, f0;
+      init_angles(p, px, py, h0, t0, f0);
+      double st = 0.0, sf = 0.0;     // sums of deviations for the mean (:1235-1240; wm0 + 2 Na wi = 1)
+      for (int q = 0; q < 8; ++q) {
+        double t, f;
+        init_angles(p, px, py, h0 + dr[4 * q + 3], t, f);
+        av[(j * 8 + q) * 2 + 0] = t - t0;
+        av[(j * 8 + q) * 2 + 1] = f - f0;
+        st += t - t0;
+        sf += f - f0;
+      }
+      double bb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < 2; ++c)
+        for (int sgn = 0; sgn < 2; ++sgn) {
+          const double g = sgn ? (-1) * a.gamma : a.gamma;
+          const double qx = (c == 0) ? px * 1 + p.sigma_measure * g + 0 : px;
+          const double qy = (c == 1) ? py * 1 + p.sigma_measure * g + 0 : py;
+          double t, f;
+          init_angles(p, qx, qy, h0, t, f);
+          const double dt = t - t0, df = f - f0;
+          st += dt;
+          sf += df;
+          bb[0] += dt * dt; bb[1] += dt * df; bb[4] += df * df;
+        }
+      const double dp = (a.rho0 * 1 + a.sigma_rho * a.gamma + 0) - a.rho0;
+      const double dm = (a.rho0 * 1 + a.sigma_rho * ((-1) * a.gamma) + 0) - a.rho0;
+      bb[8] = dp * dp + dm * dm;
+      bb[3] = bb[1];
+      for (int e = 0; e < 9; ++e) Bj[9 * j + e] = a.wi * bb[e];
+      xb[6 * j + 0] = x4[0];   // anchor = robot position at first sight (:1223, :1247-1248)
+      xb[6 * j + 1] = x4[1];
+      xb[6 * j + 2] = x4[2];
+      xb[6 * j + 3] = t0 + a.wi * st;
+      xb[6 * j + 4] = f0 + a.wi * sf;
+      xb[6 * j + 5] = a.rho0 + a.wi * (dp + dm);
+    }
+    if (tid < 4) xb[6 * L + tid] = x4[tid];
+    if (tid < 16) {
+      const int c1 = tid >> 2, c2 = tid & 3;
+      double s = 0.0;
+      for (int q = 0; q < 8; ++q) s += dr[4 * q + c1] * dr[4 * q + c2];
+      Prr[tid] = a.wi * s;
+    }
+    __syncthreads();
+    for (int i = tid; i < 8 * L; i += NT) {
+      const int j = i >> 3, t = (i >> 2) & 1, c = i & 3;
+      double s = 0.0;
+      for (int q = 0; q < 8; ++q) s += av[(j * 8 + q) * 2 + t] * dr[4 * q + c];
+      Ar[i] = a.wi * s;
+    }
+    __syncthreads();
+    // covariance in canonical order, lower triangle by columns (== upper-packed rows)
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int c0 = warp; c0 < n; c0 += NT / 32) {
+      int j1 = -1, k1 = c0 - 6 * L;   // non-angle rows act through robot component k (anchor k < 3)
+      bool ang1 = false;
+      if (c0 < 6 * L) { j1 = c0 / 6; k1 = c0 - 6 * j1; ang1 = k1 >= 3; if (ang1) k1 -= 3; }
+      double* col = Gb + tri_off(c0, n);
+      for (int r0 = c0 + lane; r0 < n; r0 += 32) {
+        int j2 = -1, k2 = r0 - 6 * L;
+        bool ang2 = false;
+        if (r0 < 6 * L) { j2 = r0 / 6; k2 = r0 - 6 * j2; ang2 = k2 >= 3; if (ang2) k2 -= 3; }
+        double v;
+        if (!ang1 && !ang2) v = Prr[4 * k1 + k2];
+        else if (ang1 && !ang2) v = (k1 < 2) ? Ar[(j1 * 2 + k1) * 4 + k2] : 0.0;
+        else if (!ang1 && ang2) v = (k2 < 2) ? Ar[(j2 * 2 + k2) * 4 + k1] : 0.0;
+        else {
+          v = 0.0;
+          if (k1 < 2 && k2 < 2) {
+            double s = 0.0;
+            for (int q = 0; q < 8; ++q) s += av[(j1 * 8 + q) * 2 + k1] * av[(j2 * 8 + q) * 2 + k2];
+            v = a.wi * s;
+          }
+          if (j1 == j2) v += Bj[9 * j1 + 3 * k1 + k2];
+        }
+        col[r0 - c0] = v;
+      }
+    }
+    __syncthreads();
+    uint32_t flags = 0;
+    mchol_inplace(p, Gb, Sb, wcol, red, flags);
+    __syncthreads();
+    for (int i = tid; i < n; i += NT)
+      if (!isfinite(Sb[bp_idx(i, i, np)]) || !isfinite(xb[i])) flags |= SRUKF_FLAG_NAN;
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (tid == 0) flagsg[b] = 0;
+    __syncthreads();
+    if ((tid & 31) == 0 && flags) atomicOr(flagsg + b, flags);
+    if (Pd) form_P(p, Sb, Pd + (size_t)b * np);
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // auxiliary kernels
 // -------------------------------------------------------------------------------------------------
 // external formats <-> internal square S.  fmt 0: dense [nb][n][n] row-major, fmt 1: upper-packed [nb][ntri]
@@ -1465,6 +1628,14 @@ void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStrea
 }
 void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, int use_worklist, cudaStream_t st) {
   k_downdate<<<nblocks, NT, downdate_smem_bytes(p), st>>>(p, q, mode, use_worklist);
+}
+void launch_init_features(const DevParams& p, int nblocks, const double* x4, const double* S4, const double* kp,
+                          double rho0, double sigma_rho, double gamma, double wi, double* x, double* S, double* Pd,
+                          double* G, uint32_t* flags, cudaStream_t st) {
+  InitArgs a{x4, S4, kp, rho0, sigma_rho, gamma, wi, p.B};
+  const size_t smem = sizeof(double) * (size_t)(p.n + 40 + 33 * p.L + 16 + 32);
+  cudaFuncSetAttribute(k_init_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_init_features<<<nblocks, NT, smem, st>>>(p, a, x, S, Pd, G, flags);
 }
 void launch_import(const DevParams& p, int nb, int fmt, const double* ext, double* bp, cudaStream_t st) {
   k_import<<<nb, 256, 0, st>>>(p.n, p.np, p.ntri, p.nbp, fmt, ext, bp);

@@ -103,6 +103,18 @@ class CSLAMBatch:
         capi.check(self._lib.srukf_get_prediction(self._h, capi.ptr(hbar), capi.ptr(si), capi.ptr(vis)))
         return hbar, si, vis
 
+    def initFeatures(self, x4: np.ndarray, S4: np.ndarray, keypoints: np.ndarray, rho0: float = 1.0 / 3.0,
+                     sigma_rho: float | None = None):
+        """Frame-1 feature initialisation on the device (addFeatures with an empty map, SLAM.cpp:818-871,
+        1177-1334): x4 [B,4], S4 [B,4,4], keypoints [B,L,2] distorted pixels.  Replaces the state of every filter."""
+        x4 = np.ascontiguousarray(np.broadcast_to(np.asarray(x4, dtype=np.float64), (self.B, 4)))
+        S4 = np.ascontiguousarray(np.broadcast_to(np.asarray(S4, dtype=np.float64), (self.B, 4, 4)))
+        kp = np.ascontiguousarray(keypoints, dtype=np.float64).reshape(self.B, self.L, 2)
+        if sigma_rho is None:
+            sigma_rho = rho0 / 2.0     # SLAM.cpp:173
+        capi.check(self._lib.srukf_init_features(self._h, capi.ptr(x4), capi.ptr(S4), capi.ptr(kp), float(rho0),
+                                                 float(sigma_rho)))
+
     CHI2INV_95_2 = 5.99146454710798   # CHI2INV_TABLE(0,2), SLAM.cpp:54
 
     def chi2Gate(self, candidates: np.ndarray, threshold: float = CHI2INV_95_2):

@@ -214,8 +214,17 @@ class CSLAMBatch {
 
   void setState(const double* x, const double* S_packed) { check(srukf_set_state(h_, x, S_packed), "srukf_set_state"); }
   void getState(double* x, double* S_packed) { check(srukf_get_state(h_, x, S_packed), "srukf_get_state"); }
+  /* addFeatures with an empty map (SLAM.cpp:818-871): x4 [B][4], S4 [B][4][4], keypoints [B][L][2] */
+  void initFeatures(const double* x4, const double* S4, const double* keypoints, double rho0 = 1.0 / 3.0,
+                    double sigma_rho = 1.0 / 6.0) {
+    check(srukf_init_features(h_, x4, S4, keypoints, rho0, sigma_rho), "srukf_init_features");
+  }
   void predictMotion() { check(srukf_predict_motion(h_, Ut.data()), "srukf_predict_motion"); }
   void predictMeasurement() { check(srukf_predict_measurement(h_), "srukf_predict_measurement"); }
+  /* chi-square gate of dataAssociation (SLAM.cpp:1946-1977) on the candidates in matchLocation -> isMatching */
+  void chi2Gate(double threshold = 5.99146454710798, double* d2 = nullptr) {
+    check(srukf_chi2_gate(h_, matchLocation.data(), threshold, isMatching.data(), d2), "srukf_chi2_gate");
+  }
   void KalmanUpdate() { check(srukf_kalman_update(h_, matchLocation.data(), isMatching.data()), "srukf_kalman_update"); }
   void SLAM() { check(srukf_step(h_, Ut.data(), matchLocation.data(), isMatching.data()), "srukf_step"); }
   void sync() { check(srukf_sync(h_), "srukf_sync"); }

@@ -81,6 +81,15 @@ int srukf_predict_measurement(srukf_t *h);
 /* m_allPredictSet / map_p->predictLocation, map_p->Si, map_p->isVisible (SLAM.cpp:1724-1738):
  * hbar [B][L][2], si [B][L][4] (2x2 row-major upper triangular), visible [B][L]; any may be NULL. */
 int srukf_get_prediction(srukf_t *h, double *hbar, double *si, uint8_t *visible);
+/* Feature initialisation at frame 1: CSLAM::addFeatures with an empty map (SLAM.cpp:818-871), i.e.
+ * passSigmaThroughMapingFunction (:1177-1250), QrAndCholeskyForInitilization (:1260-1300) and getPermutationMatrix
+ * (:1303-1334).  For every filter: robot prior x4 [B][4] = (x, y, z, theta) and its factor S4 [B][4][4] (dense rows,
+ * :851-857), L key-points in distorted pixels keypoints [B][L][2] = (pt.x, pt.y) (:859-861), inverse-depth prior rho0
+ * +- sigma_rho (:172-173); the pixel sigma is SrukfParams.sigma_measure.  Replaces the whole state (m_X_k, m_S_k) of
+ * the handle, in canonical order [f_0(6) .. f_{L-1}(6) | robot(4)]; flags are reset (SRUKF_FLAG_GMW_FLOOR is expected:
+ * the anchors make the covariance rank 4 + 3L). */
+int srukf_init_features(srukf_t *h, const double *x4, const double *S4, const double *keypoints, double rho0,
+                        double sigma_rho);
 /* Chi-square gate of CSLAM::dataAssociation (SLAM.cpp:1946-1977, CHI2INV_TABLE(0,2) = 5.99146454710798 at :54):
  * candidate pixels z [B][L][2] are accepted when (z - predictLocation) (Si^T Si)^-1 (z - predictLocation)^T < threshold
  * and the feature is visible.  accept [B][L] (the isMatching mask for srukf_kalman_update), d2 [B][L] or NULL.

@@ -73,6 +73,7 @@ def lib():
         L.oracle_predict_measurement.argtypes = [C.c_void_p]
         L.oracle_kalman_update.argtypes = [C.c_void_p, _dp, _bp]
         L.oracle_step.argtypes = [C.c_void_p, _dp, _dp, _bp]
+        L.oracle_filter_get_prediction.argtypes = [C.c_void_p, _dp, _dp, _bp]
         L.oracle_chi2_gate.argtypes = [C.c_void_p, _dp, C.c_double, _bp, _dp]
         L.oracle_init_features.argtypes = [C.POINTER(OracleParams), _dp, _dp, C.c_int, _dp, C.c_double,
                                            C.c_double, _dp, _dp]
@@ -184,6 +185,14 @@ class Filter:
     def kalman_update(self, z, matched):
         lib().oracle_kalman_update(self._h, np.ascontiguousarray(z, dtype=np.float64),
                                    np.ascontiguousarray(matched, dtype=np.uint8))
+
+    def prediction(self):
+        """(m_allPredictSet [L,2], Si [L,2,2], isVisible [L]) after predict_measurement"""
+        hbar = np.zeros((self.L, 2))
+        si = np.zeros((self.L, 2, 2))
+        vis = np.zeros(self.L, dtype=np.uint8)
+        lib().oracle_filter_get_prediction(self._h, hbar, si, vis)
+        return hbar, si, vis
 
     def chi2_gate(self, z, threshold=5.99146454710798):
         acc = np.zeros(self.L, dtype=np.uint8)

@@ -609,6 +609,13 @@ void oracle_kalman_update(OracleFilter *f, const double *z, const unsigned char 
   }
 }
 
+/* m_allPredictSet / map_p->Si / isVisible as left by predictMeasurement (SLAM.cpp:1724-1738) */
+void oracle_filter_get_prediction(const OracleFilter *f, double *hbar, double *si, unsigned char *visible) {
+  memcpy(hbar, f->hbar, sizeof(double) * 2 * (size_t)f->L);
+  memcpy(si, f->si, sizeof(double) * 4 * (size_t)f->L);
+  memcpy(visible, f->visible, (size_t)f->L);
+}
+
 /* Chi-square gate of dataAssociation, SLAM.cpp:1946-1977: pi = Si^T Si, pii = err * pi^-1 * err^T with
  * err = candidate - predictLocation, accepted when pii < CHI2INV_TABLE(0,2) (:54).  cv::Mat::inv on a 2x2 is the
  * determinant closed form.  d2 (may be NULL) receives pii; unvisible features are rejected with d2 = -1. */

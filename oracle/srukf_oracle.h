@@ -108,6 +108,7 @@ void oracle_predict_motion(OracleFilter *f, const double *u3);
 void oracle_predict_measurement(OracleFilter *f);
 /* SLAM.cpp:2048-2096 (+2020-2038, 2106-2153); z is L x 2 (matchLocation.x, .y), matched L flags */
 void oracle_kalman_update(OracleFilter *f, const double *z, const unsigned char *matched);
+void oracle_filter_get_prediction(const OracleFilter *f, double *hbar, double *si, unsigned char *visible);
 /* SLAM.cpp:1946-1977 chi-square gate of candidate pixels z (L x 2) against the current prediction */
 void oracle_chi2_gate(const OracleFilter *f, const double *z, double threshold, unsigned char *accept, double *d2);
 /* one full frame of the hot path */
