@@ -47,6 +47,9 @@ void launch_cov_block(const DevParams& p, const double* S, int r0, int nr, doubl
 void launch_init_features(const DevParams& p, int nblocks, const double* x4, const double* S4, const double* kp,
                           double rho0, double sigma_rho, double gamma, double wi, double* x, double* S, double* Pd,
                           double* G, uint32_t* flags, cudaStream_t st);
+void launch_delete_feature(const DevParams& p, int nblocks, const double* xs, const double* Ss, int ns, int nps,
+                           const int* ids, double* x, double* S, double* Pd, double* G, double* V,
+                           const uint32_t* flags_src, uint32_t* flags, cudaStream_t st);
 void launch_gate(const DevParams& p, const double* z, const double* hbar, const double* si, const uint8_t* visible,
                  double threshold, uint8_t* accept, double* d2, cudaStream_t st);
 void launch_stats(const DevParams& p, const double* x, const double* S, const double* truth, double* perf,
@@ -422,6 +425,35 @@ int srukf_init_features(srukf_t* h, const double* x4, const double* S4, const do
   cudaFree(d_in);
   if (e != cudaSuccess) return fail(SRUKF_ECUDA, "srukf_init_features", e);
   h->phase = 0;
+  return SRUKF_OK;
+}
+
+int srukf_delete_feature(srukf_t* src, srukf_t* dst, const int32_t* ids) {
+  if (!src || !dst || !ids) return fail(SRUKF_EINVAL, "srukf_delete_feature: null argument");
+  if (src == dst || dst->p.B != src->p.B || dst->p.L != src->p.L - 1 || dst->device != src->device)
+    return fail(SRUKF_EINVAL, "srukf_delete_feature: dst must be another handle on the same device with the same B and L-1 features");
+  for (int b = 0; b < src->p.B; ++b)
+    if (ids[b] < 0 || ids[b] >= src->p.L) return fail(SRUKF_EINVAL, "srukf_delete_feature: feature id out of range");
+  CU(cudaSetDevice(dst->device));
+  CU(cudaStreamSynchronize(src->stream));
+  const DevParams& p = dst->p;
+  const int nblocks = p.B < dst->gslots ? p.B : dst->gslots;
+  int* d_ids = nullptr;
+  double* d_V = nullptr;
+  CU(cudaMalloc(&d_ids, sizeof(int) * (size_t)p.B));
+  cudaError_t e = cudaMalloc(&d_V, sizeof(double) * (size_t)nblocks * 6 * p.np);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_ids, ids, sizeof(int) * (size_t)p.B, cudaMemcpyHostToDevice, dst->stream);
+  if (e == cudaSuccess) {
+    launch_delete_feature(p, nblocks, src->x, src->S, src->p.n, src->p.np, d_ids, dst->x, dst->S, dst->Pd, dst->G, d_V,
+                          src->flags, dst->flags, dst->stream);
+    dst->launches++;
+    e = cudaStreamSynchronize(dst->stream);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(d_ids);
+  if (d_V) cudaFree(d_V);
+  if (e != cudaSuccess) return fail(SRUKF_ECUDA, "srukf_delete_feature", e);
+  dst->phase = 0;
   return SRUKF_OK;
 }
 

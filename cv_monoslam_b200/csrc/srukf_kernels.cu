@@ -1155,9 +1155,9 @@ __device__ void mchol_inplace(const DevParams& p, double* G, double* S, double* 
   }
 }
 
-// G = S^T S - sum_c Ut(c,:)^T Ut(c,:) over c in [c0, c1), upper-packed
+// G = S^T S + sign * sum_c Ut(c,:)^T Ut(c,:) over c in [c0, c1), upper-packed
 __device__ void form_G(const DevParams& p, const double* __restrict__ S, const double* __restrict__ Ut, int c0, int c1,
-                       double* G) {
+                       double* G, double sign = -1.0) {
   const int n = p.n, np = p.np;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int j = warp; j < n; j += NT / 32) {
@@ -1170,7 +1170,7 @@ __device__ void form_G(const DevParams& p, const double* __restrict__ S, const d
       }
       double sub = 0.0;
       for (int c = c0; c < c1; ++c) sub += Ut[(size_t)c * np + j] * Ut[(size_t)c * np + i];
-      col[i - j] = acc - sub;
+      col[i - j] = fma(sign, sub, acc);   // sign = -1: DOWNDATING (:2149), +1: UPDATING (:2144)
     }
   }
 }
@@ -1416,6 +1416,63 @@ __global__ void __launch_bounds__(NT) k_init_features(DevParams p, InitArgs a, d
 }
 
 // -------------------------------------------------------------------------------------------------
+// k_delete_feature -- deleteOneFeature (SLAM.cpp:2637-2663): filter b drops feature ids[b].  The surviving
+// entries of x and rows/columns of S move up, the six dropped rows (surviving columns only) are V, and
+// GSLCholeskyUpdate(V^T, UPDATING, NEEDNOT_REORDER) (:2139-2153) runs as in the reference: six times
+// S <- modifiedCholesky(S^T S + v v^T).  p describes the DESTINATION (L-1 features); the source has pitch nps.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_delete_feature(DevParams p, const double* __restrict__ xs,
+                                                       const double* __restrict__ Ss, int ns, int nps,
+                                                       const int* __restrict__ ids, double* x, double* S, double* Pd,
+                                                       double* G, double* V, const uint32_t* flags_src,
+                                                       uint32_t* flagsg) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, n = p.n, np = p.np;
+  double* wcol = sm;
+  double* red = wcol + n;
+  double* Gb = G + (size_t)blockIdx.x * p.ntri;
+  double* Vb = V + (size_t)blockIdx.x * 6 * np;
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const int id = ids[b];
+    const double* So = Ss + (size_t)b * nps * nps;
+    double* Sb = S + (size_t)b * p.nbp;
+    for (int r = tid; r < n; r += NT) x[(size_t)b * n + r] = xs[(size_t)b * ns + ((r < 6 * id) ? r : r + 6)];
+    for (int i = tid; i < p.nbp; i += NT) {
+      const int r = i / np, c = i - r * np;
+      double v = 0.0;
+      if (r < n && c < n) {
+        if (c >= r) v = So[(size_t)((r < 6 * id) ? r : r + 6) * nps + ((c < 6 * id) ? c : c + 6)];
+      } else if (r == c) {
+        v = 1.0;
+      }
+      Sb[i] = v;
+    }
+    // V: the dropped rows over the surviving columns.  Left of the dropped block the factor is structurally zero
+    // (in the fused mode the source holds the carried covariance there, not the factor)
+    for (int i = tid; i < 6 * np; i += NT) {
+      const int r = i / np, c = i - r * np;
+      Vb[i] = (c < n && c >= 6 * id) ? So[(size_t)(6 * id + r) * nps + c + 6] : 0.0;
+    }
+    __syncthreads();
+    uint32_t flags = 0;
+    for (int c = 0; c < 6; ++c) {
+      form_G(p, Sb, Vb, c, c + 1, Gb, +1.0);
+      __syncthreads();
+      mchol_inplace(p, Gb, Sb, wcol, red, flags);
+      __syncthreads();
+    }
+    for (int i = tid; i < n; i += NT)
+      if (!isfinite(Sb[bp_idx(i, i, np)])) flags |= SRUKF_FLAG_NAN;
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (tid == 0) flagsg[b] = flags_src[b];
+    __syncthreads();
+    if ((tid & 31) == 0 && flags) atomicOr(flagsg + b, flags);
+    if (Pd) form_P(p, Sb, Pd + (size_t)b * np);
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // auxiliary kernels
 // -------------------------------------------------------------------------------------------------
 // external formats <-> internal square S.  fmt 0: dense [nb][n][n] row-major, fmt 1: upper-packed [nb][ntri]
@@ -1636,6 +1693,11 @@ void launch_init_features(const DevParams& p, int nblocks, const double* x4, con
   const size_t smem = sizeof(double) * (size_t)(p.n + 40 + 33 * p.L + 16 + 32);
   cudaFuncSetAttribute(k_init_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_init_features<<<nblocks, NT, smem, st>>>(p, a, x, S, Pd, G, flags);
+}
+void launch_delete_feature(const DevParams& p, int nblocks, const double* xs, const double* Ss, int ns, int nps,
+                           const int* ids, double* x, double* S, double* Pd, double* G, double* V,
+                           const uint32_t* flags_src, uint32_t* flags, cudaStream_t st) {
+  k_delete_feature<<<nblocks, NT, downdate_smem_bytes(p), st>>>(p, xs, Ss, ns, nps, ids, x, S, Pd, G, V, flags_src, flags);
 }
 void launch_import(const DevParams& p, int nb, int fmt, const double* ext, double* bp, cudaStream_t st) {
   k_import<<<nb, 256, 0, st>>>(p.n, p.np, p.ntri, p.nbp, fmt, ext, bp);

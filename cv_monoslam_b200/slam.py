@@ -36,6 +36,7 @@ class CSLAMBatch:
         self.B, self.L, self.n = int(B), int(L), 6 * int(L) + 4
         self.ntri = self.n * (self.n + 1) // 2
         self.params = params or capi.default_params()
+        self.device = int(device)
         h = C.c_void_p()
         capi.check(self._lib.srukf_create(device, self.B, self.L, C.byref(self.params), C.byref(h)))
         self._h = h
@@ -114,6 +115,14 @@ class CSLAMBatch:
             sigma_rho = rho0 / 2.0     # SLAM.cpp:173
         capi.check(self._lib.srukf_init_features(self._h, capi.ptr(x4), capi.ptr(S4), capi.ptr(kp), float(rho0),
                                                  float(sigma_rho)))
+
+    def deleteFeature(self, ids) -> "CSLAMBatch":
+        """deleteOneFeature (SLAM.cpp:2637-2663) for every filter: filter b drops feature ids[b].  Returns a new
+        batch with L-1 features (a handle has a fixed state dimension); this one is left untouched."""
+        ids = np.ascontiguousarray(np.broadcast_to(np.asarray(ids, dtype=np.int32), (self.B,)))
+        out = CSLAMBatch(self.B, self.L - 1, self.params, self.device)
+        capi.check(self._lib.srukf_delete_feature(self._h, out._h, capi.ptr(ids)))
+        return out
 
     CHI2INV_95_2 = 5.99146454710798   # CHI2INV_TABLE(0,2), SLAM.cpp:54
 

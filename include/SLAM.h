@@ -219,6 +219,10 @@ class CSLAMBatch {
                     double sigma_rho = 1.0 / 6.0) {
     check(srukf_init_features(h_, x4, S4, keypoints, rho0, sigma_rho), "srukf_init_features");
   }
+  /* deleteOneFeature (SLAM.cpp:2637-2663): filter b drops feature ids[b]; dst must hold L-1 features */
+  void deleteFeature(CSLAMBatch& dst, const int32_t* ids) {
+    check(srukf_delete_feature(h_, dst.h_, ids), "srukf_delete_feature");
+  }
   void predictMotion() { check(srukf_predict_motion(h_, Ut.data()), "srukf_predict_motion"); }
   void predictMeasurement() { check(srukf_predict_measurement(h_), "srukf_predict_measurement"); }
   /* chi-square gate of dataAssociation (SLAM.cpp:1946-1977) on the candidates in matchLocation -> isMatching */

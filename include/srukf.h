@@ -90,6 +90,13 @@ int srukf_get_prediction(srukf_t *h, double *hbar, double *si, uint8_t *visible)
  * the anchors make the covariance rank 4 + 3L). */
 int srukf_init_features(srukf_t *h, const double *x4, const double *S4, const double *keypoints, double rho0,
                         double sigma_rho);
+/* CSLAM::deleteOneFeature (SLAM.cpp:2637-2663), state and factor part: filter b of src drops feature ids[b] (0-based
+ * position in the state); the reduced state is written to dst, a handle created for the same B, L-1 features and the
+ * same device (the state dimension of a handle is fixed).  The factor is rebuilt as the reference does it: the dropped
+ * rows V of S re-enter through GSLCholeskyUpdate(V^T, UPDATING, NEEDNOT_REORDER) (:2661-2662, :2139-2153), six
+ * modified-Cholesky re-factorisations of S^T S + v v^T.  Flags of src carry over.  src is left untouched.  The
+ * NEED_REORDER branch (:2122-2138, pivoted factorisation on the frame after features were added) is not built. */
+int srukf_delete_feature(srukf_t *src, srukf_t *dst, const int32_t *ids);
 /* Chi-square gate of CSLAM::dataAssociation (SLAM.cpp:1946-1977, CHI2INV_TABLE(0,2) = 5.99146454710798 at :54):
  * candidate pixels z [B][L][2] are accepted when (z - predictLocation) (Si^T Si)^-1 (z - predictLocation)^T < threshold
  * and the feature is visible.  accept [B][L] (the isMatching mask for srukf_kalman_update), d2 [B][L] or NULL.

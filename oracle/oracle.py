@@ -77,6 +77,7 @@ def lib():
         L.oracle_chi2_gate.argtypes = [C.c_void_p, _dp, C.c_double, _bp, _dp]
         L.oracle_init_features.argtypes = [C.POINTER(OracleParams), _dp, _dp, C.c_int, _dp, C.c_double,
                                            C.c_double, _dp, _dp]
+        L.oracle_delete_feature.argtypes = [C.POINTER(OracleParams), C.c_int, _dp, _dp, C.c_int, _dp, _dp]
         L.oracle_batch_step.argtypes = [C.c_int, C.c_int, C.POINTER(OracleParams), _dp, _dp, _dp, _dp, _bp,
                                         C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib = L
@@ -151,6 +152,17 @@ def init_features(p, x4, S4, kp, rho0, sigma_rho):
     lib().oracle_init_features(C.byref(p), np.ascontiguousarray(x4, dtype=np.float64),
                                np.ascontiguousarray(S4, dtype=np.float64), M, kp, rho0, sigma_rho, x, S)
     return x, S
+
+
+def delete_feature(p, x, S, id_):
+    """deleteOneFeature (SLAM.cpp:2637-2663): (x [n], S [n,n]) -> (x [n-6], S [n-6,n-6])"""
+    n = x.shape[0]
+    L = (n - 4) // 6
+    xo = np.zeros(n - 6)
+    So = np.zeros((n - 6, n - 6))
+    lib().oracle_delete_feature(C.byref(p), L, np.ascontiguousarray(x, dtype=np.float64),
+                                np.ascontiguousarray(S, dtype=np.float64), int(id_), xo, So)
+    return xo, So
 
 
 class Filter:

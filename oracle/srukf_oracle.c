@@ -552,6 +552,32 @@ static void cholesky_update(OracleFilter *f, const double *U, int nc, double sig
   free(E);
 }
 
+/* deleteOneFeature, SLAM.cpp:2637-2663 (state and factor part; the list surgery at :2665-2706 has no arithmetic):
+ * drop the feature's six entries of x and its six rows and columns of S, keep the dropped rows (restricted to the
+ * surviving columns) as V, then GSLCholeskyUpdate(V^T, UPDATING, NEEDNOT_REORDER) (:2661-2662, :2139-2153): six
+ * rank-one updates, each re-forming S^T S + v v^T and re-factorising with the modified Cholesky.
+ * x [n], S [n x n] of an L-feature filter -> x_out [n-6], S_out [(n-6) x (n-6)]. */
+void oracle_delete_feature(const OracleParams *p, int L, const double *x, const double *S, int id, double *x_out,
+                           double *S_out) {
+  int n = 6 * L + 4, m = n - 6;
+  OracleFilter *f = oracle_filter_create(L - 1, p);
+  double *U = (double *)calloc((size_t)m * 6, sizeof(double)); /* VT: m x 6 */
+  for (int r = 0; r < m; r++) {
+    int rs = (r < 6 * id) ? r : r + 6;
+    f->x[r] = x[rs];
+    for (int c = 0; c < m; c++) {
+      int cs = (c < 6 * id) ? c : c + 6;
+      f->S[(size_t)r * m + c] = S[(size_t)rs * n + cs];
+    }
+    for (int k = 0; k < 6; k++) U[(size_t)r * 6 + k] = S[(size_t)(6 * id + k) * n + rs];
+  }
+  cholesky_update(f, U, 6, +1.0);
+  memcpy(x_out, f->x, sizeof(double) * (size_t)m);
+  memcpy(S_out, f->S, sizeof(double) * (size_t)m * m);
+  free(U);
+  oracle_filter_destroy(f);
+}
+
 /* SLAM.cpp:2048-2096 (non-RANSAC branch) */
 void oracle_kalman_update(OracleFilter *f, const double *z, const unsigned char *matched) {
   int n = f->n, P = f->P, L = f->L;

@@ -120,6 +120,10 @@ void oracle_step(OracleFilter *f, const double *u3, const double *z, const unsig
 void oracle_init_features(const OracleParams *p, const double *x4, const double *S4, int M,
                           const double *kp, double rho0, double sigma_rho, double *x_out, double *S_out);
 
+/* deleteOneFeature (SLAM.cpp:2637-2663) + GSLCholeskyUpdate(UPDATING, NEEDNOT_REORDER) (:2139-2153) */
+void oracle_delete_feature(const OracleParams *p, int L, const double *x, const double *S, int id, double *x_out,
+                           double *S_out);
+
 /* batch helpers used by tests / bench (OpenMP over filters when available) */
 void oracle_batch_step(int B, int L, const OracleParams *p, double *x /*B x n*/, double *S /*B x n x n*/,
                        const double *u /*B x 3*/, const double *z /*B x L x 2*/,

@@ -180,6 +180,48 @@ def test_init_features_matches_oracle(gpu, oracle, L, B):
             assert relmax(Sg[b].T @ Sg[b], S1.T @ S1) < 10 * tol
 
 
+def test_delete_feature_matches_oracle(gpu, oracle):
+    """deleteOneFeature + rank-6 UPDATING (SLAM.cpp:2637-2663, 2139-2153) after two filter steps, a
+    different feature per filter (first, middle, last), then one more step on the reduced state."""
+    from cv_monoslam_b200 import CSLAMBatch, SrukfError
+    L, B = 8, 4
+    sc = synth.make_scenario(L, B, 3)
+    g = CSLAMBatch(B, L)
+    g.set_state(sc.x0, sc.S0)
+    for s in range(2):
+        g.SLAM(sc.u[s], sc.z[s], sc.matched[s])
+    x, S = g.get_state()
+    ids = np.array([0, 3, L - 1, 5], dtype=np.int32)
+    g2 = g.deleteFeature(ids)
+    assert g2.L == L - 1
+    x2, S2 = g2.get_state()
+    p = oracle.default_params()
+    keep = [np.r_[0:6 * i, 6 * i + 6:6 * L + 4] for i in ids]
+    for b in range(B):
+        xo, So = oracle.delete_feature(p, x[b], S[b], ids[b])
+        assert np.array_equal(x2[b], xo)
+        assert relmax(S2[b].T @ S2[b], So.T @ So) < 1e-9
+        P = S[b].T @ S[b]                                  # deletion == marginalisation of the covariance
+        assert relmax(S2[b].T @ S2[b], P[np.ix_(keep[b], keep[b])]) < 1e-9
+    # the reduced filters keep running: one more frame against the oracle from the same reduced state
+    u = sc.u[2]
+    z = np.stack([np.delete(sc.z[2, b], ids[b], axis=0) for b in range(B)])
+    m = np.stack([np.delete(sc.matched[2, b], ids[b]) for b in range(B)])
+    g2.SLAM(u, z, m)
+    x3, S3 = g2.get_state()
+    for b in range(B):
+        f = oracle.Filter(L - 1)
+        f.set_state(x2[b], S2[b])
+        f.step(u[b], z[b], m[b])
+        x1, S1 = f.get_state()
+        assert relmax(x3[b], x1) < 1e-9
+        assert relmax(S3[b].T @ S3[b], S1.T @ S1) < 1e-9
+    with pytest.raises(SrukfError):
+        g.deleteFeature(np.full(B, L, dtype=np.int32))      # id out of range
+    x_again, _ = g.get_state()
+    assert np.array_equal(x_again, x)                       # the source handle is untouched
+
+
 def test_chi2_gate_matches_oracle(gpu, oracle):
     """the chi-square gate of dataAssociation (SLAM.cpp:1946-1977) on the prediction of the device."""
     from cv_monoslam_b200 import CSLAMBatch
