@@ -21,6 +21,7 @@ struct StepPtrs {
   double* S2; int* worklist; int rel0; unsigned long long* dbg;
   const CUtensorMap* tmaps; int sbuf; int tm_dz; int dz_filter0;
   double* Pd; double* Pd2; int carry_p;
+  double* G2; int n_new;
 };
 // tensor-map table layout and box geometry (must match srukf_kernels.cu)
 constexpr int TM_S0 = 0, TM_S1 = 4, TM_UT = 8, TM_DZ = 12, TM_DZ_ALL = 13, TM_COUNT = 14;
@@ -84,6 +85,7 @@ struct srukf_handle {
   // scratch
   int chunk = 0;           // filters per pipeline pass of srukf_step
   double *dZ = nullptr, *U = nullptr, *G = nullptr;
+  double* G2 = nullptr;    // scratch of the NEED_REORDER update (allocated on first use)
   int gslots = 0;          // CTAs (and G scratch slots) of the reference-order fallback kernel
   int* worklist = nullptr;
   unsigned long long* dbg = nullptr;  // phase-cycle counters (SRUKF_PHASE_TIMING=1)
@@ -324,7 +326,7 @@ int srukf_destroy(srukf_t* h) {
   if (!h) return SRUKF_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->Pd, h->Pd2, h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+  void* ptrs[] = {h->G2, h->Pd, h->Pd2, h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -341,6 +343,7 @@ static StepPtrs base_ptrs(srukf_t* h) {
   q.S2 = h->S2; q.worklist = h->worklist; q.rel0 = 0; q.dbg = h->dbg;
   q.tmaps = h->tmaps; q.sbuf = h->sbuf; q.tm_dz = TM_DZ; q.dz_filter0 = 0;
   q.Pd = h->Pd; q.Pd2 = h->Pd2; q.carry_p = (h->prm.downdate_mode == 0) ? 1 : 0;
+  q.G2 = h->G2; q.n_new = 0;
   return q;
 }
 
@@ -590,6 +593,38 @@ int srukf_kalman_update(srukf_t* h, const double* z, const uint8_t* matched) {
     run_update(h, qq, b0, nb);
   }
   flip_buffers(h);
+  CU(cudaGetLastError());
+  h->phase = 0;
+  return SRUKF_OK;
+}
+
+int srukf_kalman_update_reorder(srukf_t* h, const double* z, const uint8_t* matched, int n_new) {
+  if (!h || !z || !matched) return fail(SRUKF_EINVAL, "srukf_kalman_update_reorder: null argument");
+  if (n_new < 0 || n_new > h->p.L) return fail(SRUKF_EINVAL, "srukf_kalman_update_reorder: n_new must be in 0..L");
+  if (n_new == 0) return srukf_kalman_update(h, z, matched);   // m_nAddings == 0: NEEDNOT_REORDER (:2087-2090)
+  if (h->phase != 2) return fail(SRUKF_ESTATE, "srukf_kalman_update_reorder: call srukf_predict_measurement first");
+  CU(cudaSetDevice(h->device));
+  const DevParams& p = h->p;
+  if (!h->G2) CU(cudaMalloc(&h->G2, sizeof(double) * (size_t)h->gslots * ((size_t)p.ntri + 2 * (size_t)p.nbp)));
+  CU(cudaMemcpyAsync(h->z, z, sizeof(double) * (size_t)p.B * 2 * p.L, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->matched, matched, (size_t)p.B * p.L, cudaMemcpyHostToDevice, h->stream));
+  StepPtrs q = base_ptrs(h);
+  q.n_new = n_new;
+  for (int b0 = 0; b0 < p.B; b0 += h->chunk) {
+    const int nb = p.B - b0 < h->chunk ? p.B - b0 : h->chunk;
+    StepPtrs qq = q;
+    if (h->dZ_all) { qq.dZ = h->dZ_all + (size_t)b0 * p.np * p.Lc; qq.tm_dz = TM_DZ_ALL; qq.dz_filter0 = b0; }
+    qq.chunk0 = b0;
+    launch_gain(p, qq, nb, h->stream);
+    h->launches++;
+    for (int r0 = 0; r0 < nb; r0 += h->gslots) {   // reference order, in place on the current factor
+      qq.rel0 = r0;
+      const int m = nb - r0 < h->gslots ? nb - r0 : h->gslots;
+      launch_downdate(p, qq, m, 3, 0, h->stream);
+      h->launches++;
+    }
+    if (h->Pd) { launch_form_P(p, b0, nb, h->S, h->Pd, h->stream); h->launches++; }   // carried covariance rebuilt
+  }
   CU(cudaGetLastError());
   h->phase = 0;
   return SRUKF_OK;

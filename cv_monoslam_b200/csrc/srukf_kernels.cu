@@ -53,6 +53,8 @@ struct StepPtrs {
   double* Pd;              // [B][np] diagonal of P belonging to q.S
   double* Pd2;             // [B][np] ... belonging to q.S2
   int carry_p;
+  double* G2;             // [gslots][ntri + 2 nbp] scratch of the NEED_REORDER downdate (mode 3; lazily allocated)
+  int n_new;              // m_nFilters: the last n_new features were added on the previous frame (mode 3)
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -1113,8 +1115,10 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
 // G (column j of the lower triangle == row j of an upper-packed layout), right-looking, unblocked, in place;
 // S (blocked-packed) receives sqrt(D) L^T.
 // -------------------------------------------------------------------------------------------------
-__device__ void mchol_inplace(const DevParams& p, double* G, double* S, double* wcol, double* red, uint32_t& flags) {
-  const int tid = threadIdx.x, n = p.n, np = p.np;
+// (n, pitch, eps explicit: the NEED_REORDER path factorises a leading block; evec, if given, receives E_j = d_j - c_jj)
+__device__ void mchol_core(int n, int np, double eps, double* G, double* S, double* wcol, double* red, uint32_t& flags,
+                           double* evec) {
+  const int tid = threadIdx.x;
   // :2204-2211
   double gmax = -1.0e300, zmax = 0.0;
   for (int j = 0; j < n; ++j) {
@@ -1134,8 +1138,9 @@ __device__ void mchol_inplace(const DevParams& p, double* G, double* S, double* 
     for (int i = 1 + tid; i < len; i += NT) th = fmax(th, fabs(col[i]));
     th = block_max<NT>(th, red);  // :2264-2276
     const double cjj = col[0];
-    const double d = fmax(fmax(p.epsilon, fabs(cjj)), th * th / beta2);  // :2279-2285
-    if (d != cjj) flags |= (d > 16.0 * p.epsilon) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
+    const double d = fmax(fmax(eps, fabs(cjj)), th * th / beta2);  // :2279-2285
+    if (d != cjj) flags |= (d > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
+    if (evec && tid == 0) evec[j] = d - cjj;
     const double sd = sqrt(d);
     double* srow = S + bp_idx(j, j, np);
     for (int i = tid; i < len; i += NT) {
@@ -1153,6 +1158,9 @@ __device__ void mchol_inplace(const DevParams& p, double* G, double* S, double* 
     }
     __syncthreads();
   }
+}
+__device__ void mchol_inplace(const DevParams& p, double* G, double* S, double* wcol, double* red, uint32_t& flags) {
+  mchol_core(p.n, p.np, p.epsilon, G, S, wcol, red, flags, nullptr);
 }
 
 // G = S^T S + sign * sum_c Ut(c,:)^T Ut(c,:) over c in [c0, c1), upper-packed
@@ -1196,10 +1204,74 @@ __global__ void __launch_bounds__(NT) k_form_P(DevParams p, double* S, double* P
 }
 
 // -------------------------------------------------------------------------------------------------
+// NEED_REORDER branch of GSLCholeskyUpdate (SLAM.cpp:2122-2138) with CholeskyDecompositionWithPivoting
+// (:2158-2179), one U column: the last M features were added on the previous frame, getPermutationMatrix
+// (:1303-1334) orders the state [old features | robot | (theta,phi,rho) of the new | anchors of the new], the
+// leading r = n - 3M block C11 of the permuted G gets the modified Cholesky R11, R12 = R11^-T C12, and the factor
+// [R11 R12; 0 0] is permuted back and re-triangularised (:2137).  Its covariance is G with the anchor block
+// replaced by R12^T R12 and E11 added to the leading diagonal (R11^T R11 = C11 + E11, R11^T R12 = C12), which is
+// what is factorised here in canonical order.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reorder_canon(int a, int n, int M) {   // disordered index -> canonical index
+  const int dimOld = n - 6 * M;
+  if (a < dimOld - 4) return a;
+  if (a < dimOld) return n - 4 + (a - (dimOld - 4));
+  if (a < dimOld + 3 * M) { const int id = (a - dimOld) / 3, kk = (a - dimOld) - 3 * id; return dimOld - 4 + 6 * id + 3 + kk; }
+  const int t = a - dimOld - 3 * M, id = t / 3, kk = t - 3 * id;
+  return dimOld - 4 + 6 * id + kk;
+}
+__device__ __forceinline__ double sym_packed(const double* G, int i, int j, int n) {
+  return (i >= j) ? G[tri_off(j, n) + (i - j)] : G[tri_off(i, n) + (j - i)];
+}
+__device__ void reorder_project(const DevParams& p, int M, double* G, double* G2, double* wcol, double* red,
+                                uint32_t& flags) {
+  const int tid = threadIdx.x, n = p.n, np = p.np;
+  const int r = n - 3 * M, m3 = 3 * M;
+  double* C11 = G2;                    // packed r(r+1)/2
+  double* R11 = G2 + p.ntri;           // [r][np]
+  double* X = R11 + p.nbp;             // [r][m3]   C12, then R12
+  double* evec = red + 40;             // [r]  (k_downdate's shared memory: wcol[n] | red[40] | evec[n])
+  for (int b = tid >> 5; b < r; b += NT / 32) {   // column b of the lower triangle of C11
+    const int cb = reorder_canon(b, n, M);
+    double* col = C11 + tri_off(b, r);
+    for (int a = b + (tid & 31); a < r; a += 32) col[a - b] = sym_packed(G, reorder_canon(a, n, M), cb, n);
+  }
+  for (int i = tid; i < r * m3; i += NT) {
+    const int a = i / m3, t = i - a * m3;
+    X[i] = sym_packed(G, reorder_canon(a, n, M), reorder_canon(r + t, n, M), n);
+  }
+  __syncthreads();
+  mchol_core(r, np, p.epsilon, C11, R11, wcol, red, flags, evec);   // :2173
+  __syncthreads();
+  // R12 = R11^-T C12 (:2175): forward substitution with R11^T, one thread per column of C12
+  for (int t = tid; t < m3; t += NT) {
+    for (int a = 0; a < r; ++a) {
+      double s = X[(size_t)a * m3 + t];
+      for (int kk = 0; kk < a; ++kk) s = fma(-R11[(size_t)kk * np + a], X[(size_t)kk * m3 + t], s);
+      X[(size_t)a * m3 + t] = s / R11[(size_t)a * np + a];
+    }
+  }
+  __syncthreads();
+  // covariance of [R11 R12; 0 0] back in canonical order: anchor block = R12^T R12, leading diagonal += E11
+  for (int i = tid; i < m3 * m3; i += NT) {
+    const int t1 = i / m3, t2 = i - t1 * m3;
+    const int c1 = reorder_canon(r + t1, n, M), c2 = reorder_canon(r + t2, n, M);
+    if (c1 < c2) continue;
+    double s = 0.0;
+    for (int kk = 0; kk < r; ++kk) s = fma(X[(size_t)kk * m3 + t1], X[(size_t)kk * m3 + t2], s);
+    G[tri_off(c2, n) + (c1 - c2)] = s;
+  }
+  for (int a = tid; a < r; a += NT) G[tri_off(reorder_canon(a, n, M), n)] += evec[a];
+  __syncthreads();
+}
+
+// -------------------------------------------------------------------------------------------------
 // k_downdate -- GSLCholeskyUpdate, DOWNDATING / NEEDNOT_REORDER (SLAM.cpp:2106-2121,2139-2153), reference order.
 //   mode 1: the reference's sequence: for every matched feature, for each of its 2 U columns,
 //           re-form S^T S, subtract u u^T, re-factorise.
 //   mode 2: one unblocked GMW factorisation of S^T S - U U^T (all matched features at once).
+//   mode 3: mode 1 with the NEED_REORDER projection per column (:2122-2138), for the frame after q.n_new features
+//           were added.
 //   use_worklist: process only the filters queued by k_update (their result is rebuilt from S_old into S2);
 //   otherwise one CTA per filter of the chunk, in place on S.
 // -------------------------------------------------------------------------------------------------
@@ -1235,6 +1307,7 @@ __global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mo
         for (int c = 0; c < 2; ++c) {
           form_G(p, Sg, Ut, 2 * j + c, 2 * j + c + 1, G);
           __syncthreads();
+          if (mode == 3) reorder_project(p, q.n_new, G, q.G2 + (size_t)blockIdx.x * (p.ntri + 2 * (size_t)p.nbp), wcol, red, flags);
           mchol_inplace(p, G, Sg, wcol, red, flags);
           __syncthreads();
         }
@@ -1638,7 +1711,7 @@ size_t update_smem_bytes(const DevParams& p) {
   size_t panel = (size_t)p.np * CP_PITCH;
   return off + sizeof(double) * (ring > panel ? ring : panel);
 }
-size_t downdate_smem_bytes(const DevParams& p) { return sizeof(double) * ((size_t)p.n + 40); }
+size_t downdate_smem_bytes(const DevParams& p) { return sizeof(double) * (2 * (size_t)p.n + 40); }
 
 cudaError_t configure_kernels(const DevParams& p) {
   cudaError_t e;

@@ -139,6 +139,13 @@ class CSLAMBatch:
         m = np.ascontiguousarray(isMatching, dtype=np.uint8).reshape(self.B, self.L)
         capi.check(self._lib.srukf_kalman_update(self._h, capi.ptr(z), capi.ptr(m)))
 
+    def KalmanUpdateReorder(self, matchLocation: np.ndarray, isMatching: np.ndarray, n_new: int):
+        """KalmanUpdate on the frame after n_new features were added (m_nAddings != 0): NEED_REORDER branch of
+        GSLCholeskyUpdate (SLAM.cpp:2083-2086, 2122-2138, 2158-2179)."""
+        z = np.ascontiguousarray(matchLocation, dtype=np.float64).reshape(self.B, self.L, 2)
+        m = np.ascontiguousarray(isMatching, dtype=np.uint8).reshape(self.B, self.L)
+        capi.check(self._lib.srukf_kalman_update_reorder(self._h, capi.ptr(z), capi.ptr(m), int(n_new)))
+
     def SLAM(self, Ut, matchLocation, isMatching):
         """One frame of the hot path: predictMotion + predictMeasurement + KalmanUpdate (SLAM.cpp:91-99)."""
         u = np.ascontiguousarray(Ut, dtype=np.float64).reshape(self.B, 3)

@@ -230,6 +230,10 @@ class CSLAMBatch {
     check(srukf_chi2_gate(h_, matchLocation.data(), threshold, isMatching.data(), d2), "srukf_chi2_gate");
   }
   void KalmanUpdate() { check(srukf_kalman_update(h_, matchLocation.data(), isMatching.data()), "srukf_kalman_update"); }
+  /* KalmanUpdate while m_nAddings != 0 (NEED_REORDER, SLAM.cpp:2083-2086): nNew = m_nFilters */
+  void KalmanUpdateReorder(int nNew) {
+    check(srukf_kalman_update_reorder(h_, matchLocation.data(), isMatching.data(), nNew), "srukf_kalman_update_reorder");
+  }
   void SLAM() { check(srukf_step(h_, Ut.data(), matchLocation.data(), isMatching.data()), "srukf_step"); }
   void sync() { check(srukf_sync(h_), "srukf_sync"); }
   srukf_t* handle() { return h_; }

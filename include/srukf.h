@@ -90,12 +90,17 @@ int srukf_get_prediction(srukf_t *h, double *hbar, double *si, uint8_t *visible)
  * the anchors make the covariance rank 4 + 3L). */
 int srukf_init_features(srukf_t *h, const double *x4, const double *S4, const double *keypoints, double rho0,
                         double sigma_rho);
+/* CSLAM::KalmanUpdate on the frame after features were added (m_nAddings != 0, SLAM.cpp:2083-2086): the covariance
+ * downdate takes GSLCholeskyUpdate's NEED_REORDER branch (:2122-2138) with CholeskyDecompositionWithPivoting
+ * (:2158-2179) for every U column.  n_new = m_nFilters, the number of features (the last ones of the state) added on the
+ * previous frame -- L on the frame after srukf_init_features; 0 behaves as srukf_kalman_update.  Reference order, one
+ * CTA per filter (not the fused kernel): meant for the one frame that follows an addition. */
+int srukf_kalman_update_reorder(srukf_t *h, const double *z, const uint8_t *matched, int n_new);
 /* CSLAM::deleteOneFeature (SLAM.cpp:2637-2663), state and factor part: filter b of src drops feature ids[b] (0-based
  * position in the state); the reduced state is written to dst, a handle created for the same B, L-1 features and the
  * same device (the state dimension of a handle is fixed).  The factor is rebuilt as the reference does it: the dropped
  * rows V of S re-enter through GSLCholeskyUpdate(V^T, UPDATING, NEEDNOT_REORDER) (:2661-2662, :2139-2153), six
- * modified-Cholesky re-factorisations of S^T S + v v^T.  Flags of src carry over.  src is left untouched.  The
- * NEED_REORDER branch (:2122-2138, pivoted factorisation on the frame after features were added) is not built. */
+ * modified-Cholesky re-factorisations of S^T S + v v^T.  Flags of src carry over.  src is left untouched. */
 int srukf_delete_feature(srukf_t *src, srukf_t *dst, const int32_t *ids);
 /* Chi-square gate of CSLAM::dataAssociation (SLAM.cpp:1946-1977, CHI2INV_TABLE(0,2) = 5.99146454710798 at :54):
  * candidate pixels z [B][L][2] are accepted when (z - predictLocation) (Si^T Si)^-1 (z - predictLocation)^T < threshold

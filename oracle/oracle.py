@@ -73,6 +73,7 @@ def lib():
         L.oracle_predict_measurement.argtypes = [C.c_void_p]
         L.oracle_kalman_update.argtypes = [C.c_void_p, _dp, _bp]
         L.oracle_step.argtypes = [C.c_void_p, _dp, _dp, _bp]
+        L.oracle_filter_set_new_features.argtypes = [C.c_void_p, C.c_int]
         L.oracle_filter_get_prediction.argtypes = [C.c_void_p, _dp, _dp, _bp]
         L.oracle_chi2_gate.argtypes = [C.c_void_p, _dp, C.c_double, _bp, _dp]
         L.oracle_init_features.argtypes = [C.POINTER(OracleParams), _dp, _dp, C.c_int, _dp, C.c_double,
@@ -197,6 +198,10 @@ class Filter:
     def kalman_update(self, z, matched):
         lib().oracle_kalman_update(self._h, np.ascontiguousarray(z, dtype=np.float64),
                                    np.ascontiguousarray(matched, dtype=np.uint8))
+
+    def set_new_features(self, n_new: int):
+        """m_nAddings: KalmanUpdate takes the NEED_REORDER branch (SLAM.cpp:2083-2086) while it is non-zero"""
+        lib().oracle_filter_set_new_features(self._h, int(n_new))
 
     def prediction(self):
         """(m_allPredictSet [L,2], Si [L,2,2], isVisible [L]) after predict_measurement"""

@@ -514,8 +514,108 @@ void oracle_predict_measurement(OracleFilter *f) {
 
 /* GSLCholeskyUpdate, NEEDNOT_REORDER branch, SLAM.cpp:2106-2121,2139-2153.
  * u is n x nc row-major; sign = -1 downdating (:2149), +1 updating (:2144). */
+/* getPermutationMatrix, SLAM.cpp:1303-1334, for a map whose last M = m_nFilters features are new:
+ * disordered order = [old features 6(L-M) | robot 4 | (theta,phi,rho) of the new 3M | anchors of the new 3M].
+ * canon[a] = canonical (row) index of disordered (column) index a, i.e. m_permutation(canon[a], a) = 1. */
+static void reorder_map(int L, int M, int *canon) {
+  int n = 6 * L + 4, dimOld = n - 6 * M;
+  for (int a = 0; a < dimOld - 4; a++) canon[a] = a;
+  for (int k = 0; k < 4; k++) canon[dimOld - 4 + k] = n - 4 + k;
+  for (int id = 0; id < M; id++)
+    for (int k = 0; k < 3; k++) {
+      canon[dimOld + 3 * M + 3 * id + k] = dimOld - 4 + 6 * id + k;
+      canon[dimOld + 3 * id + k] = dimOld - 4 + 6 * id + 3 + k;
+    }
+}
+
+/* cv::Mat::inv() (DECOMP_LU) on an upper-triangular r x r matrix, OpenCV 2.4.3 modules/core/src/lapack.cpp LUImpl
+ * applied to [A | I]: partial pivoting finds the diagonal (everything below it is exactly zero), the elimination
+ * is a no-op, a pivot below DBL_EPSILON makes inv() return the zero matrix; then back substitution
+ * b(i,:) = (b(i,:) - sum_{k>i} A(i,k) b(k,:)) * (1/A(i,i)). */
+static int inv_upper(const double *A, int r, double *X) {
+  memset(X, 0, sizeof(double) * (size_t)r * r);
+  for (int i = 0; i < r; i++) {
+    if (fabs(A[(size_t)i * r + i]) < 2.220446049250313e-16) {
+      memset(X, 0, sizeof(double) * (size_t)r * r);
+      return 0;
+    }
+    X[(size_t)i * r + i] = 1.0;
+  }
+  for (int i = r - 1; i >= 0; i--) {
+    double dinv = -(-1.0 / A[(size_t)i * r + i]); /* LUImpl keeps d = -1/A(i,i) and stores A(i,i) = -d */
+    for (int j = 0; j < r; j++) {
+      double s = X[(size_t)i * r + j];
+      for (int k = i + 1; k < r; k++) s -= A[(size_t)i * r + k] * X[(size_t)k * r + j];
+      X[(size_t)i * r + j] = s * dinv;
+    }
+  }
+  return 1;
+}
+
+/* GSLCholeskyUpdate, NEED_REORDER branch (SLAM.cpp:2122-2138) with CholeskyDecompositionWithPivoting
+ * (:2158-2179): per column, dst = Perm^T (S^T S -+ u u^T) Perm; R11 = modified Cholesky of the leading
+ * covRank x covRank block, R12 = R11^-T dst12, S_dis = [R11 R12; 0 0]; m_S_k = R of QR(Perm S_dis Perm^T).
+ * M = m_nFilters (features added on the previous frame), covRank = dim - 3M (:2131). */
+static void cholesky_update_reorder(OracleFilter *f, const double *U, int nc, double sign, int M) {
+  int n = f->n, r = n - 3 * M, m2 = n - r;
+  double *Pm = f->work_P;
+  int *canon = (int *)malloc(sizeof(int) * (size_t)n);
+  double *dst = (double *)malloc(sizeof(double) * (size_t)n * n);
+  double *Sdis = (double *)malloc(sizeof(double) * (size_t)n * n);
+  double *B = (double *)malloc(sizeof(double) * (size_t)n * n);
+  double *C11 = (double *)malloc(sizeof(double) * (size_t)r * r);
+  double *R11 = (double *)malloc(sizeof(double) * (size_t)r * r);
+  double *Xi = (double *)malloc(sizeof(double) * (size_t)r * r);
+  reorder_map(f->L, M, canon);
+  for (int c = 0; c < nc; c++) {
+    memset(Pm, 0, sizeof(double) * (size_t)n * n); /* src1 = S^T S, :2118 */
+    for (int k = 0; k < n; k++) {
+      const double *row = f->S + (size_t)k * n;
+      for (int i = k; i < n; i++) {
+        double a = row[i];
+        double *pr = Pm + (size_t)i * n;
+        for (int j = k; j < n; j++) pr[j] += a * row[j];
+      }
+    }
+    for (int i = 0; i < n; i++) {
+      double ui = U[(size_t)i * nc + c];
+      for (int j = 0; j < n; j++) Pm[(size_t)i * n + j] = Pm[(size_t)i * n + j] + sign * (ui * U[(size_t)j * nc + c]);
+    }
+    for (int a = 0; a < n; a++) /* :2127 / :2132 */
+      for (int b = 0; b < n; b++) dst[(size_t)a * n + b] = Pm[(size_t)canon[a] * n + canon[b]] + 0;
+    memset(Sdis, 0, sizeof(double) * (size_t)n * n); /* :2161 */
+    if (n == r) {
+      oracle_mchol(dst, n, f->prm.epsilon, Sdis, NULL);
+    } else {
+      for (int a = 0; a < r; a++)
+        for (int b = 0; b < r; b++) C11[(size_t)a * r + b] = dst[(size_t)a * n + b];
+      int mod = oracle_mchol(C11, r, f->prm.epsilon, R11, NULL); /* :2173 */
+      f->n_mchol_calls++;
+      if (mod) f->n_mchol_modified++;
+      inv_upper(R11, r, Xi); /* :2175 R12 = R11.inv().t() * Cov12 */
+      for (int a = 0; a < r; a++) {
+        for (int b = 0; b < r; b++) Sdis[(size_t)a * n + b] = R11[(size_t)a * r + b];
+        for (int t = 0; t < m2; t++) {
+          double s = 0.0;
+          for (int k = 0; k < r; k++) s += Xi[(size_t)k * r + a] * dst[(size_t)k * n + r + t];
+          Sdis[(size_t)a * n + r + t] = s;
+        }
+      }
+    }
+    /* :2137 m_S_k = R of QR(Perm S_dis Perm^T): (Perm X Perm^T)(i,j) = X(dis(i), dis(j)) */
+    for (int a = 0; a < n; a++)
+      for (int b = 0; b < n; b++) B[(size_t)canon[a] * n + canon[b]] = Sdis[(size_t)a * n + b];
+    oracle_qr_R(B, n, n, f->S);
+  }
+  free(Xi); free(R11); free(C11); free(B); free(Sdis); free(dst); free(canon);
+}
+
 static void cholesky_update(OracleFilter *f, const double *U, int nc, double sign) {
   int n = f->n;
+  if (sign < 0 && f->n_new > 0) { /* KalmanUpdate :2083-2090: NEED_REORDER while m_nAddings != 0 */
+    cholesky_update_reorder(f, U, nc, sign, f->n_new);
+    return;
+  }
   double *Pm = f->work_P;
   double *E = (double *)malloc(sizeof(double) * (size_t)n);
   int mode = f->prm.downdate_mode;
@@ -634,6 +734,10 @@ void oracle_kalman_update(OracleFilter *f, const double *z, const unsigned char 
     cholesky_update(f, U, 2, -1.0); /* :2089 */
   }
 }
+
+/* m_nAddings / m_nFilters of the previous frame's addFeatures (SLAM.cpp:758-766): while non-zero, KalmanUpdate takes
+ * the NEED_REORDER branch (:2083-2086).  The reference resets it in addFeatures at the end of every frame (:554). */
+void oracle_filter_set_new_features(OracleFilter *f, int n_new) { f->n_new = n_new; }
 
 /* m_allPredictSet / map_p->Si / isVisible as left by predictMeasurement (SLAM.cpp:1724-1738) */
 void oracle_filter_get_prediction(const OracleFilter *f, double *hbar, double *si, unsigned char *visible) {

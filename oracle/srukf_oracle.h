@@ -90,6 +90,7 @@ typedef struct OracleFilter {
   double *si;       /* L x 4        map_p->Si        */
   unsigned char *visible; /* L      map_p->isVisible (this frame) */
   double Mt[3], Ut[3];
+  int n_new;        /* m_nAddings: the last n_new features were added on the previous frame */
   /* diagnostics */
   long n_mchol_calls, n_mchol_modified;
   double max_E; /* largest diagonal modification seen in the last update */
@@ -108,6 +109,7 @@ void oracle_predict_motion(OracleFilter *f, const double *u3);
 void oracle_predict_measurement(OracleFilter *f);
 /* SLAM.cpp:2048-2096 (+2020-2038, 2106-2153); z is L x 2 (matchLocation.x, .y), matched L flags */
 void oracle_kalman_update(OracleFilter *f, const double *z, const unsigned char *matched);
+void oracle_filter_set_new_features(OracleFilter *f, int n_new);
 void oracle_filter_get_prediction(const OracleFilter *f, double *hbar, double *si, unsigned char *visible);
 /* SLAM.cpp:1946-1977 chi-square gate of candidate pixels z (L x 2) against the current prediction */
 void oracle_chi2_gate(const OracleFilter *f, const double *z, double threshold, unsigned char *accept, double *d2);

@@ -180,6 +180,74 @@ def test_init_features_matches_oracle(gpu, oracle, L, B):
             assert relmax(Sg[b].T @ Sg[b], S1.T @ S1) < 10 * tol
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_kalman_update_reorder_matches_oracle(gpu, oracle, mode):
+    """KalmanUpdate on the frame after features were added -- NEED_REORDER branch of GSLCholeskyUpdate
+    with CholeskyDecompositionWithPivoting (SLAM.cpp:2083-2086, 2122-2138, 2158-2179).  (a) the frame after the
+    frame-1 initialisation (all L features new), (b) a running filter whose last 3 features count as new."""
+    from cv_monoslam_b200 import CSLAMBatch, capi
+    prm = capi.default_params()
+    prm.downdate_mode = mode
+    p = oracle.default_params()
+    rng = np.random.default_rng(7)
+    # (a)
+    L, B = 6, 3
+    x4 = np.column_stack([rng.normal(0, 0.3, (B, 3)), rng.uniform(-np.pi, np.pi, B)])
+    S4 = np.tile(np.diag([0.02, 0.02, 0.005, 0.02]), (B, 1, 1))
+    ang, rad = rng.uniform(0, 2 * np.pi, (B, L)), rng.uniform(30, 150, (B, L))
+    kp = np.stack([p.cam_cx + rad * np.cos(ang), p.cam_cy + rad * np.sin(ang)], axis=-1)
+    g = CSLAMBatch(B, L, prm)
+    g.initFeatures(x4, S4, kp)
+    x0, S0 = g.get_state()
+    u = np.tile([0.005, 0.002, 0.005], (B, 1)) + rng.normal(0, 1e-3, (B, 3))
+    g.predictMotion(u)
+    g.predictMeasurement()
+    hbar, _, vis = g.prediction()
+    z = hbar + rng.normal(0, 1.0, hbar.shape)
+    vis[0, 2] = 0                                            # one unmatched feature
+    g.KalmanUpdateReorder(z, vis, L)
+    xg, Sg = g.get_state()
+    differs = 0.0
+    for b in range(B):
+        ref = []
+        for n_new in (L, 0):
+            f = oracle.Filter(L)
+            f.set_state(x0[b], S0[b])
+            f.set_new_features(n_new)
+            f.predict_motion(u[b])
+            f.predict_measurement()
+            f.kalman_update(z[b], vis[b])
+            ref.append(f.get_state())
+        x1, S1 = ref[0]
+        assert relmax(xg[b], x1) < 1e-9
+        assert relmax(Sg[b].T @ Sg[b], S1.T @ S1) < 1e-9
+        differs = max(differs, relmax(S1.T @ S1, ref[1][1].T @ ref[1][1]))
+    assert differs > 1e-7          # the branch is not a no-op: it projects the anchors onto the leading block
+    # the filter keeps running on the ordinary path afterwards
+    g.SLAM(u, z, vis)
+    assert np.isfinite(g.get_x()).all() and not (g.flags() & 1).any()
+    # (b)
+    L, B, n_new = 7, 2, 3
+    sc = synth.make_scenario(L, B, 3)
+    g = CSLAMBatch(B, L, prm)
+    g.set_state(sc.x0, sc.S0)
+    for s in range(2):
+        g.SLAM(sc.u[s], sc.z[s], sc.matched[s])
+    x0, S0 = g.get_state()
+    g.predictMotion(sc.u[2])
+    g.predictMeasurement()
+    g.KalmanUpdateReorder(sc.z[2], sc.matched[2], n_new)
+    xg, Sg = g.get_state()
+    for b in range(B):
+        f = oracle.Filter(L)
+        f.set_state(x0[b], S0[b])
+        f.set_new_features(n_new)
+        f.step(sc.u[2, b], sc.z[2, b], sc.matched[2, b])
+        x1, S1 = f.get_state()
+        assert relmax(xg[b], x1) < 1e-9
+        assert relmax(Sg[b].T @ Sg[b], S1.T @ S1) < 1e-9
+
+
 def test_delete_feature_matches_oracle(gpu, oracle):
     """deleteOneFeature + rank-6 UPDATING (SLAM.cpp:2637-2663, 2139-2153) after two filter steps, a
     different feature per filter (first, middle, last), then one more step on the reduced state."""
