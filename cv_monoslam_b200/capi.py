@@ -50,6 +50,7 @@ SYMBOLS = {
     "srukf_get_prediction": (C.c_int, [_VP, _VP, _VP, _VP]),
     "srukf_init_features": (C.c_int, [_VP, _VP, _VP, _VP, C.c_double, C.c_double]),
     "srukf_kalman_update_reorder": (C.c_int, [_VP, _VP, _VP, C.c_int]),
+    "srukf_add_features": (C.c_int, [_VP, _VP, _VP, C.c_double, C.c_double]),
     "srukf_delete_feature": (C.c_int, [_VP, _VP, _VP]),
     "srukf_chi2_gate": (C.c_int, [_VP, _VP, C.c_double, _VP, _VP]),
     "srukf_kalman_update": (C.c_int, [_VP, _VP, _VP]),

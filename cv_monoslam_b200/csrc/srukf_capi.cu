@@ -48,6 +48,9 @@ void launch_cov_block(const DevParams& p, const double* S, int r0, int nr, doubl
 void launch_init_features(const DevParams& p, int nblocks, const double* x4, const double* S4, const double* kp,
                           double rho0, double sigma_rho, double gamma, double wi, double* x, double* S, double* Pd,
                           double* G, uint32_t* flags, cudaStream_t st);
+void launch_add_features(const DevParams& p, int nblocks, const double* kp, double rho0, double sigma_rho, double gamma,
+                         double wi, const double* xs, const double* Ss, int ns, int nps, int M, double* x, double* S,
+                         double* Pd, double* G, double* Ascr, const uint32_t* flags_src, uint32_t* flags, cudaStream_t st);
 void launch_delete_feature(const DevParams& p, int nblocks, const double* xs, const double* Ss, int ns, int nps,
                            const int* ids, double* x, double* S, double* Pd, double* G, double* V,
                            const uint32_t* flags_src, uint32_t* flags, cudaStream_t st);
@@ -428,6 +431,37 @@ int srukf_init_features(srukf_t* h, const double* x4, const double* S4, const do
   cudaFree(d_in);
   if (e != cudaSuccess) return fail(SRUKF_ECUDA, "srukf_init_features", e);
   h->phase = 0;
+  return SRUKF_OK;
+}
+
+int srukf_add_features(srukf_t* src, srukf_t* dst, const double* keypoints, double rho0, double sigma_rho) {
+  if (!src || !dst || !keypoints) return fail(SRUKF_EINVAL, "srukf_add_features: null argument");
+  const int M = dst->p.L - src->p.L;
+  if (src == dst || dst->p.B != src->p.B || M < 1 || dst->device != src->device)
+    return fail(SRUKF_EINVAL, "srukf_add_features: dst must be another handle on the same device with the same B and more features");
+  CU(cudaSetDevice(dst->device));
+  CU(cudaStreamSynchronize(src->stream));
+  const DevParams& p = dst->p;
+  const int ns = src->p.n;
+  double wm0, wc0, wi, wi_sr, gamma;
+  sample_weights(dst->prm, ns + 3 * M, wm0, wc0, wi, wi_sr, gamma);   // Na = dim + 3 m_nFilters, SLAM.cpp:827,867
+  const int nblocks = p.B < dst->gslots ? p.B : dst->gslots;
+  double *d_kp = nullptr, *d_A = nullptr;
+  CU(cudaMalloc(&d_kp, sizeof(double) * (size_t)p.B * 2 * M));
+  cudaError_t e = cudaMalloc(&d_A, sizeof(double) * (size_t)nblocks * ((size_t)M * 4 * ns + 12 * M));
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_kp, keypoints, sizeof(double) * (size_t)p.B * 2 * M, cudaMemcpyHostToDevice, dst->stream);
+  if (e == cudaSuccess) {
+    launch_add_features(p, nblocks, d_kp, rho0, sigma_rho, gamma, wi, src->x, src->S, ns, src->p.np, M, dst->x, dst->S,
+                        dst->Pd, dst->G, d_A, src->flags, dst->flags, dst->stream);
+    dst->launches++;
+    e = cudaStreamSynchronize(dst->stream);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(d_kp);
+  if (d_A) cudaFree(d_A);
+  if (e != cudaSuccess) return fail(SRUKF_ECUDA, "srukf_add_features", e);
+  dst->phase = 0;
   return SRUKF_OK;
 }
 

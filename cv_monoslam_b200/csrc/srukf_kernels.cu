@@ -1131,6 +1131,7 @@ __device__ void mchol_core(int n, int np, double eps, double* G, double* S, doub
   double nu = sqrt((double)n * n - 1.0);
   if (nu < 1.0) nu = 1.0;
   const double beta2 = fmax(fmax(gmax, zmax / nu), 1e-15);
+  if (eps < 0.0) eps = fmax(-eps * gmax, 1e-300);   // relative floor (NEED_REORDER re-triangularisation)
   for (int j = 0; j < n; ++j) {
     double* col = G + tri_off(j, n);
     const int len = n - j;
@@ -1307,8 +1308,16 @@ __global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mo
         for (int c = 0; c < 2; ++c) {
           form_G(p, Sg, Ut, 2 * j + c, 2 * j + c + 1, G);
           __syncthreads();
-          if (mode == 3) reorder_project(p, q.n_new, G, q.G2 + (size_t)blockIdx.x * (p.ntri + 2 * (size_t)p.nbp), wcol, red, flags);
-          mchol_inplace(p, G, Sg, wcol, red, flags);
+          if (mode == 3) {
+            reorder_project(p, q.n_new, G, q.G2 + (size_t)blockIdx.x * (p.ntri + 2 * (size_t)p.nbp), wcol, red, flags);
+            // :2137 re-triangularises [R11 R12; 0 0] with a QR, which adds nothing to the covariance.  An EPSILON
+            // floor here would add up to 1e-13 to pivots of that very size in the next column's leading block (old
+            // anchors), and R12 divides by them: floor at 1e-16 of the largest diagonal entry instead.
+            uint32_t fl2 = 0;   // pivot flags of this step are rounding noise, not reported
+            mchol_core(p.n, p.np, -1e-16, G, Sg, wcol, red, fl2, nullptr);
+          } else {
+            mchol_inplace(p, G, Sg, wcol, red, flags);
+          }
           __syncthreads();
         }
       }
@@ -1481,6 +1490,147 @@ __global__ void __launch_bounds__(NT) k_init_features(DevParams p, InitArgs a, d
       if (!isfinite(Sb[bp_idx(i, i, np)]) || !isfinite(xb[i])) flags |= SRUKF_FLAG_NAN;
     flags = __reduce_or_sync(0xffffffffu, flags);
     if (tid == 0) flagsg[b] = 0;
+    __syncthreads();
+    if ((tid & 31) == 0 && flags) atomicOr(flagsg + b, flags);
+    if (Pd) form_P(p, Sb, Pd + (size_t)b * np);
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_add_features -- integrateFeaturesInformation on a NON-empty map (SLAM.cpp:818-871 with dim = 6 Lold + 4):
+// M key-points are appended to the state of the source filter (ns = dim entries, factor pitch nps); the result goes
+// to the destination (p: L = Lold + M features) in canonical order [old features | new features | robot].
+// sr = blockdiag(S, diag(sigma_pix, sigma_pix, sigma_rho)...): sigma pair k <= dim moves the old state by
+// +-gamma S(k,:) and, through the heading S(k, dim-1), the (theta, phi) of every new key-point; the key-point's own
+// three pairs move only its own angles / rho; the anchors repeat the robot position (:1223).  As in
+// k_init_features the covariance of those deviations is formed directly in canonical order and factorised with the
+// reference's modified Cholesky.  Scratch A: per CTA [M][2 angles][2 signs][ns] deviations + [M][12].
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_add_features(DevParams p, InitArgs a, const double* __restrict__ xs,
+                                                     const double* __restrict__ Ss, int ns, int nps, int M,
+                                                     double* x, double* S, double* Pd, double* G, double* Ascr,
+                                                     const uint32_t* flags_src, uint32_t* flagsg) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, n = p.n, np = p.np;
+  const int Lold = (ns - 4) / 6, nfo = 6 * Lold;
+  double* wcol = sm;
+  double* red = wcol + n;
+  double* Gb = G + (size_t)blockIdx.x * p.ntri;
+  double* Ab = Ascr + (size_t)blockIdx.x * ((size_t)M * 4 * ns + 12 * M);
+  double* Bj = Ab + (size_t)M * 4 * ns;   // [M][9] own-pair covariance, then [M][3] means
+  const double c2 = 2.0 * a.wi * a.gamma * a.gamma;   // sum over the +- pair of (gamma e)(gamma e') wi; == 1 analytically
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const double* xo = xs + (size_t)b * ns;
+    const double* So = Ss + (size_t)b * nps * nps;
+    const double* kp = a.kp + 2 * (size_t)M * b;
+    double* xb = x + (size_t)b * n;
+    double* Sb = S + (size_t)b * p.nbp;
+    const double h0 = xo[ns - 1];
+    for (int i = tid; i < p.nbp; i += NT) {
+      const int r = i / np, c = i - r * np;
+      Sb[i] = (r == c && r >= n) ? 1.0 : 0.0;
+    }
+    // (theta, phi) deviations of key-point id under sigma pair k (+ / -): Ab[((id*2 + t)*2 + s)*ns + k]
+    for (int i = tid; i < M * ns; i += NT) {
+      const int id = i / ns, kk = i - id * ns;
+      const double px = kp[2 * id], py = kp[2 * id + 1];
+      double t0, f0, tp, fp, tm, fm;
+      init_angles(p, px, py, h0, t0, f0);
+      const double e = So[(size_t)kk * nps + (ns - 1)];   // S(k, heading); k <= ns-1, so always in the upper triangle
+      init_angles(p, px, py, h0 * 1 + e * a.gamma + 0, tp, fp);
+      init_angles(p, px, py, h0 * 1 + e * ((-1) * a.gamma) + 0, tm, fm);
+      double* base = Ab + (size_t)id * 4 * ns + kk;
+      base[0 * ns] = tp - t0; base[1 * ns] = tm - t0;
+      base[2 * ns] = fp - f0; base[3 * ns] = fm - f0;
+    }
+    __syncthreads();
+    for (int id = tid; id < M; id += NT) {
+      const double px = kp[2 * id], py = kp[2 * id + 1];
+      double t0, f0;
+      init_angles(p, px, py, h0, t0, f0);
+      double st = 0.0, sf = 0.0;
+      const double* base = Ab + (size_t)id * 4 * ns;
+      for (int kk = 0; kk < ns; ++kk) {
+        st += base[kk] + base[ns + kk];
+        sf += base[2 * ns + kk] + base[3 * ns + kk];
+      }
+      double bb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < 2; ++c)
+        for (int sgn = 0; sgn < 2; ++sgn) {
+          const double g = sgn ? (-1) * a.gamma : a.gamma;
+          const double qx = (c == 0) ? px * 1 + p.sigma_measure * g + 0 : px;
+          const double qy = (c == 1) ? py * 1 + p.sigma_measure * g + 0 : py;
+          double t, f;
+          init_angles(p, qx, qy, h0, t, f);
+          const double dt = t - t0, df = f - f0;
+          st += dt;
+          sf += df;
+          bb[0] += dt * dt; bb[1] += dt * df; bb[4] += df * df;
+        }
+      const double dp = (a.rho0 * 1 + a.sigma_rho * a.gamma + 0) - a.rho0;
+      const double dm = (a.rho0 * 1 + a.sigma_rho * ((-1) * a.gamma) + 0) - a.rho0;
+      bb[8] = dp * dp + dm * dm;
+      bb[3] = bb[1];
+      for (int e = 0; e < 9; ++e) Bj[9 * id + e] = a.wi * bb[e];
+      double* xf = xb + nfo + 6 * id;
+      xf[0] = xo[ns - 4]; xf[1] = xo[ns - 3]; xf[2] = xo[ns - 2];
+      xf[3] = t0 + a.wi * st;
+      xf[4] = f0 + a.wi * sf;
+      xf[5] = a.rho0 + a.wi * (dp + dm);
+    }
+    for (int i = tid; i < nfo; i += NT) xb[i] = xo[i];
+    if (tid < 4) xb[n - 4 + tid] = xo[ns - 4 + tid];
+    __syncthreads();
+    // covariance, canonical order, lower triangle by columns.  A destination index is either "linear" (a source
+    // state entry: old feature entry, robot entry, or an anchor = robot position entry) or an angle of a new key-point.
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int cj = warp; cj < n; cj += NT / 32) {
+      int sj = -1, idj = -1, tj = 0;   // linear source index, or (key-point, component)
+      if (cj < nfo) sj = cj;
+      else if (cj >= nfo + 6 * M) sj = ns - 4 + (cj - nfo - 6 * M);
+      else { idj = (cj - nfo) / 6; tj = (cj - nfo) - 6 * idj; if (tj < 3) { sj = ns - 4 + tj; idj = -1; } else tj -= 3; }
+      double* col = Gb + tri_off(cj, n);
+      for (int ci = cj + lane; ci < n; ci += 32) {
+        int si = -1, idi = -1, ti = 0;
+        if (ci < nfo) si = ci;
+        else if (ci >= nfo + 6 * M) si = ns - 4 + (ci - nfo - 6 * M);
+        else { idi = (ci - nfo) / 6; ti = (ci - nfo) - 6 * idi; if (ti < 3) { si = ns - 4 + ti; idi = -1; } else ti -= 3; }
+        double v = 0.0;
+        if (si >= 0 && sj >= 0) {
+          const int kmax = si < sj ? si : sj;
+          double s = 0.0;
+          for (int kk = 0; kk <= kmax; ++kk) s = fma(So[(size_t)kk * nps + si], So[(size_t)kk * nps + sj], s);
+          v = c2 * s;
+        } else if (si >= 0 || sj >= 0) {
+          const int sl = si >= 0 ? si : sj, id = si >= 0 ? idj : idi, t = si >= 0 ? tj : ti;
+          if (t < 2) {
+            const double* ap = Ab + ((size_t)(id * 2 + t) * 2) * ns;
+            double s = 0.0;
+            for (int kk = 0; kk <= sl; ++kk) s = fma(So[(size_t)kk * nps + sl], ap[kk] - ap[ns + kk], s);
+            v = a.wi * a.gamma * s;
+          }
+        } else {
+          if (ti < 2 && tj < 2) {
+            const double* ai = Ab + ((size_t)(idi * 2 + ti) * 2) * ns;
+            const double* aj = Ab + ((size_t)(idj * 2 + tj) * 2) * ns;
+            double s = 0.0;
+            for (int kk = 0; kk < ns; ++kk) s += ai[kk] * aj[kk] + ai[ns + kk] * aj[ns + kk];
+            v = a.wi * s;
+          }
+          if (idi == idj) v += Bj[9 * idi + 3 * ti + tj];
+        }
+        col[ci - cj] = v;
+      }
+    }
+    __syncthreads();
+    uint32_t flags = 0;
+    mchol_inplace(p, Gb, Sb, wcol, red, flags);
+    __syncthreads();
+    for (int i = tid; i < n; i += NT)
+      if (!isfinite(Sb[bp_idx(i, i, np)]) || !isfinite(xb[i])) flags |= SRUKF_FLAG_NAN;
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (tid == 0) flagsg[b] = flags_src[b];
     __syncthreads();
     if ((tid & 31) == 0 && flags) atomicOr(flagsg + b, flags);
     if (Pd) form_P(p, Sb, Pd + (size_t)b * np);
@@ -1766,6 +1916,12 @@ void launch_init_features(const DevParams& p, int nblocks, const double* x4, con
   const size_t smem = sizeof(double) * (size_t)(p.n + 40 + 33 * p.L + 16 + 32);
   cudaFuncSetAttribute(k_init_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_init_features<<<nblocks, NT, smem, st>>>(p, a, x, S, Pd, G, flags);
+}
+void launch_add_features(const DevParams& p, int nblocks, const double* kp, double rho0, double sigma_rho, double gamma,
+                         double wi, const double* xs, const double* Ss, int ns, int nps, int M, double* x, double* S,
+                         double* Pd, double* G, double* Ascr, const uint32_t* flags_src, uint32_t* flags, cudaStream_t st) {
+  InitArgs a{nullptr, nullptr, kp, rho0, sigma_rho, gamma, wi, p.B};
+  k_add_features<<<nblocks, NT, downdate_smem_bytes(p), st>>>(p, a, xs, Ss, ns, nps, M, x, S, Pd, G, Ascr, flags_src, flags);
 }
 void launch_delete_feature(const DevParams& p, int nblocks, const double* xs, const double* Ss, int ns, int nps,
                            const int* ids, double* x, double* S, double* Pd, double* G, double* V,

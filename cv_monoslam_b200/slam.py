@@ -116,6 +116,18 @@ class CSLAMBatch:
         capi.check(self._lib.srukf_init_features(self._h, capi.ptr(x4), capi.ptr(S4), capi.ptr(kp), float(rho0),
                                                  float(sigma_rho)))
 
+    def addFeatures(self, keypoints: np.ndarray, rho0: float = 1.0 / 3.0, sigma_rho: float | None = None) -> "CSLAMBatch":
+        """integrateFeaturesInformation on a non-empty map (SLAM.cpp:818-871): keypoints [B,M,2] are appended to
+        every filter.  Returns a new batch with L+M features; call KalmanUpdateReorder(..., M) on its next frame."""
+        kp = np.ascontiguousarray(keypoints, dtype=np.float64)
+        kp = kp.reshape(self.B, -1, 2)
+        M = kp.shape[1]
+        if sigma_rho is None:
+            sigma_rho = rho0 / 2.0
+        out = CSLAMBatch(self.B, self.L + M, self.params, self.device)
+        capi.check(self._lib.srukf_add_features(self._h, out._h, capi.ptr(kp), float(rho0), float(sigma_rho)))
+        return out
+
     def deleteFeature(self, ids) -> "CSLAMBatch":
         """deleteOneFeature (SLAM.cpp:2637-2663) for every filter: filter b drops feature ids[b].  Returns a new
         batch with L-1 features (a handle has a fixed state dimension); this one is left untouched."""

@@ -219,6 +219,10 @@ class CSLAMBatch {
                     double sigma_rho = 1.0 / 6.0) {
     check(srukf_init_features(h_, x4, S4, keypoints, rho0, sigma_rho), "srukf_init_features");
   }
+  /* integrateFeaturesInformation on a non-empty map (SLAM.cpp:818-871): dst holds L + M features */
+  void addFeatures(CSLAMBatch& dst, const double* keypoints, double rho0 = 1.0 / 3.0, double sigma_rho = 1.0 / 6.0) {
+    check(srukf_add_features(h_, dst.h_, keypoints, rho0, sigma_rho), "srukf_add_features");
+  }
   /* deleteOneFeature (SLAM.cpp:2637-2663): filter b drops feature ids[b]; dst must hold L-1 features */
   void deleteFeature(CSLAMBatch& dst, const int32_t* ids) {
     check(srukf_delete_feature(h_, dst.h_, ids), "srukf_delete_feature");

@@ -90,6 +90,11 @@ int srukf_get_prediction(srukf_t *h, double *hbar, double *si, uint8_t *visible)
  * the anchors make the covariance rank 4 + 3L). */
 int srukf_init_features(srukf_t *h, const double *x4, const double *S4, const double *keypoints, double rho0,
                         double sigma_rho);
+/* CSLAM::integrateFeaturesInformation on a NON-empty map (SLAM.cpp:818-871 with dim > 4): M = dst.L - src.L key-points
+ * (keypoints [B][M][2], distorted pixels) are appended to every filter of src; the augmented state goes to dst (same B,
+ * same device) in canonical order [old features | new features | robot].  Follow it with
+ * srukf_kalman_update_reorder(dst, ..., M) on the next frame, as the reference does.  src is left untouched. */
+int srukf_add_features(srukf_t *src, srukf_t *dst, const double *keypoints, double rho0, double sigma_rho);
 /* CSLAM::KalmanUpdate on the frame after features were added (m_nAddings != 0, SLAM.cpp:2083-2086): the covariance
  * downdate takes GSLCholeskyUpdate's NEED_REORDER branch (:2122-2138) with CholeskyDecompositionWithPivoting
  * (:2158-2179) for every U column.  n_new = m_nFilters, the number of features (the last ones of the state) added on the

@@ -78,6 +78,8 @@ def lib():
         L.oracle_chi2_gate.argtypes = [C.c_void_p, _dp, C.c_double, _bp, _dp]
         L.oracle_init_features.argtypes = [C.POINTER(OracleParams), _dp, _dp, C.c_int, _dp, C.c_double,
                                            C.c_double, _dp, _dp]
+        L.oracle_add_features.argtypes = [C.POINTER(OracleParams), C.c_int, _dp, _dp, C.c_int, _dp, C.c_double,
+                                          C.c_double, _dp, _dp]
         L.oracle_delete_feature.argtypes = [C.POINTER(OracleParams), C.c_int, _dp, _dp, C.c_int, _dp, _dp]
         L.oracle_batch_step.argtypes = [C.c_int, C.c_int, C.POINTER(OracleParams), _dp, _dp, _dp, _dp, _bp,
                                         C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -153,6 +155,18 @@ def init_features(p, x4, S4, kp, rho0, sigma_rho):
     lib().oracle_init_features(C.byref(p), np.ascontiguousarray(x4, dtype=np.float64),
                                np.ascontiguousarray(S4, dtype=np.float64), M, kp, rho0, sigma_rho, x, S)
     return x, S
+
+
+def add_features(p, x, S, kp, rho0, sigma_rho):
+    """integrateFeaturesInformation on a non-empty map: (x [n], S [n,n]) + M key-points -> (x [n+6M], S)"""
+    kp = np.ascontiguousarray(kp, dtype=np.float64).reshape(-1, 2)
+    M = kp.shape[0]
+    n = x.shape[0]
+    xo = np.zeros(n + 6 * M)
+    So = np.zeros((n + 6 * M, n + 6 * M))
+    lib().oracle_add_features(C.byref(p), (n - 4) // 6, np.ascontiguousarray(x, dtype=np.float64),
+                              np.ascontiguousarray(S, dtype=np.float64), M, kp, rho0, sigma_rho, xo, So)
+    return xo, So
 
 
 def delete_feature(p, x, S, id_):

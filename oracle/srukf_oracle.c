@@ -779,21 +779,23 @@ void oracle_step(OracleFilter *f, const double *u3, const double *z, const unsig
 /* ------------------------------------------------------------------------------------------ */
 /* feature initialisation at frame 1, SLAM.cpp:818-871, 1177-1334                              */
 /* ------------------------------------------------------------------------------------------ */
-void oracle_init_features(const OracleParams *p, const double *x4, const double *S4, int M,
-                          const double *kp, double rho0, double sigma_rho, double *x_out, double *S_out) {
-  int dim = 4;
+/* integrateFeaturesInformation for a map of Lold features (dim = 6 Lold + 4; Lold = 0 is frame 1):
+ * x (dim), S (dim x dim) -> x_out (dim + 6M), S_out in canonical order [old features | new features | robot]. */
+void oracle_add_features(const OracleParams *p, int Lold, const double *xin, const double *Sin, int M,
+                         const double *kp, double rho0, double sigma_rho, double *x_out, double *S_out) {
+  int dim = 6 * Lold + 4;
   int Na = dim + 3 * M;     /* :827 */
   int nCols = 2 * Na + 1;
   int dimNew = dim + 6 * M;
   OracleWeights w;
   oracle_sample_parameters(Na, p, &w); /* :867 */
 
-  /* mu, sr : :847-868 */
+  /* mu, sr : :847-868 (expandMatrix :1123-1135) */
   double *mu = (double *)calloc((size_t)Na, sizeof(double));
   double *sr = (double *)calloc((size_t)Na * Na, sizeof(double));
   for (int i = 0; i < dim; i++) {
-    mu[i] = x4[i];
-    for (int j = 0; j < dim; j++) sr[(size_t)i * Na + j] = S4[i * dim + j];
+    mu[i] = xin[i];
+    for (int j = 0; j < dim; j++) sr[(size_t)i * Na + j] = Sin[(size_t)i * dim + j];
   }
   for (int i = 0; i < M; i++) {
     int idx = dim + 3 * i;
@@ -847,12 +849,12 @@ void oracle_init_features(const OracleParams *p, const double *x4, const double 
       }
     }
   }
-  /* x_new, :1245-1249 (disordered: [robot(4) | angles(3M) | positions(3M)]) */
+  /* x_new, :1245-1249 (disordered: [x(dim) | angles(3M) | positions(3M)]) */
   double *xdis = (double *)calloc((size_t)dimNew, sizeof(double));
-  for (int r = 0; r < dim; r++) xdis[r] = x4[r];
+  for (int r = 0; r < dim; r++) xdis[r] = xin[r];
   for (int r = 0; r < 3 * M; r++) xdis[dim + r] = mu_angle[r];
   for (int id = 0; id < M; id++)
-    for (int k = 0; k < 3; k++) xdis[Na + 3 * id + k] = x4[dim - 4 + k];
+    for (int k = 0; k < 3; k++) xdis[Na + 3 * id + k] = xin[dim - 4 + k];
   /* QrAndCholeskyForInitilization, :1260-1300 */
   int m = 2 * Na;
   double *A = (double *)calloc((size_t)m * dimNew, sizeof(double));
@@ -861,9 +863,10 @@ void oracle_init_features(const OracleParams *p, const double *x4, const double 
       A[(size_t)i * dimNew + c] = w.wi_sr * (sout[(size_t)c * nCols + i + 1] - sout[(size_t)c * nCols + 0]);
   double *Sdis = (double *)calloc((size_t)dimNew * dimNew, sizeof(double));
   oracle_qr_R(A, m, dimNew, Sdis);
-  /* getPermutationMatrix, :1303-1334, dimOld = 4: perm[row] = source index */
+  /* getPermutationMatrix, :1303-1334: src[canonical row] = disordered index */
   int *src = (int *)calloc((size_t)dimNew, sizeof(int));
-  int dimOld = 4;
+  int dimOld = dim;
+  for (int r = 0; r < dimOld - 4; r++) src[r] = r;
   for (int k = 0; k < 4; k++) src[dimNew - 4 + k] = dimOld - 4 + k;
   for (int id = 0; id < M; id++) {
     for (int k = 0; k < 3; k++) {
@@ -888,6 +891,11 @@ void oracle_init_features(const OracleParams *p, const double *x4, const double 
   free(sin_);
   free(sr);
   free(mu);
+}
+
+void oracle_init_features(const OracleParams *p, const double *x4, const double *S4, int M,
+                          const double *kp, double rho0, double sigma_rho, double *x_out, double *S_out) {
+  oracle_add_features(p, 0, x4, S4, M, kp, rho0, sigma_rho, x_out, S_out);
 }
 
 /* ------------------------------------------------------------------------------------------ */

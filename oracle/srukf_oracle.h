@@ -126,6 +126,11 @@ void oracle_init_features(const OracleParams *p, const double *x4, const double 
 void oracle_delete_feature(const OracleParams *p, int L, const double *x, const double *S, int id, double *x_out,
                            double *S_out);
 
+/* integrateFeaturesInformation for a non-empty map (SLAM.cpp:818-871 with dim = 6 Lold + 4 > 4): M key-points are
+ * appended to the Lold-feature state; outputs in canonical order [old features | new features | robot]. */
+void oracle_add_features(const OracleParams *p, int Lold, const double *x, const double *S, int M, const double *kp,
+                         double rho0, double sigma_rho, double *x_out, double *S_out);
+
 /* batch helpers used by tests / bench (OpenMP over filters when available) */
 void oracle_batch_step(int B, int L, const OracleParams *p, double *x /*B x n*/, double *S /*B x n x n*/,
                        const double *u /*B x 3*/, const double *z /*B x L x 2*/,

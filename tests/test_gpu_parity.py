@@ -248,6 +248,53 @@ def test_kalman_update_reorder_matches_oracle(gpu, oracle, mode):
         assert relmax(Sg[b].T @ Sg[b], S1.T @ S1) < 1e-9
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_add_features_matches_oracle(gpu, oracle, mode):
+    """integrateFeaturesInformation on a non-empty map (SLAM.cpp:818-871, dim > 4), then the reference's
+    next frame: predict + NEED_REORDER update with n_new = M."""
+    from cv_monoslam_b200 import CSLAMBatch, capi
+    prm = capi.default_params()
+    prm.downdate_mode = mode
+    p = oracle.default_params()
+    L, B, M = 6, 3, 3
+    sc = synth.make_scenario(L, B, 3)
+    g = CSLAMBatch(B, L, prm)
+    g.set_state(sc.x0, sc.S0)
+    for s in range(2):
+        g.SLAM(sc.u[s], sc.z[s], sc.matched[s])
+    x, S = g.get_state()
+    rng = np.random.default_rng(11)
+    kp = np.stack([p.cam_cx + rng.uniform(-120, 120, (B, M)), p.cam_cy + rng.uniform(-90, 90, (B, M))], axis=-1)
+    g2 = g.addFeatures(kp)
+    assert g2.L == L + M
+    x2, S2 = g2.get_state()
+    keep = np.r_[0:6 * L, 6 * (L + M):6 * (L + M) + 4]
+    for b in range(B):
+        xo, So = oracle.add_features(p, x[b], S[b], kp[b], 1.0 / 3.0, 1.0 / 6.0)
+        assert relmax(x2[b], xo) < 1e-9
+        assert relmax(S2[b].T @ S2[b], So.T @ So) < 1e-9
+        assert np.array_equal(x2[b][keep], x[b])                       # old entries and the robot are untouched
+        assert relmax((S2[b].T @ S2[b])[np.ix_(keep, keep)], S[b].T @ S[b]) < 1e-9
+    # next frame on the augmented filters
+    u = sc.u[2]
+    g2.predictMotion(u)
+    g2.predictMeasurement()
+    hbar, _, vis = g2.prediction()
+    z = hbar + rng.normal(0, 1.0, hbar.shape)
+    g2.KalmanUpdateReorder(z, vis, M)
+    x3, S3 = g2.get_state()
+    for b in range(B):
+        f = oracle.Filter(L + M)
+        f.set_state(x2[b], S2[b])
+        f.set_new_features(M)
+        f.predict_motion(u[b])
+        f.predict_measurement()
+        f.kalman_update(z[b], vis[b])
+        x1, S1 = f.get_state()
+        assert relmax(x3[b], x1) < 1e-9
+        assert relmax(S3[b].T @ S3[b], S1.T @ S1) < 1e-9
+
+
 def test_delete_feature_matches_oracle(gpu, oracle):
     """deleteOneFeature + rank-6 UPDATING (SLAM.cpp:2637-2663, 2139-2153) after two filter steps, a
     different feature per filter (first, middle, last), then one more step on the reduced state."""
