@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libsrukf_b200.so")
+_LIB = os.environ.get("SRUKF_LIB_PATH") or os.path.join(_HERE, "libsrukf_b200.so")   # override: tuning builds only
 
 SRUKF_OK, SRUKF_EINVAL, SRUKF_ECUDA, SRUKF_ENOMEM, SRUKF_ESTATE, SRUKF_ENODEV = 0, -1, -2, -3, -4, -5
 FLAG_NAN, FLAG_GMW_FLOOR, FLAG_GMW_MODIFIED, FLAG_OUT_OF_VIEW, FLAG_INVISIBLE, FLAG_FALLBACK = 1, 2, 4, 8, 16, 32

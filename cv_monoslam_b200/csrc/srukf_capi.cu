@@ -28,7 +28,10 @@ constexpr int TM_S0 = 0, TM_S1 = 4, TM_UT = 8, TM_DZ = 12, TM_DZ_ALL = 13, TM_CO
 #ifndef SRUKF_TW
 #define SRUKF_TW 64
 #endif
-constexpr int TP = SRUKF_TW + 8;
+#ifndef SRUKF_PAD
+#define SRUKF_PAD 4
+#endif
+constexpr int TP = SRUKF_TW + SRUKF_PAD;
 int gain_dz_box(const DevParams& p);
 int gain_variant(const DevParams& p);
 int tile_warps(const DevParams& p);

@@ -381,7 +381,14 @@ constexpr int MAXQ = 5;     // strips per warp: np <= 8 * NW * MAXQ
 #define SRUKF_TW 64
 #endif
 constexpr int TW = SRUKF_TW;   // payload columns per TMA box (64 or 128)
-constexpr int TP = TW + 8;     // box width == smem row pitch inside a box (doubles), == 8 mod 16
+#ifndef SRUKF_PAD
+#define SRUKF_PAD 4
+#endif
+// box width == smem row pitch inside a box (doubles).  A DMMA fragment load reads element (k = lane & 3, c = lane >> 2)
+// at k * pitch + c; a 64-bit shared load is served per half-warp (c = 0..3), so the four k rows must land 8 banks
+// (4 doubles) apart: pitch == 4 (mod 8).  (pitch == 8 mod 16 put rows k and k+2 on the same banks: ncu counted
+// 48 % of the shared wavefronts of k_update / k_gain as conflicts.)
+constexpr int TP = TW + SRUKF_PAD;
 constexpr int CP_PITCH = NB + 1;  // odd pitch: one row per lane/thread is bank-conflict free
 constexpr int WD_PITCH = NB + 1;
 
@@ -394,6 +401,18 @@ constexpr int TM_UT = 8;    // +0..3: Ut scratch
 __host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 __host__ __device__ __forceinline__ int ntiles(int width) { return (width + TW - 1) / TW; }
 __host__ __device__ __forceinline__ int stage_doubles_for(int np) { return KC * ntiles(np) * TP; }
+#ifndef SRUKF_UPD_ROWS
+#define SRUKF_UPD_ROWS 16
+#endif
+#ifndef SRUKF_UPD_NSTAGE
+#define SRUKF_UPD_NSTAGE 2
+#endif
+constexpr int UNS = SRUKF_UPD_NSTAGE;   // ring depth of k_update
+// k_update: K rows per stage when the panel has its full width (narrower panels take more rows, up to 32).
+// Every chunk costs each warp ~190 instructions of ring / dispatch bookkeeping next to its 40-160 DMMAs, so two deep
+// stages of 16 rows beat three of 8 (k_update 93.3 -> 82.4 ms per step of 65,536 filters at L = 50); the ring still
+// fits under the panel's shared memory with two CTAs per SM.
+__host__ __device__ __forceinline__ int upd_stage_doubles_for(int np) { return SRUKF_UPD_ROWS * ntiles(np) * TP; }
 
 struct Ring {
   uint64_t* full;    // [NSTAGE]  expect_tx by the producer thread + TMA complete_tx
@@ -402,14 +421,14 @@ struct Ring {
   uint32_t consumed; // chunks consumed so far by this warp
 };
 
-template <int NW>
+template <int NW, int NS = NSTAGE>
 __device__ __forceinline__ void ring_init(Ring& r, uint64_t* bars) {
   r.full = bars;
-  r.empty = bars + NSTAGE;
+  r.empty = bars + NS;
   r.produced = 0;
   r.consumed = 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) {
+    for (int i = 0; i < NS; ++i) {
       mbar_init(r.full + i, 1);
       mbar_init(r.empty + i, NW);
     }
@@ -425,24 +444,27 @@ __device__ __forceinline__ bool ring_my_turn(const Ring& r) {
   return ((threadIdx.x & 31) == 0) && ((int)(r.produced % NW) == (int)(threadIdx.x >> 5));
 }
 // elected thread: claim the next stage (waits until every warp released its previous occupant), post the byte count
+template <int NS = NSTAGE>
 __device__ __forceinline__ int ring_acquire(Ring& r, uint32_t bytes) {
   const uint32_t g = r.produced;
-  const int st = g % NSTAGE;
-  const uint32_t use = g / NSTAGE;
+  const int st = g % NS;
+  const uint32_t use = g / NS;
   if (use > 0) mbar_wait(r.empty + st, (use - 1) & 1);
   mbar_expect_tx(r.full + st, bytes);
   return st;
 }
 __device__ __forceinline__ void ring_next(Ring& r) { r.produced++; }
 // all threads of a warp: wait for the next chunk, returns its stage
+template <int NS = NSTAGE>
 __device__ __forceinline__ int ring_wait(Ring& r) {
   const uint32_t g = r.consumed;
-  const int st = g % NSTAGE;
-  mbar_wait(r.full + st, (g / NSTAGE) & 1);
+  const int st = g % NS;
+  mbar_wait(r.full + st, (g / NS) & 1);
   return st;
 }
+template <int NS = NSTAGE>
 __device__ __forceinline__ void ring_release(Ring& r) {
-  const int st = r.consumed % NSTAGE;
+  const int st = r.consumed % NS;
   r.consumed++;
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(r.empty + st);
@@ -535,7 +557,7 @@ template <int NW, int MQ, int NTM>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
   constexpr int NBG = 8 * NTM;                       // measurement columns per pass
-  constexpr int BPB = (NBG % 16 == 0) ? NBG + 8 : NBG + 16;  // dZ box width == smem pitch, == 8 mod 16
+  constexpr int BPB = (SRUKF_PAD == 4) ? NBG + 4 : ((NBG % 16 == 0) ? NBG + 8 : NBG + 16);  // dZ box width == smem pitch, == 4 mod 8
   extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = q.chunk0 + blockIdx.x;
@@ -874,16 +896,16 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   const double* PdOld = q.Pd + (size_t)b * np;
   double* PdNew = q.Pd2 + (size_t)b * np;
   const CUtensorMap* tmUt = q.tmaps + TM_UT;
-  const int sdoubles = stage_doubles_for(np);
+  const int sdoubles = upd_stage_doubles_for(np);
   size_t off = 0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * NSTAGE * sizeof(uint64_t));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * UNS * sizeof(uint64_t));
   double* Wd = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB * WD_PITCH;
   double* dsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;    // 1 / pivot d_j
   double* sdsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;   // sqrt(d_j)
   double* esm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;    // E_j = d_j - c_jj
   double* gdiag = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;  // G(j,j) of the panel
   double* red = reinterpret_cast<double*>(smraw + off); off = (off + sizeof(double) * 40 + 127) & ~(size_t)127;
-  double* Xs = reinterpret_cast<double*>(smraw + off);  // ring: NSTAGE stages, aliased by the panel Cp
+  double* Xs = reinterpret_cast<double*>(smraw + off);  // ring: UNS stages, aliased by the panel Cp
   double* Cp = Xs;
   uint32_t flags = 0;
 
@@ -895,7 +917,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     return;
   }
   Ring ring;
-  ring_init<NW>(ring, bars);
+  ring_init<NW, UNS>(ring, bars);
   double gmax = -1.0e300, zmax = 0.0, tmax = 0.0;
   // optional phase timing (thread 0 of every CTA): K loop / barrier skew / panel store / factor / write-out
   const bool timing = TIMING && (q.dbg != nullptr) && tid == 0;  // (sees only the chunks warp 0 issues)
@@ -930,7 +952,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
       int row0;
       const int nrows = chunk_rows(t, row0);
       long long tk0 = (TIMING && timing) ? clock64() : 0;
-      const int st = ring_acquire(ring, (uint32_t)(nbx * nrows * TP * sizeof(double)));
+      const int st = ring_acquire<UNS>(ring, (uint32_t)(nbx * nrows * TP * sizeof(double)));
       if (TIMING && timing) { long long t1_ = clock64(); tkl[0] += t1_ - tk0; tk0 = t1_; }
       const CUtensorMap* tm = ((t < cB) ? tmUt : tmNew) + (nrows / 8 - 1);
       const int c2 = (t < cB) ? (int)blockIdx.x : b;
@@ -940,19 +962,19 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     };
     auto consume = [&](int t0, int t1) {
       for (int t = t0; t < t1; ++t) {
-        if (t + NSTAGE - 1 < nchunks) {
-          if (ring_my_turn<NW>(ring)) produce(t + NSTAGE - 1);
+        if (t + UNS - 1 < nchunks) {
+          if (ring_my_turn<NW>(ring)) produce(t + UNS - 1);
           ring_next(ring);
         }
         int row0;
         const int nrows = chunk_rows(t, row0);
         long long tk0 = (TIMING && timing) ? clock64() : 0;
-        const int st = ring_wait(ring);
+        const int st = ring_wait<UNS>(ring);
         if (TIMING && timing) { long long t1_ = clock64(); tkl[2] += t1_ - tk0; tk0 = t1_; }
         const double* xs_ = Xs + (size_t)st * sdoubles;
         if (!(p.dbg_skip_mma & 1)) mma_chunk_any<NW, MAXQ, NB / 8, false>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nullptr, nrows / 4, lane, warp);
         if (TIMING && timing) { long long t1_ = clock64(); tkl[3] += t1_ - tk0; tk0 = t1_; }
-        ring_release(ring);
+        ring_release<UNS>(ring);
         if (TIMING && timing) { tkl[4] += clock64() - tk0; tkl[5] += 1; }
       }
     };
@@ -962,7 +984,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
 #pragma unroll
         for (int t = 0; t < NB / 8; ++t) { acc[qq][t][0] = -acc[qq][t][0]; acc[qq][t][1] = -acc[qq][t][1]; }
     };
-    for (int t = 0; t < NSTAGE - 1 && t < nchunks; ++t) {
+    for (int t = 0; t < UNS - 1 && t < nchunks; ++t) {
       if (ring_my_turn<NW>(ring)) {
         fence_proxy_async();  // the ring aliases the previous panel's Cp (generic-proxy stores)
         produce(t);
@@ -1839,7 +1861,10 @@ int gain_variant(const DevParams& p) {
   if (p.np <= 8 * 16 * 3) return 1;
   return 2;
 }
-int gain_dz_box(const DevParams& p) { return gain_variant(p) == 1 ? 72 : 40; }
+int gain_dz_box(const DevParams& p) {
+  if (SRUKF_PAD == 4) return gain_variant(p) == 1 ? 60 : 36;
+  return gain_variant(p) == 1 ? 72 : 40;
+}
 size_t predict_smem_bytes(const DevParams& p) {
   size_t slots = (p.L <= NT) ? (size_t)(NT / p.L) * p.L : (size_t)p.L;
   size_t work = slots * 13;
@@ -1854,10 +1879,10 @@ size_t gain_smem_bytes(const DevParams& p) {
   return off + sizeof(double) * (size_t)NSTAGE * (stage_doubles_for(p.np) + KC * gain_dz_box(p));
 }
 size_t update_smem_bytes(const DevParams& p) {
-  size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
+  size_t off = align16(2 * UNS * sizeof(uint64_t));
   off += sizeof(double) * (NB * WD_PITCH + 4 * NB);
   off = (off + sizeof(double) * 40 + 127) & ~(size_t)127;
-  size_t ring = (size_t)NSTAGE * stage_doubles_for(p.np);  // stage size is fixed: 8 rows at full width
+  size_t ring = (size_t)UNS * upd_stage_doubles_for(p.np);  // stage size is fixed: SRUKF_UPD_ROWS rows at full width
   size_t panel = (size_t)p.np * CP_PITCH;
   return off + sizeof(double) * (ring > panel ? ring : panel);
 }
