@@ -473,8 +473,8 @@ __device__ __forceinline__ void ring_release(Ring& r) {
 // DMMA over one chunk held as boxes [tile][row][TP]: strip slots [QLO, QHI) of this warp x NTT column tiles.
 //   The chunk's column 0 is output row/column `c0` of the panel; strip s covers chunk columns 8*(s-s0)..+7,
 //   i.e. box (8*(s-s0)) / 64 at offset (8*(s-s0)) % 64.  B fragments come from `bbase` (pitch bpitch).
-//   MASK: the strip on the chunk's own diagonal (s == s0) only takes A(k, col) with col >= k (the entries left of
-//   the diagonal of S's square buffer hold the carried covariance, not zeros).
+//   MASK: only A(k, col) with col >= k is taken (the entries left of the diagonal of S's square buffer hold the
+//   carried covariance, not zeros); this touches the first KC/8 strips of a chunk.
 //   b2base != nullptr: the LAST of the NTT column tiles takes its B fragment from b2base (pitch TP) instead.
 template <int NW, int MQ, int NTM, int QLO, int QHI, int NTT, bool MASK>
 __device__ __forceinline__ void mma_chunk(double (&acc)[MQ][NTM][2], const double* abase, int tstride, int s0,
@@ -498,7 +498,7 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MQ][NTM][2], const doubl
 #pragma unroll
     for (int q = QLO; q < QHI; ++q) {
       double a = ar[aoff[q - QLO]];
-      if (MASK && (warp + NW * q == s0) && (lane >> 2) < kk) a = 0.0;
+      if (MASK && 8 * (warp + NW * q - s0) + (lane >> 2) < kk) a = 0.0;   // left of the diagonal: carried covariance, not S
 #pragma unroll
       for (int tt = 0; tt < NTT; ++tt) dmma(acc[q][tt][0], acc[q][tt][1], a, bf[tt]);
     }
@@ -553,7 +553,7 @@ __device__ __forceinline__ void mma_chunk_any(double (&acc)[MQ][NTM][2], int qlo
 // -------------------------------------------------------------------------------------------------
 // Tile shapes: <8 warps, 5 strips, 4 tiles> (32 columns per pass, 2 CTAs/SM) or <16 warps, 3 strips, 7 tiles>
 // (56 columns per pass, 1 CTA/SM: half as many passes over S -- the kernel is bound by streaming S, not by DMMA).
-template <int NW, int MQ, int NTM>
+template <int NW, int MQ, int NTM, int KCG>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
   constexpr int NBG = 8 * NTM;                       // measurement columns per pass
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = q.chunk0 + blockIdx.x;
   const int n = p.n, nf = p.nf, L = p.L, L2 = 2 * p.L, np = p.np, Lc = p.Lc;
-  const int sdoubles = stage_doubles_for(np);
+  const int sdoubles = KCG * ntiles(np) * TP;   // KCG rows of S per chunk
   size_t off = 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * NSTAGE * sizeof(uint64_t));
   double* sii = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 4 * (Lc / 2);   // per column pair
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
   double* Bs = reinterpret_cast<double*>(smraw + off);
   int* nact = act + L;
   for (int i = tid; i < np; i += NTH) dxs[i] = 0.0;
-  const CUtensorMap* tmS = q.tmaps + (q.sbuf ? TM_S1 : TM_S0);   // 8-row boxes
+  const CUtensorMap* tmS = q.tmaps + (q.sbuf ? TM_S1 : TM_S0) + (KCG / 8 - 1);   // KCG-row boxes
   const CUtensorMap* tmZ = q.tmaps + q.tm_dz;
   double* Ut = q.U + (size_t)blockIdx.x * Lc * np;
   double* Sgw = q.S + (size_t)b * p.nbp;   // robot rows of the carried covariance are written here
@@ -634,16 +634,18 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
 #pragma unroll
       for (int t = 0; t < NTM; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
     // only blocks whose rows can touch a feature row matter: S rows >= nf (robot) have zero dZ
-    const int nchunk = (nf + 7) / 8;
+    const int nchunk = (nf + KCG - 1) / KCG;
     auto produce = [&](int t) {  // elected thread: S rows 8t..8t+7 from column 8t on (boxes of 64+8 columns) + dZ rows
-      const int nbx = ntiles(np - 8 * t);
-      const int st = ring_acquire(ring, (uint32_t)((nbx * KC * TP + (ncol ? KC * BPB : 0)) * sizeof(double)));
+      const int nbx = ntiles(np - KCG * t);
+      const int st = ring_acquire(ring, (uint32_t)((nbx * KCG * TP + (ncol ? KCG * BPB : 0)) * sizeof(double)));
       double* xd = Xs + (size_t)st * sdoubles;
       // S is streamed once per pass: ask L2 to keep it; dZ is read once
       for (int j = 0; j < nbx; ++j)
-        tma_load_3d_hint(xd + (size_t)j * KC * TP, tmS, 8 * t + TW * j, 8 * t, b, ring.full + st, pol_keep);
+        tma_load_3d_hint(xd + (size_t)j * KCG * TP, tmS, KCG * t + TW * j, KCG * t, b, ring.full + st, pol_keep);
       if (ncol)
-        tma_load_3d_hint(Bs + (size_t)st * KC * BPB, tmZ, cg, 8 * t, q.dz_filter0 + blockIdx.x, ring.full + st, pol_once);
+        for (int hh = 0; hh < KCG / 8; ++hh)   // the dZ map has 8-row boxes
+          tma_load_3d_hint(Bs + ((size_t)st * KCG + 8 * hh) * BPB, tmZ, cg, KCG * t + 8 * hh, q.dz_filter0 + blockIdx.x,
+                           ring.full + st, pol_once);
     };
     for (int t = 0; t < NSTAGE - 1 && t < nchunk && !(p.dbg_skip_mma & 2); ++t) {
       if (ring_my_turn<NW>(ring)) produce(t);
@@ -655,13 +657,14 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
         ring_next(ring);
       }
       const int st = (p.dbg_skip_mma & 2) ? (t % NSTAGE) : ring_wait(ring);
-      const double* xa = Xs + (size_t)st * sdoubles;     // column 0 == state row 8t
-      const double* xb = Bs + (size_t)st * KC * BPB;
+      const double* xa = Xs + (size_t)st * sdoubles;     // column 0 == state row KCG*t
+      const double* xb = Bs + (size_t)st * KCG * BPB;
       // output strip s = warp + NW*q receives S rows k <= its own: active slots are q >= qlo
-      const int qlo = (t > warp) ? (t - warp + NW - 1) / NW : 0;
-      const int xrel = nf - 8 * t;  // chunk column of S(:, nf): new robot columns (columns >= n are zero)
-      const double* b2 = xtile ? xa + (size_t)(xrel / TW) * (KC * TP) + (xrel % TW) : nullptr;
-      if (!(p.dbg_skip_mma & 1)) mma_chunk_any<NW, MQ, NTM, true>(acc, qlo, nq_w, nt, xa, KC * TP, t, xb, BPB, b2, KC / 4, lane, warp);
+      const int s0 = (KCG / 8) * t;
+      const int qlo = (s0 > warp) ? (s0 - warp + NW - 1) / NW : 0;
+      const int xrel = nf - KCG * t;  // chunk column of S(:, nf): new robot columns (columns >= n are zero)
+      const double* b2 = xtile ? xa + (size_t)(xrel / TW) * (KCG * TP) + (xrel % TW) : nullptr;
+      if (!(p.dbg_skip_mma & 1)) mma_chunk_any<NW, MQ, NTM, true>(acc, qlo, nq_w, nt, xa, KCG * TP, s0, xb, BPB, b2, KCG / 4, lane, warp);
       if (!(p.dbg_skip_mma & 2)) ring_release(ring);
     }
     // epilogue: apply wi*gamma and si^-1 to each column pair, store Ut[c][f] (transposed), accumulate the shift
@@ -1876,7 +1879,8 @@ size_t gain_smem_bytes(const DevParams& p) {
   size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
   off += sizeof(double) * (8 * (p.Lc / 2) + p.np);
   off = (off + sizeof(int) * (p.L + 1) + 127) & ~(size_t)127;
-  return off + sizeof(double) * (size_t)NSTAGE * (stage_doubles_for(p.np) + KC * gain_dz_box(p));
+  const size_t kc = (gain_variant(p) == 1) ? 16 : 8;   // K rows per chunk (template argument KCG of the variant)
+  return off + sizeof(double) * (size_t)NSTAGE * kc * ((size_t)ntiles(p.np) * TP + gain_dz_box(p));
 }
 size_t update_smem_bytes(const DevParams& p) {
   size_t off = align16(2 * UNS * sizeof(uint64_t));
@@ -1895,9 +1899,9 @@ cudaError_t configure_kernels(const DevParams& p) {
   if ((e = cudaFuncSetAttribute(k_predict<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
   if ((e = cudaFuncSetAttribute(k_predict<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
   int gs = (int)gain_smem_bytes(p), us = (int)update_smem_bytes(p);
-  if ((e = cudaFuncSetAttribute(k_gain<8, 5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
-  if ((e = cudaFuncSetAttribute(k_gain<16, 3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
-  if ((e = cudaFuncSetAttribute(k_gain<16, 5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
+  if ((e = cudaFuncSetAttribute(k_gain<8, 5, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
+  if ((e = cudaFuncSetAttribute(k_gain<16, 3, 7, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
+  if ((e = cudaFuncSetAttribute(k_gain<16, 5, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
   if ((e = cudaFuncSetAttribute(k_update<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
   if ((e = cudaFuncSetAttribute(k_update<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
   if ((e = cudaFuncSetAttribute(k_update<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
@@ -1916,9 +1920,9 @@ void launch_predict(const DevParams& p, const StepPtrs& q, int nblocks, bool mot
 }
 void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
   switch (gain_variant(p)) {
-    case 0: k_gain<8, 5, 4><<<nblocks, 256, gain_smem_bytes(p), st>>>(p, q); break;
-    case 1: k_gain<16, 3, 7><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
-    default: k_gain<16, 5, 4><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
+    case 0: k_gain<8, 5, 4, 8><<<nblocks, 256, gain_smem_bytes(p), st>>>(p, q); break;
+    case 1: k_gain<16, 3, 7, 16><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
+    default: k_gain<16, 5, 4, 8><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
   }
 }
 void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
