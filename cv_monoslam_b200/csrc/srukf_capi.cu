@@ -24,7 +24,7 @@ struct StepPtrs {
   double* G2; int n_new;
 };
 // tensor-map table layout and box geometry (must match srukf_kernels.cu)
-constexpr int TM_S0 = 0, TM_S1 = 4, TM_UT = 8, TM_DZ = 12, TM_DZ_ALL = 13, TM_COUNT = 14;
+constexpr int TM_S0 = 0, TM_S1 = 8, TM_UT = 16, TM_DZ = 24, TM_DZ_ALL = 25, TM_COUNT = 26, TM_ROWSETS = 8;
 #ifndef SRUKF_TW
 #define SRUKF_TW 64
 #endif
@@ -227,7 +227,7 @@ static int build_tensor_maps(srukf_handle* h, double* sbuf0, double* sbuf1) {
   CUtensorMap hm[TM_COUNT];
   memset(hm, 0, sizeof(hm));
   int rc;
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < TM_ROWSETS; ++r) {
     if ((rc = encode_map(&hm[TM_S0 + r], sbuf0, p.np, p.np, p.B, TP, 8 * (r + 1)))) return rc;
     if ((rc = encode_map(&hm[TM_S1 + r], sbuf1 ? sbuf1 : sbuf0, p.np, p.np, p.B, TP, 8 * (r + 1)))) return rc;
     if ((rc = encode_map(&hm[TM_UT + r], h->U, p.np, p.Lc, h->chunk, TP, 8 * (r + 1)))) return rc;

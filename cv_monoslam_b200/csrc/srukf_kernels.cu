@@ -393,10 +393,10 @@ constexpr int CP_PITCH = NB + 1;  // odd pitch: one row per lane/thread is bank-
 constexpr int WD_PITCH = NB + 1;
 
 // indices into the handle's tensor-map table (StepPtrs::tmaps)
-constexpr int TM_S0 = 0;    // +0..3: S buffer 0, boxes of 8/16/24/32 rows x TP columns
-constexpr int TM_S1 = 4;    // +0..3: S buffer 1
-constexpr int TM_UT = 8;    // +0..3: Ut scratch
-// 12: dZ scratch (chunk), box 8 rows x BP_B columns; 13: dZ of the whole batch (split API) -- see StepPtrs::tm_dz
+constexpr int TM_S0 = 0;    // +0..7: S buffer 0, boxes of 8/16/../64 rows x TP columns
+constexpr int TM_S1 = 8;    // +0..7: S buffer 1
+constexpr int TM_UT = 16;   // +0..7: Ut scratch
+// 24: dZ scratch (chunk), box 8 rows x BP_B columns; 25: dZ of the whole batch (split API) -- see StepPtrs::tm_dz
 
 __host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 __host__ __device__ __forceinline__ int ntiles(int width) { return (width + TW - 1) / TW; }
@@ -406,6 +406,9 @@ __host__ __device__ __forceinline__ int stage_doubles_for(int np) { return KC * 
 #endif
 #ifndef SRUKF_UPD_NSTAGE
 #define SRUKF_UPD_NSTAGE 2
+#endif
+#ifndef SRUKF_UPD_MAXROWS
+#define SRUKF_UPD_MAXROWS 64
 #endif
 constexpr int UNS = SRUKF_UPD_NSTAGE;   // ring depth of k_update
 // k_update: K rows per stage when the panel has its full width (narrower panels take more rows, up to 32).
@@ -553,7 +556,7 @@ __device__ __forceinline__ void mma_chunk_any(double (&acc)[MQ][NTM][2], int qlo
 // -------------------------------------------------------------------------------------------------
 // Tile shapes: <8 warps, 5 strips, 4 tiles> (32 columns per pass, 2 CTAs/SM) or <16 warps, 3 strips, 7 tiles>
 // (56 columns per pass, 1 CTA/SM: half as many passes over S -- the kernel is bound by streaming S, not by DMMA).
-template <int NW, int MQ, int NTM, int KCG>
+template <int NW, int MQ, int NTM, int KCG, int NSG>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
   constexpr int NBG = 8 * NTM;                       // measurement columns per pass
@@ -564,13 +567,13 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
   const int n = p.n, nf = p.nf, L = p.L, L2 = 2 * p.L, np = p.np, Lc = p.Lc;
   const int sdoubles = KCG * ntiles(np) * TP;   // KCG rows of S per chunk
   size_t off = 0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * NSTAGE * sizeof(uint64_t));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * NSG * sizeof(uint64_t));
   double* sii = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 4 * (Lc / 2);   // per column pair
   double* gv = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 2 * (Lc / 2);    // si^-T (z - hbar)
   double* ct = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 2 * (Lc / 2);    // c^T si^-1
   double* dxs = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * np;             // state shift U g
   int* act = reinterpret_cast<int*>(smraw + off); off = (off + sizeof(int) * (L + 1) + 127) & ~(size_t)127;
-  double* Xs = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NSTAGE * sdoubles;
+  double* Xs = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NSG * sdoubles;
   double* Bs = reinterpret_cast<double*>(smraw + off);
   int* nact = act + L;
   for (int i = tid; i < np; i += NTH) dxs[i] = 0.0;
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
     ct[2 * j + 1] = c0 * i01 + c1 * i11;
   }
   Ring ring;
-  ring_init<NW>(ring, bars);
+  ring_init<NW, NSG>(ring, bars);
   const uint64_t pol_keep = l2_policy_evict_last(), pol_once = l2_policy_evict_first();
   // KalmanUpdate returns early without matches, :2050 (k_update copies S through); the carried covariance still
   // needs its new robot-feature rows
@@ -637,7 +640,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
     const int nchunk = (nf + KCG - 1) / KCG;
     auto produce = [&](int t) {  // elected thread: S rows 8t..8t+7 from column 8t on (boxes of 64+8 columns) + dZ rows
       const int nbx = ntiles(np - KCG * t);
-      const int st = ring_acquire(ring, (uint32_t)((nbx * KCG * TP + (ncol ? KCG * BPB : 0)) * sizeof(double)));
+      const int st = ring_acquire<NSG>(ring, (uint32_t)((nbx * KCG * TP + (ncol ? KCG * BPB : 0)) * sizeof(double)));
       double* xd = Xs + (size_t)st * sdoubles;
       // S is streamed once per pass: ask L2 to keep it; dZ is read once
       for (int j = 0; j < nbx; ++j)
@@ -647,16 +650,16 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
           tma_load_3d_hint(Bs + ((size_t)st * KCG + 8 * hh) * BPB, tmZ, cg, KCG * t + 8 * hh, q.dz_filter0 + blockIdx.x,
                            ring.full + st, pol_once);
     };
-    for (int t = 0; t < NSTAGE - 1 && t < nchunk && !(p.dbg_skip_mma & 2); ++t) {
+    for (int t = 0; t < NSG - 1 && t < nchunk && !(p.dbg_skip_mma & 2); ++t) {
       if (ring_my_turn<NW>(ring)) produce(t);
       ring_next(ring);
     }
     for (int t = 0; t < nchunk; ++t) {
-      if (t + NSTAGE - 1 < nchunk && !(p.dbg_skip_mma & 2)) {
-        if (ring_my_turn<NW>(ring)) produce(t + NSTAGE - 1);
+      if (t + NSG - 1 < nchunk && !(p.dbg_skip_mma & 2)) {
+        if (ring_my_turn<NW>(ring)) produce(t + NSG - 1);
         ring_next(ring);
       }
-      const int st = (p.dbg_skip_mma & 2) ? (t % NSTAGE) : ring_wait(ring);
+      const int st = (p.dbg_skip_mma & 2) ? (t % NSG) : ring_wait<NSG>(ring);
       const double* xa = Xs + (size_t)st * sdoubles;     // column 0 == state row KCG*t
       const double* xb = Bs + (size_t)st * KCG * BPB;
       // output strip s = warp + NW*q receives S rows k <= its own: active slots are q >= qlo
@@ -665,7 +668,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
       const int xrel = nf - KCG * t;  // chunk column of S(:, nf): new robot columns (columns >= n are zero)
       const double* b2 = xtile ? xa + (size_t)(xrel / TW) * (KCG * TP) + (xrel % TW) : nullptr;
       if (!(p.dbg_skip_mma & 1)) mma_chunk_any<NW, MQ, NTM, true>(acc, qlo, nq_w, nt, xa, KCG * TP, s0, xb, BPB, b2, KCG / 4, lane, warp);
-      if (!(p.dbg_skip_mma & 2)) ring_release(ring);
+      if (!(p.dbg_skip_mma & 2)) ring_release<NSG>(ring);
     }
     // epilogue: apply wi*gamma and si^-1 to each column pair, store Ut[c][f] (transposed), accumulate the shift
 #pragma unroll
@@ -939,7 +942,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     // K rows per pipeline stage: as many 8-row blocks as fit the fixed stage size (8 rows at full width), so the
     // DMMA work and the bytes in flight per mbarrier round trip stay roughly constant as the panel narrows
     int rpc = (sdoubles / (nbx * TP)) & ~7;
-    if (rpc > 32) rpc = 32;
+    if (rpc > SRUKF_UPD_MAXROWS) rpc = SRUKF_UPD_MAXROWS;   // tensor maps exist for boxes of 8..64 rows
     // chunk list: [B: Ut rows | C: finished S_new rows 0..J0-1]
     const int rowsB = Lc, rowsC = J0;
     const int cA = 0, cB = (rowsB + rpc - 1) / rpc, cC = (rowsC + rpc - 1) / rpc;
@@ -1859,6 +1862,13 @@ int tile_warps(const DevParams& p) {  // warps per CTA of k_update; 0 = unsuppor
 }
 // k_gain variant: 0 = <8,5,4> (np <= 320, 2 CTAs/SM), 1 = <16,3,7> (np <= 384, 1 CTA/SM, half the passes),
 // 2 = <16,5,4> (np <= 640)
+#ifndef SRUKF_GAIN_KC
+#define SRUKF_GAIN_KC 24
+#endif
+#ifndef SRUKF_GAIN_NS
+#define SRUKF_GAIN_NS 2
+#endif
+constexpr int GKC1 = SRUKF_GAIN_KC, GNS1 = SRUKF_GAIN_NS;   // K rows per chunk / ring depth of the 16-warp, 7-tile variant
 int gain_variant(const DevParams& p) {
   if (const char* e = getenv("SRUKF_GAIN_VARIANT")) return atoi(e);
   if (p.np <= 8 * 16 * 3) return 1;
@@ -1876,11 +1886,12 @@ size_t predict_smem_bytes(const DevParams& p) {
   return sizeof(double) * ((size_t)p.n + (size_t)p.P * 8 + 2 * (size_t)p.L + 40 + work);
 }
 size_t gain_smem_bytes(const DevParams& p) {
-  size_t off = align16(2 * NSTAGE * sizeof(uint64_t));
+  const bool v1 = gain_variant(p) == 1;
+  const size_t kc = v1 ? GKC1 : 8, ns = v1 ? GNS1 : NSTAGE;   // template arguments KCG / NSG of the variant
+  size_t off = align16(2 * ns * sizeof(uint64_t));
   off += sizeof(double) * (8 * (p.Lc / 2) + p.np);
   off = (off + sizeof(int) * (p.L + 1) + 127) & ~(size_t)127;
-  const size_t kc = (gain_variant(p) == 1) ? 16 : 8;   // K rows per chunk (template argument KCG of the variant)
-  return off + sizeof(double) * (size_t)NSTAGE * kc * ((size_t)ntiles(p.np) * TP + gain_dz_box(p));
+  return off + sizeof(double) * ns * kc * ((size_t)ntiles(p.np) * TP + gain_dz_box(p));
 }
 size_t update_smem_bytes(const DevParams& p) {
   size_t off = align16(2 * UNS * sizeof(uint64_t));
@@ -1899,9 +1910,9 @@ cudaError_t configure_kernels(const DevParams& p) {
   if ((e = cudaFuncSetAttribute(k_predict<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
   if ((e = cudaFuncSetAttribute(k_predict<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
   int gs = (int)gain_smem_bytes(p), us = (int)update_smem_bytes(p);
-  if ((e = cudaFuncSetAttribute(k_gain<8, 5, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
-  if ((e = cudaFuncSetAttribute(k_gain<16, 3, 7, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
-  if ((e = cudaFuncSetAttribute(k_gain<16, 5, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
+  if ((e = cudaFuncSetAttribute(k_gain<8, 5, 4, 8, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
+  if ((e = cudaFuncSetAttribute(k_gain<16, 3, 7, GKC1, GNS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
+  if ((e = cudaFuncSetAttribute(k_gain<16, 5, 4, 8, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
   if ((e = cudaFuncSetAttribute(k_update<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
   if ((e = cudaFuncSetAttribute(k_update<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
   if ((e = cudaFuncSetAttribute(k_update<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
@@ -1920,9 +1931,9 @@ void launch_predict(const DevParams& p, const StepPtrs& q, int nblocks, bool mot
 }
 void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
   switch (gain_variant(p)) {
-    case 0: k_gain<8, 5, 4, 8><<<nblocks, 256, gain_smem_bytes(p), st>>>(p, q); break;
-    case 1: k_gain<16, 3, 7, 16><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
-    default: k_gain<16, 5, 4, 8><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
+    case 0: k_gain<8, 5, 4, 8, NSTAGE><<<nblocks, 256, gain_smem_bytes(p), st>>>(p, q); break;
+    case 1: k_gain<16, 3, 7, GKC1, GNS1><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
+    default: k_gain<16, 5, 4, 8, NSTAGE><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
   }
 }
 void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
