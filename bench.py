@@ -330,8 +330,8 @@ def run(out):
                          "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": achieved / FP64_PEAK_TFLOPS,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_update launch from the committed
-                         # `ncu --set full` capture of this command (profiles/r01_ncu_summary.md): 2.94 MB per filter
-                         "traffic": (2.937e6 * per_launch_filters) if (L == 50 and args.downdate_mode == 0) else None,
+                         # `ncu --set full` capture of this command (profiles/r01_ncu_summary.md): 2.78 MB per filter
+                         "traffic": (2.776e6 * per_launch_filters) if (L == 50 and args.downdate_mode == 0) else None,
                          "peak_source": "measured: tools/fp64_peak.cu DMMA m8n8k4 (profiles/r01_fp64_peak.json); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_filter_step_kernel": wd, "flops_per_filter_step_all": w_total,
