@@ -778,7 +778,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
 // (SLAM.cpp:2197-2327 with d_j = max(EPSILON, |c_jj|), :2279-2285):
 //   U  (all warps, DMMA)   C(:, sub) -= L(:, <sub) * W(sub rows, <sub)^T,  W = unscaled C of the diagonal rows
 //   D  (one warp, 8 lanes) 8x8 diagonal block: pivots, L = C/d (:2232), in-block updates (:2253) -- the only
-//                          sequential chain (8 pivots); 28 shuffle-FMAs in registers
+//                          sequential chain (8 pivots); 28 shuffle-FMAs in registers.  It runs concurrently with
+//                          U of the rows below (warp 0 updates the diagonal strip first, the others the rest)
 //   T  (one thread per row) rows below: C(i,j) -= sum_{k<j in sub} L(i,k) W(j,k), L(i,j) = C(i,j) * (1/d_j)
 // Afterwards Cp holds L; S_new(j, i) = sqrt(d_j) L(i, j) (:2321) is written by the caller.
 // -------------------------------------------------------------------------------------------------
@@ -791,8 +792,9 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
   for (int sb = 0; sb < nsub; ++sb) {
     const int c0 = 8 * sb;
     if (sb > 0) {
-      // ---- U: strips of 8 rows from c0 down, one 8x8 tile each, K = c0 ----
-      for (int rs = sb + warp; rs < R / 8; rs += NW) {
+      // ---- U: strips of 8 rows from c0 down, one 8x8 tile each, K = c0.  Warp 0 updates only the strip of the
+      //      diagonal block and goes straight on to the pivot chain D, which the other warps' strips overlap ----
+      for (int rs = (warp == 0) ? sb : sb + warp; rs < R / 8; rs += (warp == 0) ? R : NW - 1) {
         const int i = 8 * rs + (lane >> 2);
         double* ctile = Cp + (size_t)i * CP_PITCH + c0 + 2 * (lane & 3);
         double a0 = ctile[0], a1 = ctile[1];
@@ -802,7 +804,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
         ctile[0] = a0;
         ctile[1] = a1;
       }
-      __syncthreads();
+      __syncwarp();
     }
     // ---- D: 8x8 diagonal block, warp 0, lanes 0..7 own rows c0..c0+7 ----
     if (warp == 0) {
