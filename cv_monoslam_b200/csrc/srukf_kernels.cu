@@ -1161,7 +1161,6 @@ __device__ void mchol_core(int n, int np, double eps, double* G, double* S, doub
   double nu = sqrt((double)n * n - 1.0);
   if (nu < 1.0) nu = 1.0;
   const double beta2 = fmax(fmax(gmax, zmax / nu), 1e-15);
-  if (eps < 0.0) eps = fmax(-eps * gmax, 1e-300);   // relative floor (NEED_REORDER re-triangularisation)
   for (int j = 0; j < n; ++j) {
     double* col = G + tri_off(j, n);
     const int len = n - j;
@@ -1332,22 +1331,37 @@ __global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mo
       form_G(p, Sg, Ut, 0, 2 * L, G);
       __syncthreads();
       mchol_inplace(p, G, Sg, wcol, red, flags);
+    } else if (mode == 3) {
+      // NEED_REORDER: the reference re-triangularises [R11 R12; 0 0] with a QR after every column (:2137), which adds
+      // nothing to the covariance, and re-forms S^T S for the next one (:2118).  A (modified) Cholesky in between
+      // would either inject EPSILON-sized E into pivots of that very size, which the next column's R12 = R11^-T C12
+      // divides by, or (with a smaller floor) divide rounding noise of the dependent columns by it -- 1e-8 either way.
+      // So the covariance itself is carried across the columns and factorised once at the end, with the ordinary
+      // EPSILON floor.
+      form_G(p, Sg, Ut, 0, 0, G);   // G = S^T S
+      __syncthreads();
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int j = 0; j < L; ++j) {
+        if (!(q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j])) continue;
+        for (int c = 0; c < 2; ++c) {
+          const double* urow = Ut + (size_t)(2 * j + c) * np;
+          for (int k = warp; k < n; k += NT / 32) {   // dst = src1 - u u^T (:2132)
+            double* col = G + tri_off(k, n);
+            const double uk = urow[k];
+            for (int i = k + lane; i < n; i += 32) col[i - k] = fma(-uk, urow[i], col[i - k]);
+          }
+          __syncthreads();
+          reorder_project(p, q.n_new, G, q.G2 + (size_t)blockIdx.x * (p.ntri + 2 * (size_t)p.nbp), wcol, red, flags);
+        }
+      }
+      mchol_inplace(p, G, Sg, wcol, red, flags);
     } else {
       for (int j = 0; j < L; ++j) {
         if (!(q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j])) continue;
         for (int c = 0; c < 2; ++c) {
           form_G(p, Sg, Ut, 2 * j + c, 2 * j + c + 1, G);
           __syncthreads();
-          if (mode == 3) {
-            reorder_project(p, q.n_new, G, q.G2 + (size_t)blockIdx.x * (p.ntri + 2 * (size_t)p.nbp), wcol, red, flags);
-            // :2137 re-triangularises [R11 R12; 0 0] with a QR, which adds nothing to the covariance.  An EPSILON
-            // floor here would add up to 1e-13 to pivots of that very size in the next column's leading block (old
-            // anchors), and R12 divides by them: floor at 1e-16 of the largest diagonal entry instead.
-            uint32_t fl2 = 0;   // pivot flags of this step are rounding noise, not reported
-            mchol_core(p.n, p.np, -1e-16, G, Sg, wcol, red, fl2, nullptr);
-          } else {
-            mchol_inplace(p, G, Sg, wcol, red, flags);
-          }
+          mchol_inplace(p, G, Sg, wcol, red, flags);
           __syncthreads();
         }
       }

@@ -99,7 +99,8 @@ int srukf_add_features(srukf_t *src, srukf_t *dst, const double *keypoints, doub
  * downdate takes GSLCholeskyUpdate's NEED_REORDER branch (:2122-2138) with CholeskyDecompositionWithPivoting
  * (:2158-2179) for every U column.  n_new = m_nFilters, the number of features (the last ones of the state) added on the
  * previous frame -- L on the frame after srukf_init_features; 0 behaves as srukf_kalman_update.  Reference order, one
- * CTA per filter (not the fused kernel): meant for the one frame that follows an addition. */
+ * CTA per filter (not the fused kernel): meant for the one frame that follows an addition.  The covariance is carried
+ * across the U columns and factorised once at the end (the reference's QR between columns adds nothing to it). */
 int srukf_kalman_update_reorder(srukf_t *h, const double *z, const uint8_t *matched, int n_new);
 /* CSLAM::deleteOneFeature (SLAM.cpp:2637-2663), state and factor part: filter b of src drops feature ids[b] (0-based
  * position in the state); the reduced state is written to dst, a handle created for the same B, L-1 features and the
