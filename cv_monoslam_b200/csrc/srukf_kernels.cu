@@ -1039,31 +1039,15 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
           if (tt < nt) {
             const int j = J0 + 8 * tt + 2 * (lane & 3);
             const double g0 = -acc[qq][tt][0], g1 = -acc[qq][tt][1];
-            if (rs > tt) {
+            if (rs > tt) {   // strictly below the diagonal; padding entries are exact zeros and zmax starts at 0
               *reinterpret_cast<double2*>(prow + j) = make_double2(g0, g1);
+              zmax = fmax(zmax, fmax(g0, g1));
             } else if (rs == tt) {
               if (i > j) prow[j] = g0; else if (i == j) gdiag[i - J0] = g0;
               if (i > j + 1) prow[j + 1] = g1; else if (i == j + 1) gdiag[i - J0] = g1;
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int qq = 0; qq < MAXQ; ++qq) {
-      const int rs = warp + NW * qq;
-      if (rs < nstrip) {
-        const int i = J0 + 8 * rs + (lane >> 2);
-#pragma unroll
-        for (int tt = 0; tt < NB / 8; ++tt) {
-          if (tt < nt) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int j = J0 + 8 * tt + 2 * (lane & 3) + e;
-              const double v = -acc[qq][tt][e];
-              if (i < n && j < n) {
-                if (i == j) gmax = fmax(gmax, v);
-                else if (i > j) zmax = fmax(zmax, v);
+              if (i < n) {   // diagonal tile: max diag / max off-diag of G (:2204-2205), real rows and columns only
+                if (i == j) gmax = fmax(gmax, g0); else if (i > j) zmax = fmax(zmax, g0);
+                if (i == j + 1) gmax = fmax(gmax, g1); else if (i > j + 1) zmax = fmax(zmax, g1);
               }
             }
           }
