@@ -228,6 +228,7 @@ def run(out):
         nb = min(slab, B - b0)
         idx = wof[b0:b0 + nb]
         xs, Ss = xw[idx].contiguous(), Sw[idx].contiguous()
+        torch.cuda.current_stream().synchronize()   # the handle's stream is not ordered after torch's gather
         g.set_state_dev(b0, nb, xs.data_ptr(), Ss.data_ptr())
     del xs, Ss
     stream = torch.cuda.ExternalStream(g.stream(), device=dev)

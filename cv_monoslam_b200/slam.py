@@ -166,7 +166,8 @@ class CSLAMBatch:
         capi.check(self._lib.srukf_step(self._h, capi.ptr(u), capi.ptr(z), capi.ptr(m)))
 
     def SLAM_dev(self, d_u: int, d_z: int, d_matched: int):
-        """Same, inputs already in HBM (integer device addresses); asynchronous."""
+        """Same, inputs already in HBM (integer device addresses); asynchronous on the handle's own non-blocking
+        stream: the buffers must be complete before the call (synchronise the stream that produced them)."""
         capi.check(self._lib.srukf_step_dev(self._h, d_u, d_z, d_matched))
 
     # ---- diagnostics --------------------------------------------------------------------------

@@ -119,10 +119,13 @@ int srukf_kalman_update(srukf_t *h, const double *z, const uint8_t *matched);
 /* predictMotion + predictMeasurement + KalmanUpdate of one CSLAM::SLAM() frame (SLAM.cpp:91,93,99). */
 int srukf_step(srukf_t *h, const double *u, const double *z, const uint8_t *matched);
 
-/* device-pointer variants (inputs already resident in HBM; asynchronous on the handle's stream) */
+/* device-pointer variants (inputs already resident in HBM; asynchronous on the handle's stream).  The handle's stream is
+ * non-blocking: it is NOT ordered after the caller's streams, so the buffers must be complete (synchronise or wait on an
+ * event of the stream that produced them) before the call, and must stay valid until srukf_sync(). */
 int srukf_step_dev(srukf_t *h, const double *d_u, const double *d_z, const uint8_t *d_matched);
 /* device-to-device load of filters [b0, b0+nb): d_x [nb][n], d_S_packed [nb][n(n+1)/2] (either may be NULL).
- * (The library keeps S in its own blocked layout in HBM; all exchanged formats are the ones of this header.) */
+ * (The library keeps S in its own blocked layout in HBM; all exchanged formats are the ones of this header.)
+ * Returns after the copy has completed; the same readiness rule for d_x / d_S_packed applies on entry. */
 int srukf_set_state_dev(srukf_t *h, int b0, int nb, const double *d_x, const double *d_S_packed);
 
 /* m_P_k block (SLAM.cpp:2404): P[r0:r0+nr, r0:r0+nr] of S^T S per filter, out [B][nr][nr]. */

@@ -23,6 +23,7 @@ def run(L, B, steps=3, warmup=3):
     for b0 in range(0, B, 4096):
         nb = min(4096, B - b0); idx = wof[b0:b0 + nb]
         xs, Ss = xw[idx].contiguous(), Sw[idx].contiguous()
+        torch.cuda.current_stream().synchronize()   # the handle's stream is not ordered after torch's gather
         g.set_state_dev(b0, nb, xs.data_ptr(), Ss.data_ptr())
     du = torch.from_numpy(sc.u).cuda(); dz = torch.from_numpy(sc.z).cuda(); dm = torch.from_numpy(sc.matched).cuda()
     st = torch.cuda.ExternalStream(g.stream())
