@@ -1089,7 +1089,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
         const double sdj = sdsm[j];
         const double v = (i == j) ? sdj : sdj * crow[j];
         dcol[(size_t)j * np] = v;
-        if (i > j && real) tmax = fmax(tmax, v * v);
+        if (i > j && real) tmax = fmax(tmax, fabs(v));   // squared once, after the block reduction
       }
     }
     SRUKF_TICK(4)
@@ -1112,7 +1112,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   double nu = sqrt((double)n * n - 1.0);
   if (nu < 1.0) nu = 1.0;
   const double beta2 = fmax(fmax(gmax, zmax / nu), 1e-15);
-  if (tid == 0 && tmax > beta2) flags |= SRUKF_FLAG_GMW_MODIFIED;
+  if (tid == 0 && tmax * tmax > beta2) flags |= SRUKF_FLAG_GMW_MODIFIED;
   flags = __reduce_or_sync(0xffffffffu, flags);
   if (lane == 0 && flags) {
     atomicOr(q.flags + b, flags);
