@@ -471,3 +471,43 @@ def test_property_weights_sum_to_one_and_pair_scale_is_one(Na):
         w = O.sample_parameters(Na, O.default_params(weight_type=wt))
         assert abs(w["wm0"] + 2 * Na * w["wi"] - 1.0) < 1e-12
         assert abs(np.sqrt(2.0) * w["wi_sr"] * w["gamma"] - 1.0) < 1e-14
+
+
+@settings(max_examples=15, deadline=None)
+@given(hst.integers(2, 5), hst.integers(0, 4), hst.integers(0, 2 ** 31 - 1))
+def test_property_delete_is_marginalisation_on_random_pd_states(L, id_, seed):
+    """deleteOneFeature + six rank-one UPDATINGs (SLAM.cpp:2637-2663) on a random positive definite state."""
+    import oracle as O
+    id_ = id_ % L
+    n = 6 * L + 4
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((2 * n, n)) * 0.1
+    S = O.qr_R(A)
+    x = rng.standard_normal(n)
+    xo, So = O.delete_feature(O.default_params(), x, S, id_)
+    keep = np.r_[0:6 * id_, 6 * id_ + 6:n]
+    assert np.array_equal(xo, x[keep])
+    assert relmax(So.T @ So, (S.T @ S)[np.ix_(keep, keep)]) < 1e-11
+
+
+@settings(max_examples=10, deadline=None)
+@given(hst.integers(1, 3), hst.integers(1, 3), hst.integers(0, 2 ** 31 - 1))
+def test_property_add_features_keeps_old_covariance_and_is_psd(L, M, seed):
+    """integrateFeaturesInformation (SLAM.cpp:818-871) on a random positive definite state: the old block survives,
+    the result is positive semi-definite with rank deficiency 3M - 3 >= 0 coming from the repeated anchors only."""
+    import oracle as O
+    p = O.default_params()
+    n = 6 * L + 4
+    rng = np.random.default_rng(seed)
+    S = O.qr_R(rng.standard_normal((2 * n, n)) * 0.02)
+    x = np.concatenate([rng.normal(0, 0.3, 6 * L), rng.normal(0, 0.2, 3), rng.uniform(-np.pi, np.pi, 1)])
+    kp = np.column_stack([p.cam_cx + rng.uniform(-120, 120, M), p.cam_cy + rng.uniform(-90, 90, M)])
+    xo, So = O.add_features(p, x, S, kp, 1.0 / 3.0, 1.0 / 6.0)
+    assert np.isfinite(So).all()
+    Po = So.T @ So
+    n1 = n + 6 * M
+    old = np.r_[0:6 * L, n1 - 4:n1]
+    assert relmax(Po[np.ix_(old, old)], S.T @ S) < 1e-11
+    ev = np.linalg.eigvalsh(Po)
+    assert ev.min() > -1e-12 * ev.max()
+    assert (ev > 1e-12 * ev.max()).sum() == n1 - 3 * M          # anchors are exact copies of the robot position
