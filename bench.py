@@ -6,7 +6,7 @@
 
 One "step" = one frame of the hot path for every filter of the batch.  Workload at N GPUs: BASELINE.json
 configs[2] per GPU (65,536 filters x 50 landmarks, n = 304, 619 sigma points), i.e. weak scaling towards
-configs[4] (524,288 filters at N = 8).  Synthetic inputs: cv_monoslam_b200/synth.py.
+configs[4] (524,288 filters at N = 8).  Synthetic inputs: synth.py.
 
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the library's stream with inputs
 resident in HBM; `e2e` goes through the host-pointer C ABI (pinned host buffers, H2D of the step's inputs
@@ -110,7 +110,7 @@ def cpu_reference_run(L: int, filters: int, steps: int, warmup: int, threads: in
     Returns (seconds per step list, filters)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O  # the one place bench.py executes oracle/: as the measured CPU baseline
-    from cv_monoslam_b200 import synth
+    import synth
     O.build()
     sc = synth.make_scenario(L, filters, warmup + steps, unique=min(filters, 4), first_filter=seed_first)
     p = O.default_params(downdate_mode=2)
@@ -207,7 +207,8 @@ def run(out):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     dev = ctx.local_rank
     torch.cuda.set_device(dev)
-    from cv_monoslam_b200 import CSLAMBatch, capi, synth
+    from cv_monoslam_b200 import CSLAMBatch, capi
+    import synth
     from cv_monoslam_b200.slam import tri_pack
 
     B, L = args.filters, args.landmarks

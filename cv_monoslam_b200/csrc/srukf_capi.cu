@@ -22,6 +22,7 @@ struct StepPtrs {
   const CUtensorMap* tmaps; int sbuf; int tm_dz; int dz_filter0;
   double* Pd; double* Pd2; int carry_p;
   double* G2; int n_new;
+  int* nact;
 };
 // tensor-map table layout and box geometry (must match srukf_kernels.cu)
 constexpr int TM_S0 = 0, TM_S1 = 8, TM_UT = 16, TM_DZ = 24, TM_DZ_ALL = 25, TM_COUNT = 26, TM_ROWSETS = 8;
@@ -94,6 +95,7 @@ struct srukf_handle {
   double* G2 = nullptr;    // scratch of the NEED_REORDER update (allocated on first use)
   int gslots = 0;          // CTAs (and G scratch slots) of the reference-order fallback kernel
   int* worklist = nullptr;
+  int* nact = nullptr;     // [chunk] per-filter count of features used by k_gain
   unsigned long long* dbg = nullptr;  // phase-cycle counters (SRUKF_PHASE_TIMING=1)
   // split-API persistent intermediates (allocated on first use)
   double *rsig = nullptr, *dZ_all = nullptr, *U_all = nullptr, *G_all = nullptr;
@@ -309,6 +311,8 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   CUH(cudaMalloc(&h->U, sizeof(double) * (size_t)chunk * p.Lc * p.np));
   CUH(cudaMalloc(&h->G, sizeof(double) * (size_t)h->gslots * p.ntri));
   CUH(cudaMalloc(&h->worklist, sizeof(int) * ((size_t)chunk + 1)));
+  CUH(cudaMalloc(&h->nact, sizeof(int) * (size_t)chunk));
+  CUH(cudaMemsetAsync(h->nact, 0, sizeof(int) * (size_t)chunk, h->stream));
   CUH(cudaMemsetAsync(h->dZ, 0, sizeof(double) * (size_t)chunk * p.np * p.Lc, h->stream));
   CUH(cudaMemsetAsync(h->U, 0, sizeof(double) * (size_t)chunk * p.Lc * p.np, h->stream));
   CUH(cudaMemsetAsync(h->worklist, 0, sizeof(int) * ((size_t)chunk + 1), h->stream));
@@ -332,7 +336,7 @@ int srukf_destroy(srukf_t* h) {
   if (!h) return SRUKF_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->G2, h->Pd, h->Pd2, h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+  void* ptrs[] = {h->nact, h->G2, h->Pd, h->Pd2, h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -349,7 +353,7 @@ static StepPtrs base_ptrs(srukf_t* h) {
   q.S2 = h->S2; q.worklist = h->worklist; q.rel0 = 0; q.dbg = h->dbg;
   q.tmaps = h->tmaps; q.sbuf = h->sbuf; q.tm_dz = TM_DZ; q.dz_filter0 = 0;
   q.Pd = h->Pd; q.Pd2 = h->Pd2; q.carry_p = (h->prm.downdate_mode == 0) ? 1 : 0;
-  q.G2 = h->G2; q.n_new = 0;
+  q.G2 = h->G2; q.n_new = 0; q.nact = h->nact;
   return q;
 }
 

@@ -55,6 +55,8 @@ struct StepPtrs {
   int carry_p;
   double* G2;             // [gslots][ntri + 2 nbp] scratch of the NEED_REORDER downdate (mode 3; lazily allocated)
   int n_new;              // m_nFilters: the last n_new features were added on the previous frame (mode 3)
+  int* nact;              // [chunk] features k_gain actually used (matched && visible && det(si) != 0): k_update and
+                          // k_downdate take "no update this frame" (:2050) from the same count
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -614,6 +616,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p
   // KalmanUpdate returns early without matches, :2050 (k_update copies S through); the carried covariance still
   // needs its new robot-feature rows
   const bool none = (*nact == 0);
+  if (tid == 0) q.nact[blockIdx.x] = *nact;
   if (none && !q.carry_p) return;
   const bool seq_shift = (p.wc0 != p.wm0);
   const double wg = p.wi * p.gamma;
@@ -837,7 +840,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
         sdsm[c0 + lane] = sd;
         esm[c0 + lane] = emine;
         if (modified && J0 + c0 + lane < n) flags |= (dmine > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
-        if (!isfinite(sd)) flags |= SRUKF_FLAG_NAN;
+        if (!isfinite(sd) || !isfinite(emine)) flags |= SRUKF_FLAG_NAN;   // fmax(eps, |NaN|) = eps hides a NaN pivot: E = d - c_jj does not
         double* wrow = Wd + (size_t)(c0 + lane) * WD_PITCH + c0;
         double* crow = Cp + (size_t)(c0 + lane) * CP_PITCH + c0;
 #pragma unroll
@@ -917,8 +920,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
   double* Cp = Xs;
   uint32_t flags = 0;
 
-  int nact = 0;
-  for (int j = 0; j < L; ++j) nact += (q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j]) ? 1 : 0;
+  const int nact = q.nact[blockIdx.x];   // k_gain's count: a feature with a singular si contributes U = 0 (si.inv() = 0)
   if (nact == 0) {  // KalmanUpdate returned early (:2050): factor and covariance are carried over unchanged
     for (int i = tid; i < p.nbp; i += NTH) Snew[i] = Sold[i];
     for (int i = tid; i < np; i += NTH) PdNew[i] = PdOld[i];
@@ -1303,9 +1305,7 @@ __global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mo
     const double* Ut = q.U + (size_t)rel * p.Lc * np;
     double* G = q.G + (size_t)blockIdx.x * p.ntri;
     uint32_t flags = 0;
-    int nact = 0;
-    for (int j = 0; j < L; ++j) nact += (q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j]) ? 1 : 0;
-    if (nact == 0) continue;  // :2050
+    if (q.nact[rel] == 0) continue;  // :2050 (k_gain's count; with every si singular all U columns are zero)
     if (use_worklist) {       // rebuild from the untouched old factor
       const double* So = q.S + (size_t)b * p.nbp;
       for (int i = tid; i < p.nbp; i += NT) Sg[i] = So[i];
@@ -1903,22 +1903,24 @@ size_t update_smem_bytes(const DevParams& p) {
 }
 size_t downdate_smem_bytes(const DevParams& p) { return sizeof(double) * (2 * (size_t)p.n + 40); }
 
-cudaError_t configure_kernels(const DevParams& p) {
+// The dynamic shared-memory limit is a per-function, per-device attribute shared by every handle of the process:
+// it is raised once per device to the opt-in maximum and never lowered, so handles of different L can coexist
+// (a smaller-L handle created later must not shrink the limit of a live larger-L one).
+cudaError_t configure_kernels(const DevParams&) {
+  static bool done[64] = {};
+  int dev = 0;
   cudaError_t e;
-  int smem = (int)predict_smem_bytes(p);
-  if ((e = cudaFuncSetAttribute(k_predict<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-  if ((e = cudaFuncSetAttribute(k_predict<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-  if ((e = cudaFuncSetAttribute(k_predict<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
-  int gs = (int)gain_smem_bytes(p), us = (int)update_smem_bytes(p);
-  if ((e = cudaFuncSetAttribute(k_gain<8, 5, 4, 8, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
-  if ((e = cudaFuncSetAttribute(k_gain<16, 3, 7, GKC1, GNS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
-  if ((e = cudaFuncSetAttribute(k_gain<16, 5, 4, 8, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs))) return e;
-  if ((e = cudaFuncSetAttribute(k_update<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
-  if ((e = cudaFuncSetAttribute(k_update<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
-  if ((e = cudaFuncSetAttribute(k_update<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
-  if ((e = cudaFuncSetAttribute(k_update<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, us))) return e;
-  if ((e = cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)downdate_smem_bytes(p))))
-    return e;
+  if ((e = cudaGetDevice(&dev))) return e;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  int smem = 0;
+  if ((e = cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev))) return e;
+#define SRUKF_SET(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+  SRUKF_SET((k_predict<true, true>)) SRUKF_SET((k_predict<true, false>)) SRUKF_SET((k_predict<false, true>))
+  SRUKF_SET((k_gain<8, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<16, 3, 7, GKC1, GNS1>)) SRUKF_SET((k_gain<16, 5, 4, 8, NSTAGE>))
+  SRUKF_SET((k_update<8, false>)) SRUKF_SET((k_update<16, false>)) SRUKF_SET((k_update<8, true>)) SRUKF_SET((k_update<16, true>))
+  SRUKF_SET(k_downdate) SRUKF_SET(k_init_features) SRUKF_SET(k_add_features) SRUKF_SET(k_delete_feature)
+#undef SRUKF_SET
+  if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
 }
 
@@ -1954,7 +1956,6 @@ void launch_init_features(const DevParams& p, int nblocks, const double* x4, con
                           double* G, uint32_t* flags, cudaStream_t st) {
   InitArgs a{x4, S4, kp, rho0, sigma_rho, gamma, wi, p.B};
   const size_t smem = sizeof(double) * (size_t)(p.n + 40 + 33 * p.L + 16 + 32);
-  cudaFuncSetAttribute(k_init_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_init_features<<<nblocks, NT, smem, st>>>(p, a, x, S, Pd, G, flags);
 }
 void launch_add_features(const DevParams& p, int nblocks, const double* kp, double rho0, double sigma_rho, double gamma,

@@ -7,7 +7,9 @@ arbitrary well-conditioned priors make the reference's update diverge within a f
 (SURVEY V1/V2).  The factor is then put in the form every post-update factor has in the reference,
 S <- modifiedCholesky(S^T S) (SLAM.cpp:2152, 2197-2327), so it is unique up to rounding.
 
-This module is independent of oracle/: tests use it to cross-check the C oracle.
+TEST / BENCH INPUT INFRASTRUCTURE, not part of the product package: bench.py, smoke() and tests/ import it for
+inputs; tests also use its numpy restatements as an independent cross-check of the C oracle.  It is independent
+of oracle/.
 """
 from __future__ import annotations
 
@@ -323,6 +325,9 @@ def make_scenario(L: int, B: int, steps: int, unique: int | None = None, seed0: 
         z[:, b] = wz + noise.pix_sigma * rng.standard_normal((steps, L, 2))
         if match_prob < 1.0:
             matched[:, b] = (rng.uniform(size=(steps, L)) < match_prob).astype(np.uint8)
+        # a landmark whose true pixel is outside the view (project_world returns (0, 0), as the reference's
+        # Camera2Image / distortion zeroing does) cannot be matched by dataAssociation (SLAM.cpp:1946-2001)
+        matched[:, b] &= ((wz[..., 0] != 0.0) & (wz[..., 1] != 0.0)).astype(np.uint8)
     return Scenario(L=L, B=B, steps=steps, x0=x0, S0=S0, u=u, z=z, matched=matched, truth=truth,
                     meta=dict(unique=U, seed0=seed0, match_prob=match_prob, first_filter=first_filter,
                               world_of=world_of, dense_state=dense_state))

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 import oracle as O  # noqa: E402
-from cv_monoslam_b200 import synth  # noqa: E402
+import synth  # noqa: E402
 
 CASES = {
     # name: (L, B, steps, match_prob)

@@ -4,7 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import oracle as O
-from cv_monoslam_b200 import CSLAMBatch, synth, capi
+from cv_monoslam_b200 import CSLAMBatch, capi
+import synth
 
 def relmax(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)

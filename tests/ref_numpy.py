@@ -7,7 +7,7 @@ the C camera chain.  TEST INFRASTRUCTURE ONLY.
 """
 import numpy as np
 
-from cv_monoslam_b200 import synth
+import synth
 
 
 def step(x, S, u, z, matched, cam=None, noise_sigma=3.0, a=(8, 8, 8, 8), weight_type=0, eps=1e-13):

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from cv_monoslam_b200 import synth
+import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

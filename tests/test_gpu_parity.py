@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from conftest import relmax
-from cv_monoslam_b200 import synth
+import synth
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -42,13 +42,15 @@ def check_state(g, x_ref, P_ref, tol=TOL):
 
 
 def run_against_oracle(gpu, oracle, L, B, steps, *, mode_gpu=0, split=False, match_prob=1.0, weight_type=0,
-                       unique=None, oracle_filters=None, tol=TOL):
+                       unique=None, oracle_filters=None, tol=TOL, mode_oracle=1):
+    """mode_oracle 1 = the oracle's carry-P sequence (fast), 0 = LITERAL SLAM.cpp:2116-2153 (S^T S re-formed per
+    U column, then the modified Cholesky)."""
     from cv_monoslam_b200 import CSLAMBatch
     sc = synth.make_scenario(L, B, steps, unique=unique, match_prob=match_prob)
     g = CSLAMBatch(B, L, gpu.default_params(downdate_mode=mode_gpu, weight_type=weight_type))
     g.set_state(sc.x0, sc.S0)
     sel = np.arange(B) if oracle_filters is None else np.asarray(oracle_filters)
-    p = oracle.default_params(downdate_mode=1, weight_type=weight_type)
+    p = oracle.default_params(downdate_mode=mode_oracle, weight_type=weight_type)
     x, S = sc.x0[sel].copy(), sc.S0[sel].copy()
     worst = [0.0, 0.0]
     for s in range(steps):
@@ -552,16 +554,90 @@ def test_rerun_is_bit_identical(gpu):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
 
 
-def test_config2_4096_filters_20_landmarks_100_steps(gpu, oracle):
-    """BASELINE config 2: every filter runs on the GPU for 100 steps; the oracle follows a seeded subset of
-    filters step by step (the full 4096 x 100 oracle run is ~1.5 CPU-hours), all filters are checked through
-    size-independent properties."""
-    from cv_monoslam_b200 import CSLAMBatch
-    L, B, steps = 20, 4096, 100
-    sel = np.array([0, 1, 2, 3, 1000, 2047, 3000, 4095])
-    worst, flags, sc = run_against_oracle(gpu, oracle, L, B, steps, unique=16, oracle_filters=sel)
+def test_config2_4096_filters_20_landmarks_every_filter(gpu, oracle):
+    """BASELINE config 2, part 1: ALL 4096 filters (4096 distinct worlds) against the oracle, step by step, 5 steps."""
+    worst, flags, _ = run_against_oracle(gpu, oracle, 20, 4096, 5, unique=4096)
     assert worst[0] <= TOL and worst[1] <= TOL
     assert not (flags & (gpu.FLAG_NAN | gpu.FLAG_GMW_MODIFIED)).any()
+
+
+def test_config2_4096_filters_20_landmarks_100_steps(gpu, oracle):
+    """BASELINE config 2, part 2: every filter runs on the GPU for 100 steps; the oracle follows 64 filters spread over
+    the batch (64 distinct worlds) step by step; the other filters are covered by test_..._every_filter for the
+    first steps and here through their flags."""
+    L, B, steps = 20, 4096, 100
+    sel = np.unique(np.concatenate([np.arange(0, B, 65), [B - 1]]))[:64]
+    assert len(sel) == 64
+    worst, flags, sc = run_against_oracle(gpu, oracle, L, B, steps, unique=4096, oracle_filters=sel)
+    assert worst[0] <= TOL and worst[1] <= TOL
+    assert not (flags & (gpu.FLAG_NAN | gpu.FLAG_GMW_MODIFIED)).any()
+
+
+@pytest.mark.parametrize("L,B,steps", [(50, 2, 2), (20, 4, 20)])
+def test_fused_path_matches_the_literal_reference_sequence(gpu, oracle, L, B, steps):
+    """The fused one-shot update (downdate_mode 0) against the oracle's LITERAL mode 0: per matched feature and per
+    U column, S^T S re-formed with a triangular-aware dense product, u u^T subtracted, modified Cholesky
+    (SLAM.cpp:2116-2153 as written), not the carry-P variant the other tests use for speed."""
+    worst, flags, _ = run_against_oracle(gpu, oracle, L, B, steps, unique=B, mode_oracle=0)
+    assert worst[0] <= TOL and worst[1] <= TOL
+    assert not (flags & (gpu.FLAG_NAN | gpu.FLAG_GMW_MODIFIED)).any()
+
+
+def test_sharding_is_bit_identical(gpu):
+    """the same global filter ids run as ONE batch and as TWO shards (the second shard on a second device
+    when the box has one, else a second handle on the same device) give bit-identical per-filter x and S; the
+    statistics agree to summation order."""
+    import torch
+    from cv_monoslam_b200 import CSLAMBatch
+    L, B, steps = 10, 600, 4       # several waves of CTAs per shard
+    full = synth.make_scenario(L, B, steps, unique=B)
+    one = CSLAMBatch(B, L, device=0)
+    one.set_state(full.x0, full.S0)
+    for s in range(steps):
+        one.SLAM(full.u[s], full.z[s], full.matched[s])
+    x1, S1 = one.get_state()
+    st1 = one.stats(full.truth[steps - 1])
+    one.close()
+    dev2 = 1 if torch.cuda.device_count() > 1 else 0
+    xs, Ss, st2 = [], [], np.zeros(8)
+    cut = 277                      # deliberately not a multiple of anything
+    for (lo, hi, dev) in ((0, cut, 0), (cut, B, dev2)):
+        sc = synth.make_scenario(L, hi - lo, steps, unique=B, first_filter=lo)
+        assert np.array_equal(sc.x0, full.x0[lo:hi]) and np.array_equal(sc.z, full.z[:, lo:hi])
+        g = CSLAMBatch(hi - lo, L, device=dev)
+        g.set_state(sc.x0, sc.S0)
+        for s in range(steps):
+            g.SLAM(sc.u[s], sc.z[s], sc.matched[s])
+        x, S = g.get_state()
+        xs.append(x); Ss.append(S)
+        st2 += g.stats(sc.truth[steps - 1])
+        g.close()
+    assert np.array_equal(np.concatenate(xs), x1) and np.array_equal(np.concatenate(Ss), S1)
+    assert st2[4] == st1[4] == B
+    assert np.allclose(st2[:4], st1[:4], rtol=1e-12, atol=0)
+
+
+def test_handles_of_different_size_coexist(gpu, oracle):
+    """The dynamic shared-memory limit of a kernel is per function and device, not per handle: creating a smaller-L
+    handle (here through deleteFeature, whose destination has L-1 features) must not break the launches of a live
+    larger-L handle.  L = 50 needs ~70-96 KB of dynamic shared memory per CTA."""
+    from cv_monoslam_b200 import CSLAMBatch
+    L, B = 50, 3
+    sc = synth.make_scenario(L, B, 2, unique=1)
+    a, ref = CSLAMBatch(B, L), CSLAMBatch(B, L)
+    for g in (a, ref):
+        g.set_state(sc.x0, sc.S0)
+        g.SLAM(sc.u[0], sc.z[0], sc.matched[0])
+    small = a.deleteFeature(np.full(B, 7, dtype=np.int32))    # creates an (L-1)-feature handle; `a` is left untouched
+    tiny = CSLAMBatch(2, 3)                                     # and a much smaller one
+    a.SLAM(sc.u[1], sc.z[1], sc.matched[1])
+    ref.SLAM(sc.u[1], sc.z[1], sc.matched[1])
+    xa, Sa = a.get_state()
+    xr, Sr = ref.get_state()
+    assert np.array_equal(xa, xr) and np.array_equal(Sa, Sr)
+    assert np.isfinite(small.get_x()).all()
+    for g in (a, ref, small, tiny):
+        g.close()
 
 
 def test_properties_at_headline_size(gpu):

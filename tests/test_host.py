@@ -6,7 +6,8 @@ import sys
 import numpy as np
 import pytest
 
-from cv_monoslam_b200 import dist, synth
+from cv_monoslam_b200 import dist
+import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

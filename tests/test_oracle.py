@@ -1,7 +1,7 @@
 """CPU tests of the oracle (oracle/srukf_oracle.c) -- the checker must itself be checked.
 
 The reference has no tests or golden vectors (parity unpinned), so the oracle is pinned by
-(1) an independent numpy/LAPACK restatement (tests/ref_numpy.py, cv_monoslam_b200/synth.py),
+(1) an independent numpy/LAPACK restatement (tests/ref_numpy.py, synth.py),
 (2) mpmath at 50 digits on small cases, (3) known-answer properties, (4) committed fixtures.
 """
 import glob
@@ -13,7 +13,7 @@ import pytest
 
 import ref_numpy
 from conftest import relmax
-from cv_monoslam_b200 import synth
+import synth
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

@@ -2,7 +2,8 @@
 import hashlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from cv_monoslam_b200 import CSLAMBatch, synth
+from cv_monoslam_b200 import CSLAMBatch
+import synth
 
 def run(L, B, steps):
     noise = synth.Noise() if L < 80 else synth.Noise(control=(0.003, 0.001, 0.003), odo_sigma=(3e-4, 1.5e-4, 3e-4))

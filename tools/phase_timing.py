@@ -3,7 +3,8 @@ import os, sys
 os.environ["SRUKF_PHASE_TIMING"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from cv_monoslam_b200 import CSLAMBatch, synth, capi
+from cv_monoslam_b200 import CSLAMBatch, capi
+import synth
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 50
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 592
 sc = synth.make_scenario(L, B, 3, unique=2)

@@ -5,7 +5,8 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 import bench
-from cv_monoslam_b200 import CSLAMBatch, synth
+from cv_monoslam_b200 import CSLAMBatch
+import synth
 from cv_monoslam_b200.slam import tri_pack
 
 def run(L, B, steps=3, warmup=3):
