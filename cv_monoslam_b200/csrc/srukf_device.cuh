@@ -148,6 +148,16 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return x;
 }
 
+// 1/d = x0 (1 + e2) with x0 = MUFU.RCP64H(d) (20-bit input, ~2^-20 relative error), e = 1 - d x0, e2 = e + e^2: relative
+// error e^3 < 2^-57.  Used on the pivot chains: 1/d is never formed there -- a product p = u x0 is started as soon as x0
+// is known and corrected with ONE fused multiply-add, fma(-p, e2, r - p), so that only three FP64 operations (e, e2, the
+// correction) depend on each other per pivot instead of seven.
+__device__ __forceinline__ void rcp_parts(double d, double& x0, double& e2) {
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(d));
+  const double e = fma(-d, x0, 1.0);
+  e2 = fma(e, e, e);
+}
+
 // ---------------------------------------------------------------------------------------------
 // distortOnePointRW, SLAM.cpp:3177-3213.
 // The reference solves rd + k1 rd^3 + k2 rd^5 = ru by 100 Newton steps and returns c + (xu/d)/dx with

@@ -790,7 +790,8 @@ template <int NW>
 __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm, double* sdsm, double* esm, int R,
                                              int nbe, int J0, int n, double eps, uint32_t& flags) {
   constexpr int NTH = NW * 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: plain shuffles inside `if (warp == 0)`
   const int nsub = nbe / 8;
   for (int sb = 0; sb < nsub; ++sb) {
     const int c0 = 8 * sb;
@@ -898,9 +899,10 @@ template <int NW, bool TIMING>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
   extern __shared__ __align__(128) unsigned char smraw[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int b = q.chunk0 + blockIdx.x;
-  const int n = p.n, L = p.L, np = p.np, Lc = p.Lc;
+  const int n = p.n, np = p.np, Lc = p.Lc;
   const double* Sold = q.S + (size_t)b * p.nbp;
   double* Snew = q.S2 + (size_t)b * p.nbp;
   const CUtensorMap* tmNew = q.tmaps + (q.sbuf ? TM_S0 : TM_S1);
