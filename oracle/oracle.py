@@ -1,6 +1,6 @@
 """ctypes binding of the CPU oracle (oracle/srukf_oracle.c).
 
-TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see srukf_oracle.h).  Only tests/, smoke() and
+TEST INFRASTRUCTURE ONLY -- pinned to the reference's own text by tests/test_ref_pin.py (see srukf_oracle.h).  Only tests/, smoke() and
 bench.py's cpu_baseline / --impl reference legs may import this module; the product package
 (cv_monoslam_b200) never does.
 """

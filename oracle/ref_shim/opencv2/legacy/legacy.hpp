@@ -1,0 +1,2 @@
+/* stand-in: everything the reference path needs is in ref_shim.h */
+#include "../../ref_shim.h"

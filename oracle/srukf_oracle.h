@@ -4,10 +4,18 @@
  * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call it.
  *
- * PARITY UNPINNED: the reference (MonoSLAM/SLAM.cpp, Win32/MFC + OpenCV 2.4.3 + GSL 1.8) cannot be
- * compiled here and ships no tests, golden vectors or recorded data.  This file restates its
- * arithmetic line by line (citations are MonoSLAM/SLAM.cpp:line unless noted); the restatement is
- * cross-checked against an independent numpy/mpmath restatement and LAPACK in tests/.
+ * PARITY PINNED TO THE REFERENCE'S TEXT (except at the GSL boundary).  The reference (MonoSLAM/SLAM.cpp, Win32/MFC +
+ * OpenCV 2.4.3 + GSL 1.8) ships no tests, golden vectors or recorded data and its own build cannot run here, but the
+ * bodies of its functions on this path compile unchanged against a small cv::Mat / MFC stand-in: oracle/ref_shim/
+ * extracts them verbatim from /root/reference at build time into oracle/_ref/ (git-ignored) and
+ * tests/test_ref_pin.py runs them beside this file on the same inputs.  Every function below reproduces the
+ * reference's result BIT FOR BIT in literal mode (downdate_mode 0 / 2): sample parameters, the modified Cholesky,
+ * the camera chain, whole predict / measure / update frames up to L = 50, the NEED_REORDER update, feature
+ * initialisation, augmentation and deletion.  tests/golden/*.npz are outputs of that reference build.
+ * What stays a restatement: gsl_linalg_QR_decomp (GSL is not vendored by the reference; the reference build calls
+ * oracle_qr_decomp below, which is cross-checked against LAPACK dgeqrf and mpmath in tests/test_oracle.py) and the
+ * OpenCV primitives inside the stand-in (checked against cv2 in tests/test_ref_shim.py).
+ * This file restates the arithmetic line by line (citations are MonoSLAM/SLAM.cpp:line unless noted).
  *
  * Third-party arithmetic restated (not vendored by the reference):
  *   - GSL 1.8 gsl_linalg_QR_decomp (unblocked Householder, linalg/qr.c + householder.c), called at

@@ -21,6 +21,17 @@ def oracle():
 
 
 @pytest.fixture(scope="session")
+def reference():
+    """oracle/ref.py: the reference's own function bodies (extracted at build time) behind ctypes; test infrastructure.
+    Built where /root/reference exists; elsewhere the prebuilt oracle/_ref/libsrukf_ref.so is used, else skip."""
+    import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libsrukf_ref.so absent and no reference tree to build it from")
+    R.lib()
+    return R
+
+
+@pytest.fixture(scope="session")
 def built_lib():
     """libsrukf_b200.so, built in-tree (nvcc cross-compiles without a GPU)."""
     from cv_monoslam_b200 import build, capi

@@ -414,22 +414,25 @@ def test_reorder_update_projects_the_new_anchors(oracle):
 # ---- committed fixtures ------------------------------------------------------------------------------
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*.npz"))))
 def test_oracle_reproduces_golden_fixtures(oracle, path):
+    """The fixtures are outputs of the reference's own code (make_golden.py ran oracle/_ref); the C restatement in
+    literal mode reproduces them to the bit on x and (same expression for P) on S^T S."""
     g = np.load(path)
     L, B, steps = int(g["L"]), int(g["B"]), int(g["steps"])
+    wt = int(g["weight_type"]) if "weight_type" in g.files else 0
     x, S = g["x0"].copy(), g["S0"].copy()
-    p = oracle.default_params(downdate_mode=0)
+    p = oracle.default_params(downdate_mode=0, weight_type=wt)
     for s in range(steps):
         oracle.batch_step(p, x, S, g["u"][s:s + 1], g["z"][s:s + 1], g["matched"][s:s + 1], 4)
-        P = np.einsum("bki,bkj->bij", S, S)
         for b in range(B):
-            assert relmax(x[b], g["x"][s, b]) < 1e-12
-            assert relmax(P[b], g["P"][s, b]) < 1e-12
+            assert np.array_equal(x[b], g["x"][s, b])
+            assert np.array_equal(S[b].T @ S[b], g["P"][s, b])
 
 
 def test_golden_inputs_are_reproducible_from_seeds():
     g = np.load(os.path.join(GOLD, "L3_B4_s6.npz"))
     sc = synth.make_scenario(3, 4, 6)
-    assert np.array_equal(sc.u, g["u"]) and np.array_equal(sc.z, g["z"])
+    assert np.array_equal(sc.z, g["z"])
+    assert np.abs(sc.u - g["u"]).max() < 1e-15      # g["u"] is what predictMotion derived from the odometry poses
     assert relmax(sc.x0, g["x0"]) < 1e-13 and relmax(sc.S0, g["S0"]) < 1e-9
 
 
