@@ -10,7 +10,7 @@ configs[4] (524,288 filters at N = 8).  Synthetic inputs: synth.py.
 
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the library's stream with inputs
 resident in HBM; `e2e` goes through the host-pointer C ABI (pinned host buffers, H2D of the step's inputs
-and D2H of m_X_k inside the timed region).  The roofline entry is for the dominant kernel (k_update),
+and D2H of m_X_k inside the timed region, overlapped with the neighbouring frames by the library's copy streams).  The roofline entry is for the dominant kernel (k_update),
 timed live with CUDA events by the library (srukf_set_profiling).
 """
 from __future__ import annotations
@@ -28,7 +28,35 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FP64_PEAK_TFLOPS = 37.2   # measured DMMA peak on this pool's B200 (profiles/r01_fp64_peak.json) == nominal
+FP64_PEAK_FALLBACK_TFLOPS = 37.2   # only if the in-run measurement fails: profiles/r01_fp64_peak.json (DMMA m8n8k4)
+
+
+def measured_peaks() -> dict:
+    """MEASURED_PEAKS.json (driver-written): HBM copy bandwidth of this pool's B200s.  It has no FP64 entry: the FP64
+    tensor-pipe peak is measured by the library in this very process (srukf_fp64_peak) next to the timed region."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+def committed_traffic(kernel: str, L: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per FILTER of `kernel` from the latest committed `ncu --set full`
+    summary of this command (profiles/*_traffic.json, written by tools/ncu_summary.py --json); None if there is none
+    for this L.  Never a constant in this file."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
+        try:
+            with open(path) as f:
+                rec = json.load(f)
+        except (OSError, ValueError):
+            continue
+        k = rec.get("kernels", {}).get(kernel)
+        if k and int(rec.get("landmarks", -1)) == L:
+            best = (k["dram_bytes_per_filter"], os.path.relpath(path, ROOT))
+    return best
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -104,18 +132,71 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_string(B: int, L: int) -> str:
+    n = 6 * L + 4
+    return (f"batched SRUKF predict+update, {B} filters x {L} landmarks per GPU (n={n}, {2 * (n + 5) + 1} sigma points), "
+            "FP64 (BASELINE configs[2])")
+
+
+def config_dict(B: int, L: int, unique: int, world: int, downdate_mode: int) -> dict:
+    """the `config` object of BOTH arms (the reference arm times a sample of this workload, see cpu_baseline.sample)"""
+    n = 6 * L + 4
+    ntri = n * (n + 1) // 2
+    return {"workload": workload_string(B, L),
+            "filters_per_gpu": B, "landmarks": L, "state_dim": n, "sigma_points": 2 * (n + 5) + 1,
+            "distinct_worlds": int(unique), "parallelism": f"filters sharded over {world} GPU(s)",
+            "l2": f"inputs larger than L2: {B * ntri * 8 / 2**30:.1f} GiB of packed S per GPU streamed per step",
+            "downdate_mode": downdate_mode}
+
+
 def cpu_reference_run(L: int, filters: int, steps: int, warmup: int, threads: int, seed_first: int = 0):
-    """Times the oracle port of the reference algorithm (literal mode: materialised sigma matrices, Householder
-    QR of the 2Na x n matrix, one dense S^T S + modified Cholesky per U column) on host cores.
-    Returns (seconds per step list, filters)."""
+    """Times the reference's CPU implementation of the path on `threads` host threads, one filter per thread at a time:
+    predictMotion + predictMeasurement + KalmanUpdate with materialised sigma matrices, the Householder QR of the
+    2Na x n matrix, and one dense S^T S + modified Cholesky per U column.
+
+    kind "reference": oracle/_ref/libsrukf_ref.so -- the bodies of the reference's own functions (extracted verbatim from
+    MonoSLAM/SLAM.cpp where /root/reference exists; the prebuilt library travels to the GPU box) over the cv::Mat stand-in
+    of oracle/ref_shim.  kind "port": the C restatement oracle/srukf_oracle.c (bit-identical results, ~4x faster: no
+    temporaries), used when the reference library is absent.  Returns (kind, seconds per step list)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O  # the one place bench.py executes oracle/: as the measured CPU baseline
     import synth
-    O.build()
     sc = synth.make_scenario(L, filters, warmup + steps, unique=min(filters, 4), first_filter=seed_first)
+    times = []
+    import ref as R  # oracle/ref.py: the one other place bench.py executes oracle/ -- as the measured CPU baseline
+    if R.available():
+        import threading
+        R.lib()
+        slams = []
+        for b in range(filters):
+            r = R.Slam()
+            r.set_state(sc.x0[b], sc.S0[b])
+            slams.append(r)
+        odo = [[R.control_to_odometry(sc.u[s, b]) for b in range(filters)] for s in range(warmup + steps)]
+
+        def work(tid, s):
+            for b in range(tid, filters, threads):
+                r = slams[b]
+                r.predict_motion_odometry(*odo[s][b])
+                r.predict_measurement()
+                r.kalman_update(sc.z[s, b], sc.matched[s, b])
+
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            ths = [threading.Thread(target=work, args=(t, s)) for t in range(threads)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                times.append(dt)
+        x, _ = slams[0].get_state()
+        assert np.isfinite(x).all()
+        return "reference", times
+    import oracle as O
+    O.build()
     p = O.default_params(downdate_mode=2)
     x, S = sc.x0.copy(), sc.S0.copy()
-    times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
         O.batch_step(p, x, S, sc.u[s:s + 1], sc.z[s:s + 1], sc.matched[s:s + 1], threads)
@@ -123,18 +204,24 @@ def cpu_reference_run(L: int, filters: int, steps: int, warmup: int, threads: in
         if s >= warmup:
             times.append(dt)
     assert np.isfinite(x).all()
-    return times
+    return "port", times
+
+
+CPU_KIND_TEXT = {
+    "reference": "the reference's own SLAM.cpp function bodies (oracle/_ref, g++ -O2, cv::Mat stand-in of oracle/ref_shim)",
+    "port": "oracle literal mode (C restatement of SLAM.cpp: dense S^T S + GMW per U column), gcc -O2",
+}
 
 
 def run_reference(args, ctx, out):
-    """--impl reference: the reference's CPU algorithm (oracle port; oracle/_ref is unbuildable: MFC + OpenCV 2.4.3
-    + GSL 1.8) with all host threads, each step a bounded sample of the workload."""
+    """--impl reference: the reference's CPU implementation with all host threads; each step is a bounded SAMPLE of the
+    workload (one filter per host thread), the metric is filter-steps/s of that sample."""
     if ctx.rank != 0:
         return
     cores = os.cpu_count() or 1
     L = args.landmarks
     filters = cores
-    times = cpu_reference_run(L, filters, args.steps, args.warmup, cores)
+    kind, times = cpu_reference_run(L, filters, args.steps, args.warmup, cores)
     tot = float(sum(times))
     value = filters * len(times) / tot
     n = 6 * L + 4
@@ -142,11 +229,10 @@ def run_reference(args, ctx, out):
         "impl": "reference", "metric": "srukf_filter_steps_per_sec", "value": value, "unit": "filter-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"batched SRUKF, {args.filters} filters x {L} landmarks per GPU (n={n}), FP64",
-                   "filters_per_gpu": args.filters, "landmarks": L, "state_dim": n, "sigma_points": 2 * (n + 5) + 1},
-        "cpu_baseline": {"value": value, "unit": "filter-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{filters} filters (one per host thread) x {len(times)} steps of the same workload, "
-                                   "oracle literal mode, gcc -O2"},
+        "config": config_dict(args.filters, L, min(args.unique, args.filters), args.gpus, args.downdate_mode),
+        "cpu_baseline": {"value": value, "unit": "filter-steps/s", "cores": cores, "kind": kind,
+                         "sample": f"{filters} filters (one per host thread) x {len(times)} steps of the same workload: "
+                                   + CPU_KIND_TEXT[kind]},
         "e2e": {"value": value, "unit": "filter-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -271,8 +357,10 @@ def run(out):
     hx_np = hx.numpy()
     lib, hnd = g._lib, g._h
     def e2e_step(s):
+        # inputs of this frame travel on the library's copy stream while the previous frame computes; the read-back of
+        # m_X_k of this frame overlaps the next one (srukf_get_x_async) -- both inside the timed region
         capi.check(lib.srukf_step(hnd, hu[s].data_ptr(), hz[s].data_ptr(), hm[s].data_ptr()))
-        capi.check(lib.srukf_get_state(hnd, hx.data_ptr(), None))
+        capi.check(lib.srukf_get_x_async(hnd, hx.data_ptr()))
     for s in range(W):
         e2e_step(s)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -301,10 +389,24 @@ def run(out):
     cpu = None
     if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        times = cpu_reference_run(L, cores, 6, 0, cores)
-        cpu = {"value": cores * len(times) / sum(times), "unit": "filter-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{cores} filters (one per host thread) x {len(times)} steps at L={L}, oracle literal mode "
-                         f"(dense S^T S + GMW per U column), gcc -O2, {sum(times):.1f} s"}
+        kind, t1 = cpu_reference_run(L, 1, 2 if L >= 40 else 20, 0, 1)                 # one core, as the reference runs
+        kind, tn = cpu_reference_run(L, cores, 2 if L >= 40 else 20, 0, cores)         # every core, one filter each
+        cpu = {"value": cores * len(tn) / sum(tn), "unit": "filter-steps/s", "cores": cores, "kind": kind,
+               "sample": f"{cores} filters (one per host thread) x {len(tn)} steps at L={L}: {CPU_KIND_TEXT[kind]}, "
+                         f"{sum(tn):.1f} s",
+               "one_core": {"value": len(t1) / sum(t1), "cores": 1, "seconds_per_filter_step": sum(t1) / len(t1),
+                            "sample": f"1 filter x {len(t1)} steps"}}
+
+    peak = FP64_PEAK_FALLBACK_TFLOPS
+    peak_source = "fallback: profiles/r01_fp64_peak.json (tools/fp64_peak.cu, DMMA m8n8k4)"
+    try:
+        from cv_monoslam_b200.slam import fp64_peak_tflops
+        peak = fp64_peak_tflops(dev)
+        peak_source = ("measured in this run: srukf_fp64_peak (back-to-back DMMA m8n8k4, 8 warps x 4 CTAs per SM, best of 5) "
+                       "right after the timed region; MEASURED_PEAKS.json has no FP64 entry")
+    except Exception as e:   # noqa: BLE001
+        peak_source += f" ({e})"
+    hbm_peak = float(measured_peaks().get("hbm_gbs", 0.0)) or None
 
     if ctx.rank == 0:
         total_steps = float(B) * ctx.world * K
@@ -314,34 +416,29 @@ def run(out):
         t_dd = kms[2] / max(int(kcnt[2]), 1) * 1e-3
         achieved = wd * per_launch_filters / t_dd / 1e12 if t_dd > 0 else 0.0
         w_total = wd + flops_gain(n, L) + flops_predict(n, L)
+        traffic = committed_traffic("k_update", L) if args.downdate_mode == 0 else None
         line = {
             "metric": "srukf_filter_steps_per_sec", "value": value, "unit": "filter-steps/s",
             "n_gpus": ctx.world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"batched SRUKF predict+update, {B} filters x {L} landmarks per GPU "
-                                   f"(n={n}, {2 * (n + 5) + 1} sigma points), FP64 (BASELINE configs[2])",
-                       "filters_per_gpu": B, "landmarks": L, "state_dim": n, "sigma_points": 2 * (n + 5) + 1,
-                       "distinct_worlds": int(sc.meta["unique"]), "parallelism": f"filters sharded over {ctx.world} GPU(s)",
-                       "l2": f"inputs larger than L2: {B * ntri * 8 / 2**30:.1f} GiB of packed S per GPU streamed per step",
-                       "downdate_mode": args.downdate_mode},
+            "config": config_dict(B, L, int(sc.meta["unique"]), ctx.world, args.downdate_mode),
             "clocks": clocks,
             "e2e": {"value": total_steps / (ms_e2e * 1e-3), "unit": "filter-steps/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe)", "kernel": "k_update",
-                         "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved / FP64_PEAK_TFLOPS,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_update launch from the committed
-                         # `ncu --set full` capture of this command (profiles/r01_ncu_summary.md): 2.78 MB per filter
-                         "traffic": (2.776e6 * per_launch_filters) if (L == 50 and args.downdate_mode == 0) else None,
-                         "peak_source": "measured: tools/fp64_peak.cu DMMA m8n8k4 (profiles/r01_fp64_peak.json); "
-                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak,
+                         "traffic": (traffic[0] * per_launch_filters) if traffic else None,
+                         "traffic_source": traffic[1] if traffic else None,
+                         "peak_source": peak_source,
                          "flops_per_filter_step_kernel": wd, "flops_per_filter_step_all": w_total,
-                         "whole_step_frac": value / ctx.world * w_total / (FP64_PEAK_TFLOPS * 1e12),
+                         "whole_step_frac": value / ctx.world * w_total / (peak * 1e12),
                          "kernel_ms": {"k_predict": float(kms[0]), "k_gain": float(kms[1]), "k_update": float(kms[2])},
                          "kernel_launches": [int(c) for c in kcnt],
                          "algorithmic_bytes_per_filter_step": algorithmic_bytes(n, L),
-                         "hbm_frac_of_measured_6454GBs": value / ctx.world * algorithmic_bytes(n, L) / 6454e9},
+                         "hbm_peak_gbs": hbm_peak,
+                         "hbm_frac": (value / ctx.world * algorithmic_bytes(n, L) / (hbm_peak * 1e9)) if hbm_peak else None},
             "cpu_baseline": cpu,
             "stats": stats,
         }

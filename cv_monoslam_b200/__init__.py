@@ -8,6 +8,7 @@ bench.py.  There is no CPU fallback: importing works anywhere, but creating a fi
 the built library or without a CUDA device raises.
 """
 from .capi import SrukfError, SrukfParams, default_params, lib_path, load_library  # noqa: F401
-from .slam import CSLAMBatch  # noqa: F401
+from .slam import (CSLAMBatch, GSLQrDecomposition, generateSigmaPoints,  # noqa: F401
+                   modifiedCholeskyDecomposition)
 
-__all__ = ["CSLAMBatch", "SrukfParams", "SrukfError", "default_params", "load_library", "lib_path"]
+__all__ = ["CSLAMBatch", "modifiedCholeskyDecomposition", "GSLQrDecomposition", "generateSigmaPoints", "SrukfParams", "SrukfError", "default_params", "load_library", "lib_path"]

@@ -55,6 +55,12 @@ SYMBOLS = {
     "srukf_chi2_gate": (C.c_int, [_VP, _VP, C.c_double, _VP, _VP]),
     "srukf_kalman_update": (C.c_int, [_VP, _VP, _VP]),
     "srukf_step": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "srukf_get_x_async": (C.c_int, [_VP, _VP]),
+    "srukf_mchol": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _VP, _VP, _VP]),
+    "srukf_qr_R": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
+    "srukf_generate_sigma_points": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _VP, _VP, _VP]),
+    "srukf_cholesky_update": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "srukf_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "srukf_step_dev": (C.c_int, [_VP, _VP, _VP, _VP]),
     "srukf_set_state_dev": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP]),
     "srukf_get_cov_block": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),

@@ -62,6 +62,14 @@ void launch_gate(const DevParams& p, const double* z, const double* hbar, const 
                  double threshold, uint8_t* accept, double* d2, cudaStream_t st);
 void launch_stats(const DevParams& p, const double* x, const double* S, const double* truth, double* perf,
                   const uint32_t* flags, double* out, cudaStream_t st);
+size_t downdate_smem_bytes(const DevParams& p);
+void launch_mchol_batch(int nb, int n, double eps, const double* Gd, double* Gp, double* Sd, uint32_t* flags, int grid,
+                        cudaStream_t st);
+void launch_qr_batch(int nb, int m, int n, const double* A, double* W, double* R, int grid, cudaStream_t st);
+void launch_sigma_points(int nb, int Na, double gamma, const double* mu, const double* sr, double* sigma, cudaStream_t st);
+void launch_chol_update(const DevParams& p, int grid, double* S, double* Pd, const double* Ut, int k, double sign, int M,
+                        double* G, double* G2, uint32_t* flags, cudaStream_t st);
+cudaError_t measure_fp64_peak(int sms, int iters, int reps, double* tflops, cudaStream_t st);
 }  // namespace srukf
 
 using namespace srukf;
@@ -86,6 +94,14 @@ struct srukf_handle {
   CUtensorMap* tmaps = nullptr;                       // device table of TMA tensor maps
   // per-step inputs (device copies for the host-pointer API)
   double *u = nullptr, *z = nullptr; uint8_t* matched = nullptr;
+  // srukf_step (host pointers): the inputs of step s+1 are copied on copy_stream into the other input set while step s
+  // computes; srukf_get_x_async reads m_X_k back through a staging copy on d2h_stream while the next step computes
+  double *u_in[2] = {nullptr, nullptr}, *z_in[2] = {nullptr, nullptr}; uint8_t* m_in[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_xs = nullptr, ev_xd = nullptr;
+  int in_slot = 0;
+  bool inputs_dirty = true;   // an entry point other than srukf_step has queued work that reads input set 0
+  double* x_stage = nullptr;
   // prediction outputs
   double *hbar = nullptr, *si = nullptr, *cshift = nullptr, *pxyr = nullptr; uint8_t* visible = nullptr;
   uint32_t* flags = nullptr;
@@ -336,7 +352,10 @@ int srukf_destroy(srukf_t* h) {
   if (!h) return SRUKF_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* ptrs[] = {h->nact, h->G2, h->Pd, h->Pd2, h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
+  for (cudaEvent_t e : {h->ev_in[0], h->ev_in[1], h->ev_done[0], h->ev_done[1], h->ev_xs, h->ev_xd}) if (e) cudaEventDestroy(e);
+  void* ptrs[] = {h->u_in[1], h->z_in[1], h->m_in[1], h->x_stage, h->nact, h->G2, h->Pd, h->Pd2, h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -530,6 +549,7 @@ static int ensure_split_buffers(srukf_t* h) {
 
 int srukf_predict_motion(srukf_t* h, const double* u) {
   if (!h || !u) return fail(SRUKF_EINVAL, "srukf_predict_motion: null argument");
+  h->inputs_dirty = true;
   CU(cudaSetDevice(h->device));
   int rc = ensure_split_buffers(h);
   if (rc) return rc;
@@ -570,6 +590,7 @@ int srukf_get_prediction(srukf_t* h, double* hbar, double* si, uint8_t* visible)
 int srukf_chi2_gate(srukf_t* h, const double* z, double threshold, uint8_t* accept, double* d2) {
   if (!h || !z || !accept) return fail(SRUKF_EINVAL, "srukf_chi2_gate: null argument");
   if (h->phase != 2) return fail(SRUKF_ESTATE, "srukf_chi2_gate: call srukf_predict_measurement first");
+  h->inputs_dirty = true;
   CU(cudaSetDevice(h->device));
   const DevParams& p = h->p;
   const size_t BL = (size_t)p.B * p.L;
@@ -622,6 +643,7 @@ static void flip_buffers(srukf_t* h) {
 int srukf_kalman_update(srukf_t* h, const double* z, const uint8_t* matched) {
   if (!h || !z || !matched) return fail(SRUKF_EINVAL, "srukf_kalman_update: null argument");
   if (h->phase != 2) return fail(SRUKF_ESTATE, "srukf_kalman_update: call srukf_predict_measurement first");
+  h->inputs_dirty = true;
   CU(cudaSetDevice(h->device));
   const DevParams& p = h->p;
   CU(cudaMemcpyAsync(h->z, z, sizeof(double) * (size_t)p.B * 2 * p.L, cudaMemcpyHostToDevice, h->stream));
@@ -644,6 +666,7 @@ int srukf_kalman_update_reorder(srukf_t* h, const double* z, const uint8_t* matc
   if (n_new < 0 || n_new > h->p.L) return fail(SRUKF_EINVAL, "srukf_kalman_update_reorder: n_new must be in 0..L");
   if (n_new == 0) return srukf_kalman_update(h, z, matched);   // m_nAddings == 0: NEEDNOT_REORDER (:2087-2090)
   if (h->phase != 2) return fail(SRUKF_ESTATE, "srukf_kalman_update_reorder: call srukf_predict_measurement first");
+  h->inputs_dirty = true;
   CU(cudaSetDevice(h->device));
   const DevParams& p = h->p;
   if (!h->G2) CU(cudaMalloc(&h->G2, sizeof(double) * (size_t)h->gslots * ((size_t)p.ntri + 2 * (size_t)p.nbp)));
@@ -692,14 +715,68 @@ int srukf_step_dev(srukf_t* h, const double* d_u, const double* d_z, const uint8
   return SRUKF_OK;
 }
 
+// lazily created: second input set, copy / read-back streams and their events
+static int ensure_async(srukf_t* h) {
+  if (h->copy_stream) return SRUKF_OK;
+  const DevParams& p = h->p;
+  CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+  h->u_in[0] = h->u; h->z_in[0] = h->z; h->m_in[0] = h->matched;
+  CU(cudaMalloc(&h->u_in[1], sizeof(double) * (size_t)p.B * 3));
+  CU(cudaMalloc(&h->z_in[1], sizeof(double) * (size_t)p.B * 2 * p.L));
+  CU(cudaMalloc(&h->m_in[1], (size_t)p.B * p.L));
+  for (int i = 0; i < 2; ++i) {
+    CU(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreateWithFlags(&h->ev_xs, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&h->ev_xd, cudaEventDisableTiming));
+  return SRUKF_OK;
+}
+
 int srukf_step(srukf_t* h, const double* u, const double* z, const uint8_t* matched) {
   if (!h || !u || !z || !matched) return fail(SRUKF_EINVAL, "srukf_step: null argument");
   CU(cudaSetDevice(h->device));
+  int rc = ensure_async(h);
+  if (rc) return rc;
   const DevParams& p = h->p;
-  CU(cudaMemcpyAsync(h->u, u, sizeof(double) * (size_t)p.B * 3, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->z, z, sizeof(double) * (size_t)p.B * 2 * p.L, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->matched, matched, (size_t)p.B * p.L, cudaMemcpyHostToDevice, h->stream));
-  return srukf_step_dev(h, h->u, h->z, h->matched);
+  const int s = h->in_slot;
+  h->in_slot ^= 1;
+  // this input set was last read by the srukf_step before the previous one (ev_done[s]); after any other entry point
+  // that uses h->u / h->z / h->matched (= set 0) the copy waits for everything queued on the handle's stream
+  if (h->inputs_dirty) {
+    CU(cudaEventRecord(h->ev_done[s], h->stream));
+    h->inputs_dirty = false;
+  }
+  CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[s], 0));
+  CU(cudaMemcpyAsync(h->u_in[s], u, sizeof(double) * (size_t)p.B * 3, cudaMemcpyHostToDevice, h->copy_stream));
+  CU(cudaMemcpyAsync(h->z_in[s], z, sizeof(double) * (size_t)p.B * 2 * p.L, cudaMemcpyHostToDevice, h->copy_stream));
+  CU(cudaMemcpyAsync(h->m_in[s], matched, (size_t)p.B * p.L, cudaMemcpyHostToDevice, h->copy_stream));
+  CU(cudaEventRecord(h->ev_in[s], h->copy_stream));
+  CU(cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
+  rc = srukf_step_dev(h, h->u_in[s], h->z_in[s], h->m_in[s]);
+  if (rc) return rc;
+  CU(cudaEventRecord(h->ev_done[s], h->stream));
+  return SRUKF_OK;
+}
+
+int srukf_get_x_async(srukf_t* h, double* x_host) {
+  if (!h || !x_host) return fail(SRUKF_EINVAL, "srukf_get_x_async: null argument");
+  CU(cudaSetDevice(h->device));
+  int rc = ensure_async(h);
+  if (rc) return rc;
+  const size_t bytes = sizeof(double) * (size_t)h->p.B * h->p.n;
+  if (!h->x_stage) {
+    CU(cudaMalloc(&h->x_stage, bytes));
+    CU(cudaEventRecord(h->ev_xd, h->d2h_stream));
+  }
+  CU(cudaStreamWaitEvent(h->stream, h->ev_xd, 0));    // the previous read-back has left the staging copy
+  CU(cudaMemcpyAsync(h->x_stage, h->x, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaEventRecord(h->ev_xs, h->stream));
+  CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_xs, 0));
+  CU(cudaMemcpyAsync(x_host, h->x_stage, bytes, cudaMemcpyDeviceToHost, h->d2h_stream));
+  CU(cudaEventRecord(h->ev_xd, h->d2h_stream));
+  return SRUKF_OK;
 }
 
 int srukf_set_state_dev(srukf_t* h, int b0, int nb, const double* d_x, const double* d_S_packed) {
@@ -760,10 +837,124 @@ int srukf_stats(srukf_t* h, const double* truth, double* out8) {
   return SRUKF_OK;
 }
 
+// ---- CSLAM helper methods (SLAM.h:322,341,347-348,355) as stand-alone entry points ---------------------------------
+static int helper_device(int device, const char* who) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SRUKF_ENODEV, who);
+  if (device < 0 || device >= ndev) return fail(SRUKF_EINVAL, who);
+  CU(cudaSetDevice(device));
+  DevParams dummy{};
+  CU(configure_kernels(dummy));
+  return SRUKF_OK;
+}
+
+int srukf_mchol(int device, int nb, int n, double epsilon, const double* G, double* S, uint32_t* flags) {
+  if (nb <= 0 || n <= 0 || !G || !S) return fail(SRUKF_EINVAL, "srukf_mchol: bad arguments");
+  int rc = helper_device(device, "srukf_mchol: no CUDA device (there is no CPU fallback)");
+  if (rc) return rc;
+  const size_t mat = sizeof(double) * (size_t)n * n, ntri = (size_t)n * (n + 1) / 2;
+  const int grid = nb < 296 ? nb : 296;
+  double *dG = nullptr, *dS = nullptr, *dP = nullptr;
+  uint32_t* dF = nullptr;
+  cudaError_t e = cudaMalloc(&dG, mat * nb);
+  if (!e) e = cudaMalloc(&dS, mat * nb);
+  if (!e) e = cudaMalloc(&dP, sizeof(double) * ntri * grid);
+  if (!e) e = cudaMalloc(&dF, sizeof(uint32_t) * nb);
+  if (!e) e = cudaMemcpy(dG, G, mat * nb, cudaMemcpyHostToDevice);
+  if (!e) { launch_mchol_batch(nb, n, epsilon, dG, dP, dS, dF, grid, 0); e = cudaGetLastError(); }
+  if (!e) e = cudaMemcpy(S, dS, mat * nb, cudaMemcpyDeviceToHost);
+  if (!e && flags) e = cudaMemcpy(flags, dF, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost);
+  cudaFree(dG); cudaFree(dS); cudaFree(dP); cudaFree(dF);
+  if (e) return fail(e == cudaErrorMemoryAllocation ? SRUKF_ENOMEM : SRUKF_ECUDA, "srukf_mchol", e);
+  return SRUKF_OK;
+}
+
+int srukf_qr_R(int device, int nb, int m, int n, const double* A, double* R) {
+  if (nb <= 0 || m <= 0 || n <= 0 || m < n || !A || !R) return fail(SRUKF_EINVAL, "srukf_qr_R: bad arguments (need m >= n)");
+  int rc = helper_device(device, "srukf_qr_R: no CUDA device (there is no CPU fallback)");
+  if (rc) return rc;
+  const size_t amat = sizeof(double) * (size_t)m * n, rmat = sizeof(double) * (size_t)n * n;
+  const int grid = nb < 296 ? nb : 296;
+  double *dA = nullptr, *dW = nullptr, *dR = nullptr;
+  cudaError_t e = cudaMalloc(&dA, amat * nb);
+  if (!e) e = cudaMalloc(&dW, amat * grid);
+  if (!e) e = cudaMalloc(&dR, rmat * nb);
+  if (!e) e = cudaMemcpy(dA, A, amat * nb, cudaMemcpyHostToDevice);
+  if (!e) { launch_qr_batch(nb, m, n, dA, dW, dR, grid, 0); e = cudaGetLastError(); }
+  if (!e) e = cudaMemcpy(R, dR, rmat * nb, cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(dW); cudaFree(dR);
+  if (e) return fail(e == cudaErrorMemoryAllocation ? SRUKF_ENOMEM : SRUKF_ECUDA, "srukf_qr_R", e);
+  return SRUKF_OK;
+}
+
+int srukf_generate_sigma_points(int device, int nb, int Na, double gamma, const double* mu, const double* sr,
+                                double* sigma) {
+  if (nb <= 0 || Na <= 0 || !mu || !sr || !sigma) return fail(SRUKF_EINVAL, "srukf_generate_sigma_points: bad arguments");
+  int rc = helper_device(device, "srukf_generate_sigma_points: no CUDA device (there is no CPU fallback)");
+  if (rc) return rc;
+  const size_t P = 2 * (size_t)Na + 1;
+  double *dm = nullptr, *ds = nullptr, *dg = nullptr;
+  cudaError_t e = cudaMalloc(&dm, sizeof(double) * Na * nb);
+  if (!e) e = cudaMalloc(&ds, sizeof(double) * (size_t)Na * Na * nb);
+  if (!e) e = cudaMalloc(&dg, sizeof(double) * Na * P * nb);
+  if (!e) e = cudaMemcpy(dm, mu, sizeof(double) * Na * nb, cudaMemcpyHostToDevice);
+  if (!e) e = cudaMemcpy(ds, sr, sizeof(double) * (size_t)Na * Na * nb, cudaMemcpyHostToDevice);
+  if (!e) { launch_sigma_points(nb, Na, gamma, dm, ds, dg, 0); e = cudaGetLastError(); }
+  if (!e) e = cudaMemcpy(sigma, dg, sizeof(double) * Na * P * nb, cudaMemcpyDeviceToHost);
+  cudaFree(dm); cudaFree(ds); cudaFree(dg);
+  if (e) return fail(e == cudaErrorMemoryAllocation ? SRUKF_ENOMEM : SRUKF_ECUDA, "srukf_generate_sigma_points", e);
+  return SRUKF_OK;
+}
+
+int srukf_cholesky_update(srukf_t* h, const double* U, int k, int up_or_down, int order, int n_new) {
+  if (!h || !U || k <= 0) return fail(SRUKF_EINVAL, "srukf_cholesky_update: bad arguments");
+  if ((up_or_down != SRUKF_UPDATING && up_or_down != SRUKF_DOWNDATING) ||
+      (order != SRUKF_NEED_REORDER && order != SRUKF_NEEDNOT_REORDER))
+    return fail(SRUKF_EINVAL, "srukf_cholesky_update: bad flag (use the SRUKF_* values of srukf.h)");
+  const DevParams& p = h->p;
+  const int M = (order == SRUKF_NEED_REORDER) ? n_new : 0;
+  if (order == SRUKF_NEED_REORDER && (n_new < 1 || n_new > p.L))
+    return fail(SRUKF_EINVAL, "srukf_cholesky_update: NEED_REORDER needs 1 <= n_new <= L");
+  CU(cudaSetDevice(h->device));
+  if (M && !h->G2) CU(cudaMalloc(&h->G2, sizeof(double) * (size_t)h->gslots * ((size_t)p.ntri + 2 * (size_t)p.nbp)));
+  // u is dim x k per filter (a cv::Mat in the reference); the kernels want its columns contiguous and padded to np
+  std::vector<double> ut((size_t)p.B * k * p.np, 0.0);
+  for (int b = 0; b < p.B; ++b)
+    for (int r = 0; r < p.n; ++r)
+      for (int c = 0; c < k; ++c) ut[((size_t)b * k + c) * p.np + r] = U[((size_t)b * p.n + r) * k + c];
+  double* dU = nullptr;
+  CU(cudaMalloc(&dU, sizeof(double) * ut.size()));
+  cudaError_t e = cudaMemcpyAsync(dU, ut.data(), sizeof(double) * ut.size(), cudaMemcpyHostToDevice, h->stream);
+  if (!e) {
+    const int grid = p.B < h->gslots ? p.B : h->gslots;
+    launch_chol_update(p, grid, h->S, h->Pd, dU, k, up_or_down == SRUKF_UPDATING ? +1.0 : -1.0, M, h->G, h->G2, h->flags,
+                       h->stream);
+    h->launches++;
+    e = cudaStreamSynchronize(h->stream);
+  }
+  if (!e) e = cudaGetLastError();
+  cudaFree(dU);
+  if (e) return fail(SRUKF_ECUDA, "srukf_cholesky_update", e);
+  h->phase = 0;
+  return SRUKF_OK;
+}
+
+int srukf_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(SRUKF_EINVAL, "srukf_fp64_peak: null argument");
+  int rc = helper_device(device, "srukf_fp64_peak: no CUDA device");
+  if (rc) return rc;
+  int sms = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  CU(measure_fp64_peak(sms, 20000, 5, tflops, 0));
+  return SRUKF_OK;
+}
+
 int srukf_sync(srukf_t* h) {
   if (!h) return fail(SRUKF_EINVAL, "srukf_sync: null handle");
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
+  if (h->copy_stream) CU(cudaStreamSynchronize(h->copy_stream));
+  if (h->d2h_stream) CU(cudaStreamSynchronize(h->d2h_stream));
   CU(cudaGetLastError());
   return SRUKF_OK;
 }

@@ -1135,10 +1135,10 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
 // -------------------------------------------------------------------------------------------------
 // (n, pitch, eps explicit: the NEED_REORDER path factorises a leading block; evec, if given, receives E_j = d_j - c_jj)
 __device__ void mchol_core(int n, int np, double eps, double* G, double* S, double* wcol, double* red, uint32_t& flags,
-                           double* evec) {
+                           double* evec, double zmax0 = 0.0) {
   const int tid = threadIdx.x;
-  // :2204-2211
-  double gmax = -1.0e300, zmax = 0.0;
+  // :2204-2211 (zmax0: largest entry of the other triangle when the caller's input was not symmetric)
+  double gmax = -1.0e300, zmax = zmax0;
   for (int j = 0; j < n; ++j) {
     const double* col = G + tri_off(j, n);
     if (tid == 0) gmax = fmax(gmax, col[0]);
@@ -1854,6 +1854,178 @@ __global__ void __launch_bounds__(256) k_stats_reduce(int B, const double* __res
 }
 
 // -------------------------------------------------------------------------------------------------
+// Stand-alone helper kernels behind the CSLAM helper methods of the facade (SLAM.h:322,341,347-348,355).  They run
+// the same device routines as the fallback path; one CTA per matrix / filter, unblocked, operands in global memory.
+// -------------------------------------------------------------------------------------------------
+// CSLAM::modifiedCholeskyDecomposition(Mat& sr, const Mat& Cov), SLAM.cpp:2197-2327: nb dense n x n inputs Gd (the
+// lower triangle is factorised, :2237-2261; beta^2 takes the maxima over the whole matrix, :2204-2205) -> dense upper S
+__global__ void __launch_bounds__(NT) k_mchol_batch(int nb, int n, double eps, const double* __restrict__ Gd, double* Gp,
+                                                    double* Sd, uint32_t* flagsg) {
+  extern __shared__ double sm[];
+  double* wcol = sm;
+  double* red = wcol + n;
+  const int tid = threadIdx.x, ntri = n * (n + 1) / 2;
+  double* G = Gp + (size_t)blockIdx.x * ntri;
+  for (int m = blockIdx.x; m < nb; m += gridDim.x) {
+    const double* src = Gd + (size_t)m * n * n;
+    double* S = Sd + (size_t)m * n * n;
+    double zup = 0.0;
+    for (int idx = tid; idx < n * n; idx += NT) {
+      const int i = idx / n, j = idx - i * n;
+      S[idx] = 0.0;
+      if (i >= j) G[tri_off(j, n) + (i - j)] = src[idx];
+      else zup = fmax(zup, src[idx]);
+    }
+    zup = block_max<NT>(zup, red);
+    __syncthreads();
+    uint32_t flags = 0;
+    mchol_core(n, n, eps, G, S, wcol, red, flags, nullptr, zup);
+    __syncthreads();
+    for (int i = tid; i < n; i += NT)
+      if (!isfinite(S[(size_t)i * n + i])) flags |= SRUKF_FLAG_NAN;
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (flagsg) {
+      if (tid == 0) flagsg[m] = 0;
+      __syncthreads();
+      if ((tid & 31) == 0 && flags) atomicOr(flagsg + m, flags);
+    }
+    __syncthreads();
+  }
+}
+
+// CSLAM::GSLQrDecomposition(Mat& R, const Mat& A), SLAM.cpp:2330-2353: triu(R) of gsl_linalg_QR_decomp (unblocked
+// Householder; beta = -sign(alpha) hypot(alpha, |x|), tau = (beta - alpha)/beta, v = x/(alpha - beta); tau = 0 and the
+// column untouched when |x| = 0 or the column has one element).  A [nb][m][n] row-major, W scratch [grid][m*n].
+__global__ void __launch_bounds__(NT) k_qr_batch(int nb, int m, int n, const double* __restrict__ A, double* W, double* R) {
+  __shared__ double red[40];
+  const int tid = threadIdx.x;
+  double* Wb = W + (size_t)blockIdx.x * m * n;
+  for (int mat = blockIdx.x; mat < nb; mat += gridDim.x) {
+    const double* src = A + (size_t)mat * m * n;
+    for (int i = tid; i < m * n; i += NT) Wb[i] = src[i];
+    __syncthreads();
+    const int kmax = m < n ? m : n;
+    for (int i = 0; i < kmax; ++i) {
+      const int len = m - i;
+      if (len == 1) break;                       // a one-element column: tau = 0
+      double* c = Wb + (size_t)i * n + i;        // column i from row i on, stride n
+      double mx = 0.0;
+      for (int r = 1 + tid; r < len; r += NT) mx = fmax(mx, fabs(c[(size_t)r * n]));
+      mx = block_max<NT>(mx, red);
+      if (mx == 0.0) continue;                   // |x| = 0: tau = 0, the column stays
+      double ss = 0.0;
+      for (int r = 1 + tid; r < len; r += NT) { const double v = c[(size_t)r * n] / mx; ss += v * v; }
+      ss = block_sum<NT>(ss, red);
+      const double xnorm = mx * sqrt(ss);        // dnrm2's scaled sum of squares
+      const double alpha = c[0];
+      const double beta = -(alpha >= 0.0 ? 1.0 : -1.0) * hypot(alpha, xnorm);
+      const double tau = (beta - alpha) / beta;
+      const double sc = 1.0 / (alpha - beta);
+      __syncthreads();
+      for (int r = 1 + tid; r < len; r += NT) c[(size_t)r * n] *= sc;
+      if (tid == 0) c[0] = beta;
+      __syncthreads();
+      for (int j = i + 1 + tid; j < n; j += NT) {   // gsl_linalg_householder_hm, column by column
+        double* a = Wb + (size_t)i * n + j;
+        double wj = a[0];
+        for (int r = 1; r < len; ++r) wj += a[(size_t)r * n] * c[(size_t)r * n];
+        a[0] = a[0] - tau * wj;
+        for (int r = 1; r < len; ++r) a[(size_t)r * n] = a[(size_t)r * n] - tau * c[(size_t)r * n] * wj;
+      }
+      __syncthreads();
+    }
+    double* Rb = R + (size_t)mat * n * n;
+    for (int idx = tid; idx < n * n; idx += NT) {
+      const int i = idx / n, j = idx - i * n;
+      Rb[idx] = (j >= i && i < m) ? Wb[(size_t)i * n + j] : 0.0;
+    }
+    __syncthreads();
+  }
+}
+
+// CSLAM::generateSigmaPoints(Mat& sigma, const Mat& mu, const Mat& sr), SLAM.cpp:1148-1162:
+// sigma(:,0) = mu, sigma(:,i+1) = mu*1 + sr.row(i)^T*gamma + 0, sigma(:,Na+i+1) = mu*1 + sr.row(i)^T*(-gamma) + 0
+__global__ void k_sigma_points(int Na, double gamma, const double* __restrict__ mu, const double* __restrict__ sr,
+                               double* sigma) {
+  const int P = 2 * Na + 1;
+  const double* mub = mu + (size_t)blockIdx.x * Na;
+  const double* srb = sr + (size_t)blockIdx.x * Na * Na;
+  double* sg = sigma + (size_t)blockIdx.x * Na * P;
+  for (int idx = threadIdx.x; idx < Na * P; idx += blockDim.x) {
+    const int r = idx / P, c = idx - r * P;
+    double v = mub[r];
+    if (c >= 1 && c <= Na) v = mub[r] * 1 + srb[(size_t)(c - 1) * Na + r] * gamma + 0;
+    else if (c > Na) v = mub[r] * 1 + srb[(size_t)(c - 1 - Na) * Na + r] * ((-1) * gamma) + 0;
+    sg[idx] = v;
+  }
+}
+
+// CSLAM::GSLCholeskyUpdate(const Mat& u, flag4UpOrDown, flag4Order), SLAM.cpp:2106-2155, on the handle's factor with
+// caller-supplied columns: Ut [B][k][np] (column c of filter b's u at Ut[(b*k + c)*np ..]), sign = +1 UPDATING /
+// -1 DOWNDATING.  M == 0: NEEDNOT_REORDER, per column S <- modifiedCholesky(S^T S + sign u u^T) (:2139-2153).
+// M > 0: NEED_REORDER with the last M features new (:2122-2138), the covariance carried across the columns as in
+// k_downdate mode 3.
+__global__ void __launch_bounds__(NT) k_chol_update(DevParams p, double* S, double* Pd, const double* __restrict__ Ut,
+                                                    int k, double sign, int M, double* G, double* G2, uint32_t* flagsg) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, n = p.n, np = p.np;
+  double* wcol = sm;
+  double* red = wcol + n;
+  double* Gb = G + (size_t)blockIdx.x * p.ntri;
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    double* Sg = S + (size_t)b * p.nbp;
+    const double* Ub = Ut + (size_t)b * k * np;
+    uint32_t flags = 0;
+    if (M == 0) {
+      for (int c = 0; c < k; ++c) {
+        form_G(p, Sg, Ub, c, c + 1, Gb, sign);
+        __syncthreads();
+        mchol_inplace(p, Gb, Sg, wcol, red, flags);
+        __syncthreads();
+      }
+    } else {
+      form_G(p, Sg, Ub, 0, 0, Gb);
+      __syncthreads();
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int c = 0; c < k; ++c) {
+        const double* urow = Ub + (size_t)c * np;
+        for (int kk = warp; kk < n; kk += NT / 32) {
+          double* col = Gb + tri_off(kk, n);
+          const double uk = sign * urow[kk];
+          for (int i = kk + lane; i < n; i += 32) col[i - kk] = fma(uk, urow[i], col[i - kk]);
+        }
+        __syncthreads();
+        reorder_project(p, M, Gb, G2 + (size_t)blockIdx.x * (p.ntri + 2 * (size_t)p.nbp), wcol, red, flags);
+      }
+      mchol_inplace(p, Gb, Sg, wcol, red, flags);
+      __syncthreads();
+    }
+    for (int i = tid; i < n; i += NT)
+      if (!isfinite(Sg[bp_idx(i, i, np)])) flags |= SRUKF_FLAG_NAN;
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if ((tid & 31) == 0 && flags) atomicOr(flagsg + b, flags);
+    if (Pd) form_P(p, Sg, Pd + (size_t)b * np);
+    __syncthreads();
+  }
+}
+
+// FP64 pipe peak as this process sees it (bench.py's roofline denominator): back-to-back DMMA m8n8k4 with 8
+// independent accumulator pairs per warp, 8 warps per CTA, 4 CTAs per SM.  256 FMA per warp instruction.
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+  double c0[8], c1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c0[i] = i; c1[i] = -i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma(c0[i], c1[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
+  if (s == 12345.678) out[0] = s;
+}
+
+// -------------------------------------------------------------------------------------------------
 // host-side launchers (called from srukf_capi.cu)
 // -------------------------------------------------------------------------------------------------
 int tile_warps(const DevParams& p) {  // warps per CTA of k_update; 0 = unsupported size
@@ -1921,6 +2093,7 @@ cudaError_t configure_kernels(const DevParams&) {
   SRUKF_SET((k_gain<8, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<16, 3, 7, GKC1, GNS1>)) SRUKF_SET((k_gain<16, 5, 4, 8, NSTAGE>))
   SRUKF_SET((k_update<8, false>)) SRUKF_SET((k_update<16, false>)) SRUKF_SET((k_update<8, true>)) SRUKF_SET((k_update<16, true>))
   SRUKF_SET(k_downdate) SRUKF_SET(k_init_features) SRUKF_SET(k_add_features) SRUKF_SET(k_delete_feature)
+  SRUKF_SET(k_chol_update) SRUKF_SET(k_mchol_batch)
 #undef SRUKF_SET
   if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
@@ -1987,6 +2160,44 @@ void launch_gate(const DevParams& p, const double* z, const double* hbar, const 
 }
 void launch_cov_block(const DevParams& p, const double* S, int r0, int nr, double* out, cudaStream_t st) {
   k_cov_block<<<p.B, 128, 0, st>>>(p.n, p.np, p.nbp, S, r0, nr, out);
+}
+void launch_mchol_batch(int nb, int n, double eps, const double* Gd, double* Gp, double* Sd, uint32_t* flags, int grid,
+                        cudaStream_t st) {
+  k_mchol_batch<<<grid, NT, sizeof(double) * (size_t)(n + 40), st>>>(nb, n, eps, Gd, Gp, Sd, flags);
+}
+void launch_qr_batch(int nb, int m, int n, const double* A, double* W, double* R, int grid, cudaStream_t st) {
+  k_qr_batch<<<grid, NT, 0, st>>>(nb, m, n, A, W, R);
+}
+void launch_sigma_points(int nb, int Na, double gamma, const double* mu, const double* sr, double* sigma, cudaStream_t st) {
+  k_sigma_points<<<nb, 256, 0, st>>>(Na, gamma, mu, sr, sigma);
+}
+void launch_chol_update(const DevParams& p, int grid, double* S, double* Pd, const double* Ut, int k, double sign, int M,
+                        double* G, double* G2, uint32_t* flags, cudaStream_t st) {
+  k_chol_update<<<grid, NT, downdate_smem_bytes(p), st>>>(p, S, Pd, Ut, k, sign, M, G, G2, flags);
+}
+// returns the measured DMMA throughput in TFLOP/s (best of `reps` launches of ~`iters` x 8 DMMAs per warp)
+cudaError_t measure_fp64_peak(int sms, int iters, int reps, double* tflops, cudaStream_t st) {
+  double* out = nullptr;
+  cudaError_t e = cudaMalloc(&out, sizeof(double));
+  if (e) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int blocks = sms * 4;
+  float best = 1e30f;
+  for (int r = 0; r < reps + 1; ++r) {
+    cudaEventRecord(e0, st);
+    k_fp64_peak<<<blocks, 256, 0, st>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1, st);
+    if ((e = cudaEventSynchronize(e1))) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;   // the first launch warms up
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  if (e) return e;
+  *tflops = 2.0 * 256.0 * blocks * 8.0 /*warps*/ * (double)iters * 8.0 / (best * 1e-3) * 1e-12;
+  return cudaSuccess;
 }
 void launch_stats(const DevParams& p, const double* x, const double* S, const double* truth, double* perf,
                   const uint32_t* flags, double* out, cudaStream_t st) {

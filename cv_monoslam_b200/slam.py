@@ -165,6 +165,18 @@ class CSLAMBatch:
         m = np.ascontiguousarray(isMatching, dtype=np.uint8).reshape(self.B, self.L)
         capi.check(self._lib.srukf_step(self._h, capi.ptr(u), capi.ptr(z), capi.ptr(m)))
 
+    def get_x_async(self, out_host_ptr: int):
+        """Read-back of m_X_k that overlaps the next frame (srukf_get_x_async): `out_host_ptr` is the address of a
+        pinned [B, n] float64 host buffer; complete after sync()."""
+        capi.check(self._lib.srukf_get_x_async(self._h, int(out_host_ptr)))
+
+    def GSLCholeskyUpdate(self, u: np.ndarray, flag4UpOrDown: int, flag4Order: int, n_new: int = 0):
+        """CSLAM::GSLCholeskyUpdate (SLAM.h:347, SLAM.cpp:2106-2155) on every filter's m_S_k: u [B, n, k];
+        flag values as in the reference (FLAG_4_UPDATING 0 / DOWNDATING 1, NEED_REORDER 0 / NEEDNOT_REORDER 1)."""
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(self.B, self.n, -1)
+        capi.check(self._lib.srukf_cholesky_update(self._h, capi.ptr(u), u.shape[2], int(flag4UpOrDown), int(flag4Order),
+                                                   int(n_new)))
+
     def SLAM_dev(self, d_u: int, d_z: int, d_matched: int):
         """Same, inputs already in HBM (integer device addresses); asynchronous on the handle's own non-blocking
         stream: the buffers must be complete before the call (synchronise the stream that produced them)."""
@@ -217,3 +229,51 @@ class CSLAMBatch:
     def set_state_dev(self, b0: int, nb: int, d_x: int | None, d_S_packed: int | None):
         """Device-to-device load of filters [b0, b0+nb) (integer device addresses)."""
         capi.check(self._lib.srukf_set_state_dev(self._h, b0, nb, d_x, d_S_packed))
+
+
+# ---- CSLAM helper methods that do not need a filter handle (SLAM.h:322,341,348,355) -------------------------
+FLAG_4_UPDATING, FLAG_4_DOWNDATING = 0, 1            # SLAM.cpp:31-32
+FLAG_4_NEED_REORDER, FLAG_4_NEEDNOT_REORDER = 0, 1   # SLAM.cpp:36-37
+
+
+def modifiedCholeskyDecomposition(Cov: np.ndarray, epsilon: float = 1e-13, device: int = 0, return_flags: bool = False):
+    """CSLAM::modifiedCholeskyDecomposition (SLAM.cpp:2197-2327) on the GPU: Cov [nb, n, n] or [n, n] -> sr (upper)."""
+    G = np.ascontiguousarray(Cov, dtype=np.float64)
+    single = G.ndim == 2
+    G = G.reshape(-1, G.shape[-1], G.shape[-1])
+    S = np.empty_like(G)
+    fl = np.zeros(G.shape[0], dtype=np.uint32)
+    capi.check(capi.load_library().srukf_mchol(device, G.shape[0], G.shape[-1], float(epsilon), capi.ptr(G), capi.ptr(S),
+                                               capi.ptr(fl)))
+    S = S[0] if single else S
+    return (S, fl) if return_flags else S
+
+
+def GSLQrDecomposition(A: np.ndarray, device: int = 0) -> np.ndarray:
+    """CSLAM::GSLQrDecomposition (SLAM.cpp:2330-2353) on the GPU: A [nb, m, n] or [m, n] (m >= n) -> triu(R)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    single = A.ndim == 2
+    A = A.reshape(-1, A.shape[-2], A.shape[-1])
+    R = np.empty((A.shape[0], A.shape[2], A.shape[2]))
+    capi.check(capi.load_library().srukf_qr_R(device, A.shape[0], A.shape[1], A.shape[2], capi.ptr(A), capi.ptr(R)))
+    return R[0] if single else R
+
+
+def generateSigmaPoints(mu: np.ndarray, sr: np.ndarray, gamma: float, device: int = 0) -> np.ndarray:
+    """CSLAM::generateSigmaPoints (SLAM.cpp:1148-1162) on the GPU: mu [nb, Na] or [Na], sr [nb, Na, Na] -> sigma
+    [nb, Na, 2Na+1]."""
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    single = mu.ndim == 1
+    mu = mu.reshape(-1, mu.shape[-1])
+    Na = mu.shape[1]
+    sr = np.ascontiguousarray(sr, dtype=np.float64).reshape(mu.shape[0], Na, Na)
+    out = np.empty((mu.shape[0], Na, 2 * Na + 1))
+    capi.check(capi.load_library().srukf_generate_sigma_points(device, mu.shape[0], Na, float(gamma), capi.ptr(mu),
+                                                               capi.ptr(sr), capi.ptr(out)))
+    return out[0] if single else out
+
+
+def fp64_peak_tflops(device: int = 0) -> float:
+    v = C.c_double()
+    capi.check(capi.load_library().srukf_fp64_peak(device, C.byref(v)))
+    return v.value

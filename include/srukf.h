@@ -119,6 +119,39 @@ int srukf_kalman_update(srukf_t *h, const double *z, const uint8_t *matched);
 /* predictMotion + predictMeasurement + KalmanUpdate of one CSLAM::SLAM() frame (SLAM.cpp:91,93,99). */
 int srukf_step(srukf_t *h, const double *u, const double *z, const uint8_t *matched);
 
+/* Read-back of m_X_k that overlaps the next frame: x_host [B][n] (pinned memory for a truly asynchronous copy) is
+ * filled from a device-side snapshot taken in stream order after everything queued so far; it is complete after
+ * srukf_sync().  srukf_step itself copies its inputs on a second stream into alternating device buffers, so the inputs
+ * of frame s+1 travel while frame s computes; u / z / matched must stay unmodified until the next srukf_sync() or the
+ * second-next srukf_step() of the handle. */
+int srukf_get_x_async(srukf_t *h, double *x_host);
+
+/* ---- CSLAM helper methods as stand-alone entry points (the facade include/SLAM.h binds them) ---- */
+#define SRUKF_UPDATING 0          /* FLAG_4_UPDATING,        SLAM.cpp:31 */
+#define SRUKF_DOWNDATING 1        /* FLAG_4_DOWNDATING,      SLAM.cpp:32 */
+#define SRUKF_NEED_REORDER 0      /* FLAG_4_NEED_REORDER,    SLAM.cpp:36 */
+#define SRUKF_NEEDNOT_REORDER 1   /* FLAG_4_NEEDNOT_REORDER, SLAM.cpp:37 */
+/* CSLAM::modifiedCholeskyDecomposition(Mat &sr, const Mat &Cov) (SLAM.h:355, SLAM.cpp:2197-2327) for nb matrices:
+ * G [nb][n][n] dense row-major (lower triangle factorised, maxima over the whole matrix) -> S [nb][n][n] upper
+ * triangular, S = sqrt(D) L^T; flags [nb] (SRUKF_FLAG_GMW_* / NAN) or NULL. */
+int srukf_mchol(int device, int nb, int n, double epsilon, const double *G, double *S, uint32_t *flags);
+/* CSLAM::GSLQrDecomposition(Mat &R, const Mat &A) const (SLAM.h:348, SLAM.cpp:2330-2353): triu(R) of the Householder
+ * QR in GSL's sign convention; A [nb][m][n] (m >= n), R [nb][n][n]. */
+int srukf_qr_R(int device, int nb, int m, int n, const double *A, double *R);
+/* CSLAM::generateSigmaPoints(Mat &sigma, const Mat &mu, const Mat &sr) (SLAM.h:341, SLAM.cpp:1148-1162):
+ * mu [nb][Na], sr [nb][Na][Na] (rows are the directions) -> sigma [nb][Na][2Na+1].  The step kernels never materialise
+ * this matrix; the entry exists for callers of the reference helper. */
+int srukf_generate_sigma_points(int device, int nb, int Na, double gamma, const double *mu, const double *sr,
+                                double *sigma);
+/* CSLAM::GSLCholeskyUpdate(const Mat &u, const int &flag4UpOrDown, const int &flag4Order) (SLAM.h:347,
+ * SLAM.cpp:2106-2155) on the handle's m_S_k: U [B][n][k] (u is dim x k), applied column by column in reference order:
+ * S <- modifiedCholesky(S^T S +- u u^T); with SRUKF_NEED_REORDER the last n_new features are the ones added on the
+ * previous frame (:2122-2138; n_new is ignored otherwise).  Synchronous. */
+int srukf_cholesky_update(srukf_t *h, const double *U, int k, int up_or_down, int order, int n_new);
+/* Diagnostics: FP64 tensor-pipe throughput (back-to-back DMMA m8n8k4) of `device` in TFLOP/s, measured now (bench.py's
+ * roofline denominator, taken in the same process and clock state as the timed run). */
+int srukf_fp64_peak(int device, double *tflops);
+
 /* device-pointer variants (inputs already resident in HBM; asynchronous on the handle's stream).  The handle's stream is
  * non-blocking: it is NOT ordered after the caller's streams, so the buffers must be complete (synchronise or wait on an
  * event of the stream that produced them) before the call, and must stay valid until srukf_sync(). */

@@ -1,5 +1,5 @@
 """The header-only C++ facade (include/SLAM.h, the reference's CSLAM method names) builds against the C ABI;
-on a GPU box it must reproduce the Python/ctypes path bit for bit, without a GPU it must fail loudly."""
+on a GPU box it must reproduce the CPU oracle (frames and helper methods), without a GPU it must fail loudly."""
 import os
 import struct
 import subprocess
@@ -22,13 +22,25 @@ def build_facade(tmp_path, built_lib):
     return exe
 
 
+def helper_inputs(n, seed=5):
+    rng = np.random.default_rng(seed)
+    M = rng.standard_normal((n, n))
+    G = M @ M.T + 0.5 * np.eye(n)
+    A = rng.standard_normal((2 * n, n))
+    return G, A
+
+
 def write_scenario(path, sc):
+    n = 6 * sc.L + 4
+    G, A = helper_inputs(n)
     with open(path, "wb") as f:
         f.write(struct.pack("ii", sc.L, sc.steps))
         f.write(np.ascontiguousarray(sc.x0[0]).tobytes())
         f.write(np.ascontiguousarray(sc.S0[0]).tobytes())
         f.write(np.ascontiguousarray(sc.u[:, 0]).tobytes())
         f.write(np.ascontiguousarray(sc.z[:, 0]).tobytes())
+        f.write(np.ascontiguousarray(G).tobytes())
+        f.write(np.ascontiguousarray(A).tobytes())
 
 
 def test_facade_compiles_and_refuses_to_run_without_gpu(tmp_path, built_lib):
@@ -44,23 +56,54 @@ def test_facade_compiles_and_refuses_to_run_without_gpu(tmp_path, built_lib):
 
 
 @pytest.mark.gpu
-def test_facade_matches_ctypes_path(tmp_path, built_lib):
-    from cv_monoslam_b200 import CSLAMBatch
+def test_facade_matches_the_oracle(tmp_path, built_lib, oracle):
+    """The C++ facade (reference method names, data through members) against the CPU oracle: whole frames through the
+    no-argument SLAM() (chi-square gate of dataAssociation decides the matches) and through a caller-supplied
+    association, then the helper methods modifiedCholeskyDecomposition / GSLQrDecomposition / generateSigmaPoints /
+    GSLCholeskyUpdate."""
+    from conftest import relmax
     exe = build_facade(tmp_path, built_lib)
     L, steps = 6, 4
+    n = 6 * L + 4
     sc = synth.make_scenario(L, 1, steps)
     write_scenario(tmp_path / "sc.bin", sc)
-    out = subprocess.run([exe, str(tmp_path / "sc.bin")], capture_output=True, text=True)
+    out = subprocess.run([exe, str(tmp_path / "sc.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     vals = [float(v) for v in out.stdout.split()]
-    g = CSLAMBatch(1, L)
-    g.set_state(sc.x0, sc.S0)
+    raw = np.fromfile(tmp_path / "out.bin")
+    sizes = [n, n * n, 1, n * n, n * n, n * (2 * n + 1), n * n]
+    assert raw.size == sum(sizes)
+    xf, Sf, tr, srf, Rf, sigf, S2f = np.split(raw, np.cumsum(sizes)[:-1])
+    Sf, srf, Rf, S2f = (a.reshape(n, n) for a in (Sf, srf, Rf, S2f))
+    # ---- frames: the oracle with the same association rule (gate on even frames, "all visible" on odd ones)
+    f = oracle.Filter(L, oracle.default_params(downdate_mode=0))
+    f.set_state(sc.x0[0], sc.S0[0])
+    nm = 0
     for s in range(steps):
-        g.predictMotion(sc.u[s])
-        g.predictMeasurement()
-        g.KalmanUpdate(sc.z[s], sc.matched[s])
-    x, S = g.get_state()
-    n = 6 * L + 4
-    assert np.array_equal(np.array(vals[:4]), x[0, n - 4:])
-    assert vals[4] == pytest.approx(np.trace(S[0].T @ S[0]), rel=1e-13)
-    assert int(vals[5]) == L and int(vals[6]) == L
+        f.predict_motion(sc.u[s, 0])
+        f.predict_measurement()
+        _, _, vis = f.prediction()
+        m = f.chi2_gate(sc.z[s, 0])[0] if s % 2 == 0 else vis
+        nm = int(m.sum())
+        f.kalman_update(sc.z[s, 0], m)
+    xo, So = f.get_state()
+    assert relmax(xf, xo) < 1e-9 and relmax(Sf.T @ Sf, So.T @ So) < 1e-9
+    assert np.array_equal(np.array(vals[:4]), xf[n - 4:])
+    assert vals[4] == pytest.approx(np.trace(So.T @ So), rel=1e-9)
+    assert int(vals[5]) == nm and int(vals[6]) == L
+    # ---- helpers
+    G, A = helper_inputs(n)
+    So_m, _, _ = oracle.mchol(G)
+    assert relmax(srf, So_m) < 1e-11
+    assert relmax(Rf, oracle.qr_R(A)) < 1e-11
+    gam = oracle.sample_parameters(n)["gamma"]
+    sig = np.empty((n, 2 * n + 1))
+    sig[:, 0] = xf
+    for i in range(n):
+        sig[:, 1 + i] = xf * 1 + Sf[i] * gam + 0
+        sig[:, 1 + n + i] = xf * 1 + Sf[i] * ((-1) * gam) + 0
+    assert np.array_equal(sigf.reshape(n, 2 * n + 1), sig)
+    S2 = Sf.copy()
+    for u in (0.25 * Sf[0], 0.25 * Sf[n - 4]):       # SLAM.cpp:2116-2153, NEEDNOT_REORDER / DOWNDATING
+        S2, _, _ = oracle.mchol(S2.T @ S2 - np.outer(u, u))
+    assert relmax(S2f.T @ S2f, S2.T @ S2) < 1e-10

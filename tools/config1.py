@@ -38,6 +38,9 @@ def main():
     ap.add_argument("--landmarks", type=int, default=20)
     ap.add_argument("--mode", type=int, default=2, help="oracle downdate_mode: 2 = dense S^T S as cv::Mat does (timing), 0 = triangular-aware")
     ap.add_argument("--gpu", action="store_true")
+    ap.add_argument("--reference", type=int, default=0, metavar="N",
+                    help="also run the first N frames through the reference's own code (oracle/_ref) on one core: "
+                         "its seconds per frame and whether its trajectory equals the oracle's bit for bit")
     args = ap.parse_args()
     import oracle as O
     import synth
@@ -76,6 +79,31 @@ def main():
         "finite": bool(np.isfinite(xs).all()),
         "host_cpu_count": os.cpu_count(),
     }
+    if args.reference:
+        import ref as R
+        if R.available():
+            r = R.Slam()
+            r.set_state(sc.x0[0], sc.S0[0])
+            f2 = O.Filter(L, O.default_params(downdate_mode=0))
+            f2.set_state(sc.x0[0], sc.S0[0])
+            t_ref, same = 0.0, True
+            N = min(args.reference, K)
+            for s in range(N):
+                t0 = time.perf_counter()
+                u, _ = r.predict_motion_odometry(*R.control_to_odometry(sc.u[s, 0]))
+                r.predict_measurement()
+                r.kalman_update(sc.z[s, 0], sc.matched[s, 0])
+                t_ref += time.perf_counter() - t0
+                f2.step(u, sc.z[s, 0], sc.matched[s, 0])
+                xr, Sr = r.get_state()
+                xo, So = f2.get_state()
+                same = same and np.array_equal(xr, xo) and np.array_equal(Sr, So)
+            rec["reference_frames"] = N
+            rec["reference_s_per_step"] = t_ref / N
+            rec["reference_equals_oracle_bitwise"] = bool(same)
+            rec["reference_kind"] = "SLAM.cpp bodies extracted verbatim (oracle/_ref), cv::Mat stand-in, g++ -O2, 1 core"
+        else:
+            rec["reference_frames"] = 0
     if args.gpu:
         from cv_monoslam_b200 import CSLAMBatch
         g = CSLAMBatch(1, L)

@@ -1,0 +1,19 @@
+#!/bin/bash
+# Standard GPU battery (run under gpurun): tests, bench (both arms), config 1, ncu launch list + full captures.
+# usage: tools/gpu_battery.sh <tag> [tests] [bench] [ref] [config1] [ncu]
+tag=$1; shift
+what="$*"; [ -z "$what" ] && what="tests bench ref config1 ncu"
+mkdir -p gpurun_out
+for w in $what; do
+  case $w in
+    tests)   ( time python -m pytest tests -m gpu -x -q ) > gpurun_out/${tag}_gputests.log 2>&1; tail -5 gpurun_out/${tag}_gputests.log ;;
+    bench)   python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"; cat gpurun_out/${tag}_bench.json ;;
+    ref)     python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err; echo "ref rc=$?"; cat gpurun_out/${tag}_bench_reference.json ;;
+    config1) python tools/config1.py --steps 1000 --gpu --reference 1000 > gpurun_out/${tag}_config1.json 2> gpurun_out/${tag}_config1.err; echo "config1 rc=$?"; cat gpurun_out/${tag}_config1.json ;;
+    ncu)     ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
+             for k in k_update k_gain k_predict; do
+               ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -o gpurun_out/${tag}_$k -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_$k.log 2>&1
+             done; ls -la gpurun_out/${tag}_*.ncu-rep ;;
+    smoke)   python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ;;
+  esac
+done

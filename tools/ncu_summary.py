@@ -26,5 +26,38 @@ def main(path):
                 except ValueError:
                     continue
                 if v > 0.15: print(f'  stall {k.split("issue_stalled_")[1].split("_per_issue")[0]:40s} {v:8.2f}')
+def traffic_json(out_path, landmarks, reps):
+    """profiles/*_traffic.json for bench.py's roofline.traffic: DRAM bytes per filter of each kernel in the captures
+    (one CTA per filter: per-launch bytes / grid size)."""
+    import json
+    kernels = {}
+    for path in reps:
+        out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        H, U = rows[0], rows[1]
+        for R in rows[2:]:
+            d = dict(zip(H, R))
+            import re
+            mm = re.search(r'(k_\w+)', d.get('Kernel Name', ''))
+            name = mm.group(1) if mm else d.get('Kernel Name', '')
+            def val(k):
+                v = float(d[k].replace(',', ''))
+                u = U[H.index(k)].lower()
+                return v * {'byte': 1.0, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}.get(u, 1.0)
+            grid = int(d.get('launch__grid_size', '0').replace(',', '') or 0)
+            if not grid:
+                continue
+            tot = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
+            kernels[name] = {'dram_bytes_per_launch': tot, 'filters_per_launch': grid,
+                             'dram_bytes_per_filter': tot / grid, 'capture': path.split('/')[-1]}
+    with open(out_path, 'w') as f:
+        json.dump({'landmarks': landmarks, 'source': 'ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum',
+                   'kernels': kernels}, f, indent=1)
+    print(json.dumps(kernels, indent=1))
+
+
 if __name__ == '__main__':
-    for p in sys.argv[1:]: main(p)
+    if len(sys.argv) > 1 and sys.argv[1] == '--traffic-json':
+        traffic_json(sys.argv[2], int(sys.argv[3]), sys.argv[4:])
+    else:
+        for p in sys.argv[1:]: main(p)

@@ -41,7 +41,7 @@ def run(L, B, steps=3, warmup=3):
     rate = B / (ms * 1e-3)
     fl = g.flags()
     out = dict(L=L, n=n, sigma_points=2 * (n + 5) + 1, filters=B, ms_per_step=ms, filter_steps_per_s=rate,
-               mflop_per_step=w / 1e6, frac_fp64_peak=rate * w / (bench.FP64_PEAK_TFLOPS * 1e12),
+               mflop_per_step=w / 1e6, frac_fp64_peak=rate * w / (bench.FP64_PEAK_FALLBACK_TFLOPS * 1e12),
                flag_or=int(np.bitwise_or.reduce(fl)), n_fallback=int((fl & 32 != 0).sum()),
                finite=bool(np.isfinite(g.get_x()).all()))
     g.close()
