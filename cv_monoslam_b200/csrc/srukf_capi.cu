@@ -206,6 +206,19 @@ static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
   d.img_w = s.image_width; d.img_h = s.image_height;
   d.a1 = s.a1; d.a2 = s.a2; d.a3 = s.a3; d.a4 = s.a4; d.sigma_measure = s.sigma_measure;
   d.epsilon = s.epsilon; d.newton_iters = s.newton_iters;
+  {
+    // distortion fast paths (srukf_device.cuh distort_point): largest |k1| ru^2 over the image (the corners; a pixel
+    // zeroed by the view test is the corner (0, 0))
+    double r2max = 0.0;
+    for (int cx = 0; cx < 2; ++cx)
+      for (int cy = 0; cy < 2; ++cy) {
+        const double xu = (cx * (double)s.image_width - s.cam_cx) * s.cam_dx, yu = (cy * (double)s.image_height - s.cam_cy) * s.cam_dy;
+        r2max = std::fmax(r2max, xu * xu + yu * yu);
+      }
+    d.dist_inward = (s.cam_k1 >= 0.0 && s.cam_k2 >= 0.0) ? 1 : 0;
+    d.dist_series = (s.cam_k2 == 0.0 && d.dist_inward && s.cam_k1 * r2max <= 2.5e-4 && s.newton_iters >= 6) ? 1 : 0;
+    if (getenv("SRUKF_NO_DIST_FASTPATH")) { d.dist_series = 0; d.dist_inward = 0; }
+  }
   { const char* e_ = getenv("SRUKF_DBG_SKIP_MMA"); d.dbg_skip_mma = e_ ? atoi(e_) : 0; }  // bit 0: skip DMMAs, bit 1: skip k_gain's loads
   double wm0, wc0, wi, wi_sr, gamma;
   sample_weights(s, d.Na, wm0, wc0, wi, wi_sr, gamma);

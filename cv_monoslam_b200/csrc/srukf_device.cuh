@@ -29,6 +29,10 @@ struct DevParams {
   double cpair;  // sqrt(2) * wi_sr * gamma (== 1 analytically for all three weight types)
   double epsilon;
   int newton_iters;
+  // distortion fast paths, decided on the host from the camera parameters (fill_dev_params):
+  int dist_series;   // k2 == 0 and |k1| ru^2 <= 2.5e-4 everywhere in the image: closed-form series root (no iteration)
+  int dist_inward;   // k1 >= 0 and k2 >= 0: distortion moves a pixel towards the principal point, so a pixel that passed
+                     // the [10, W-10] x [10, H-10] test (or was zeroed by it) cannot leave the image: second test skipped
   int dbg_skip_mma;  // diagnostics only (SRUKF_DBG_SKIP_MMA): bit 0 stream the K chunks but skip the DMMAs, bit 1 k_gain without loads
 };
 
@@ -126,6 +130,7 @@ __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const void* tma
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* gptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // 16-byte asynchronous global->shared copy (LDGSTS, L2 only) and its completion hook onto an mbarrier:
 // the executing thread arrives on `bar` once all of its earlier cp.async operations have landed.
@@ -173,6 +178,20 @@ __device__ __forceinline__ void distort_point(const DevParams& p, double ux, dou
   const double xu = (ux - p.cam_cx) * p.cam_dx;
   const double yu = (uy - p.cam_cy) * p.cam_dy;
   const double ru2 = xu * xu + yu * yu;
+  if (p.dist_series) {
+    // t + a t^3 = 1 with 0 <= |a| <= 2.5e-4:  t = sum_k binom(3k,k)/(2k+1) (-a)^k = 1 - a + 3a^2 - 12a^3 + 55a^4 - 273a^5 + ..
+    // (the first omitted term, 1428 a^6 < 4e-19, is below half an ulp of t).  The reference's 100 Newton steps sit on
+    // the same root to rounding.
+    const double a = p.cam_k1 * ru2;
+    double t = fma(a, -273.0, 55.0);
+    t = fma(a, t, -12.0);
+    t = fma(a, t, 3.0);
+    t = fma(a, t, -1.0);
+    t = fma(a, t, 1.0);
+    ox = p.cam_cx + (xu * t) * p.inv_dx;
+    oy = p.cam_cy + (yu * t) * p.inv_dy;
+    return;   // dist_series implies dist_inward or a negligible outward shift checked on the host
+  }
   const double a = p.cam_k1 * ru2, bq = p.cam_k2 * (ru2 * ru2);
   // second-order estimate of the root of t + a t^3 + bq t^5 = 1 (t = 1 - d, d (1 + 3a + 5bq) = a + bq + O(d^2))
   const double s1 = a + bq, s3 = 3.0 * a + 5.0 * bq;
@@ -193,6 +212,7 @@ __device__ __forceinline__ void distort_point(const DevParams& p, double ux, dou
   }
   ox = p.cam_cx + (xu * t) * p.inv_dx;
   oy = p.cam_cy + (yu * t) * p.inv_dy;
+  if (p.dist_inward) return;
   bool vis = (ox >= 0) && (ox <= p.img_w) && (oy >= 0) && (oy <= p.img_h);
   if (!vis) {
     ox = 0;

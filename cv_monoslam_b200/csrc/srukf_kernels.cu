@@ -105,16 +105,15 @@ __device__ void householder4(double* T, int rows, double* red) {
 //           robot rows of calculateOneFeatureCrossCovariance :2020-2038.
 // -------------------------------------------------------------------------------------------------
 template <bool MOTION, bool MEAS>
-__global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int save_rsig) {
+__global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int save_rsig) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   const int b = q.chunk0 + blockIdx.x;
   const int n = p.n, nf = p.nf, Na = p.Na, P = p.P, L = p.L;
   double* xs = sm;                 // n
   double* rs = xs + n;             // P x 8 : rx ry rz rtheta c/det s/det det/det -
-  double* z0 = rs + (size_t)P * 8; // 2L
-  double* red = z0 + 2 * L;        // 40
-  double* work = red + 40;         // max((n+10)*4, slots*13)
+  double* red = rs + (size_t)P * 8; // 40
+  double* work = red + 40;          // (n+10)*4 + nf*4 (motion step only)
   double* xg = q.x + (size_t)b * n;
   double* Sg = q.S + (size_t)b * p.nbp;
   const int np = p.np;
@@ -248,15 +247,33 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
 
   if (MEAS) {
     const double gsm = p.gamma * p.sigma_measure;  // Qt = I2*sigma_measure enters as a sqrt block (:1462)
-    // per slot (g, j): feature j's mean direction and world point (State2World :3250-3276), sigma point 0,
-    // then the sigma pairs k = g, g+G, ..  For pairs that do not touch feature j's own six entries
-    // (k > 6j+5: S is upper triangular) only the robot pose moves and the world point is reused.
-    const int G = (L <= NT) ? NT / L : 1;
-    double* acc = work;  // [G*L][13]
+    // Work split: features in blocks of bw = 8 (tail blocks 4 / 2 / 1); inside a warp lane = (jl = lane % bw, g = lane / bw),
+    // i.e. bw neighbouring features x 32/bw sigma-pair groups, and the 8 warps take different pair groups:
+    //   pair k = warp * (32/bw) + g, then += 8 * (32/bw).
+    // - lanes with the same k cover neighbouring features: S(k, 6j..) loads and the dZ(k, 2j..) stores are contiguous
+    //   128..384-byte pieces;
+    // - the branch "pair k perturbs feature j's own entries" (k <= 6j+5, S is upper triangular) differs inside a warp
+    //   only while k sweeps the 6*bw columns of its feature block (for the other pairs only the robot pose moves and
+    //   the world point of State2World :3250-3276 is reused); both sides end in the same projection code;
+    // - every warp sees the same mix of pairs, so the block barriers below find the warps together.
     const int Lc = p.Lc;
     double* dZ = q.dZ + (size_t)blockIdx.x * np * Lc;
-    for (int slot = tid; slot < G * L; slot += NT) {
-      const int g = slot / L, j = slot - g * L;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NWP = NT / 32;
+    double* part = work;   // [NWP][8][13] per-warp partial sums of the current feature block
+    const double W1 = 2.0 * Na * p.wi;
+    const double cab = W1 + p.wc0 - 2.0;  // coefficient of abar*bbar^T (== -1 when wc0 == wm0)
+    double* hb = q.hbar + (size_t)b * 2 * L;
+    double* sig = q.si + (size_t)b * 4 * L;
+    double* csh = q.cshift + (size_t)b * 2 * L;
+    double* pr = q.pxyr + (size_t)b * 8 * L;
+    uint8_t* vis = q.visible + (size_t)b * L;
+    for (int j0 = 0; j0 < L;) {
+      const int rem = L - j0;
+      const int lb = (rem >= 8) ? 3 : ((rem >= 4) ? 2 : ((rem >= 2) ? 1 : 0));
+      const int bw = 1 << lb, gl = 32 >> lb;
+      const int jl = lane & (bw - 1), g = lane >> lb;
+      const int j = j0 + jl;
       const double* f = xs + 6 * j;
       double sth0, cth0, sph0, cph0;
       sincos(f[3], &sth0, &cth0);
@@ -265,95 +282,111 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
       const double pwx = f[0] + ir0 * cph0 * sth0, pwy = f[1] - ir0 * sph0, pwz = f[2] + ir0 * cph0 * cth0;
       double zx0, zy0;
       pixel_from_ray(p, pwx - rs[0], pwy - rs[1], pwz - rs[2], rs[4], rs[5], rs[6], 0.0, 0.0, zx0, zy0, flags);
-      if (g == 0) { z0[2 * j] = zx0; z0[2 * j + 1] = zy0; }
-      double sb0 = 0, sb1 = 0, s00 = 0, s01 = 0, s11 = 0;
-      double sa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int k = g; k < Na; k += G) {
+      const int kown = 6 * j + 5;            // last pair that touches the feature's own entries (always < nf)
+      const int kstep = NWP * gl;
+      double t[13];
+#pragma unroll
+      for (int c = 0; c < 13; ++c) t[c] = 0.0;
+      // S(k, 6j..6j+5) of the NEXT own iteration is fetched one iteration ahead: the load latency hides behind the
+      // ~250 FP64 instructions of an iteration instead of stalling its first use
+      double snx[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) snx[c] = 0.0;
+      const int kfirst = warp * gl + g;
+      if (kfirst <= kown) {
+        const double* srow = Sg + (size_t)kfirst * np + 6 * j;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) snx[c] = (6 * j + c >= kfirst) ? srow[c] : 0.0;   // columns < k hold the carried covariance
+      }
+      for (int k = kfirst; k < Na; k += kstep) {
         const double e0 = (k == n + 3) ? gsm : 0.0, e1 = (k == n + 4) ? gsm : 0.0;
         const double* rp = rs + (size_t)(k + 1) * 8;
         const double* rm = rs + (size_t)(Na + k + 1) * 8;
-        double px, py, mx, my;
-        if (k <= 6 * j + 5) {   // (k < nf is implied) feature j's own entries are perturbed by +-gamma*S(k, 6j..6j+5)
-          const double* srow = Sg + (size_t)k * np + 6 * j;  // S is upper triangular: columns < k are zero
+        double hxp, hyp, hzp, hxm, hym, hzm;
+        if (k <= kown) {   // feature j's own entries are perturbed by +-gamma*S(k, 6j..6j+5)
           double dlt[6];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) dlt[c] = (6 * j + c >= k) ? srow[c] * p.gamma : 0.0;
+          for (int c = 0; c < 6; ++c) dlt[c] = snx[c] * p.gamma;
+          const int kn = k + kstep;
+          if (kn <= kown) {
+            const double* srow = Sg + (size_t)kn * np + 6 * j;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) snx[c] = (6 * j + c >= kn) ? srow[c] : 0.0;
+          }
           double stp, ctp, stm, ctm, spp, cpp, spm, cpm;
           sincos_pm(f[3], sth0, cth0, dlt[3], stp, ctp, stm, ctm);
           sincos_pm(f[4], sph0, cph0, dlt[4], spp, cpp, spm, cpm);
           const double irp = fast_rcp(f[5] * 1 + dlt[5]), irm = fast_rcp(f[5] * 1 - dlt[5]);
-          pixel_from_ray(p, (f[0] * 1 + dlt[0]) + irp * cpp * stp - rp[0], (f[1] * 1 + dlt[1]) - irp * spp - rp[1],
-                         (f[2] * 1 + dlt[2]) + irp * cpp * ctp - rp[2], rp[4], rp[5], rp[6], e0, e1, px, py, flags);
-          pixel_from_ray(p, (f[0] * 1 - dlt[0]) + irm * cpm * stm - rm[0], (f[1] * 1 - dlt[1]) - irm * spm - rm[1],
-                         (f[2] * 1 - dlt[2]) + irm * cpm * ctm - rm[2], rm[4], rm[5], rm[6], -e0, -e1, mx, my, flags);
+          hxp = (f[0] * 1 + dlt[0]) + irp * cpp * stp - rp[0];
+          hyp = (f[1] * 1 + dlt[1]) - irp * spp - rp[1];
+          hzp = (f[2] * 1 + dlt[2]) + irp * cpp * ctp - rp[2];
+          hxm = (f[0] * 1 - dlt[0]) + irm * cpm * stm - rm[0];
+          hym = (f[1] * 1 - dlt[1]) - irm * spm - rm[1];
+          hzm = (f[2] * 1 - dlt[2]) + irm * cpm * ctm - rm[2];
         } else {
-          pixel_from_ray(p, pwx - rp[0], pwy - rp[1], pwz - rp[2], rp[4], rp[5], rp[6], e0, e1, px, py, flags);
-          pixel_from_ray(p, pwx - rm[0], pwy - rm[1], pwz - rm[2], rm[4], rm[5], rm[6], -e0, -e1, mx, my, flags);
+          hxp = pwx - rp[0]; hyp = pwy - rp[1]; hzp = pwz - rp[2];
+          hxm = pwx - rm[0]; hym = pwy - rm[1]; hzm = pwz - rm[2];
         }
-        if (k < nf) {
-          dZ[(size_t)k * Lc + 2 * j] = px - mx;
-          dZ[(size_t)k * Lc + 2 * j + 1] = py - my;
-        }
-        double bpx = px - zx0, bpy = py - zy0, bmx = mx - zx0, bmy = my - zy0;
-        sb0 += bpx + bmx;
-        sb1 += bpy + bmy;
-        s00 += bpx * bpx + bmx * bmx;
-        s01 += bpx * bpy + bmx * bmy;
-        s11 += bpy * bpy + bmy * bmy;
+        double px, py, mx, my;
+        pixel_from_ray(p, hxp, hyp, hzp, rp[4], rp[5], rp[6], e0, e1, px, py, flags);
+        pixel_from_ray(p, hxm, hym, hzm, rm[4], rm[5], rm[6], -e0, -e1, mx, my, flags);
+        if (k < nf) *reinterpret_cast<double2*>(dZ + (size_t)k * Lc + 2 * j) = make_double2(px - mx, py - my);
+        const double bpx = px - zx0, bpy = py - zy0, bmx = mx - zx0, bmy = my - zy0;
+        t[0] += bpx + bmx;
+        t[1] += bpy + bmy;
+        t[2] += bpx * bpx + bmx * bmx;
+        t[3] += bpx * bpy + bmx * bmy;
+        t[4] += bpy * bpy + bmy * bmy;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          double ap = rp[c] - rs[c], am = rm[c] - rs[c];
-          sa[2 * c] += ap * bpx + am * bmx;
-          sa[2 * c + 1] += ap * bpy + am * bmy;
+          const double ap = rp[c] - rs[c], am = rm[c] - rs[c];
+          t[5 + 2 * c] += ap * bpx + am * bmx;
+          t[6 + 2 * c] += ap * bpy + am * bmy;
         }
       }
-      double* a = acc + (size_t)slot * 13;
-      a[0] = sb0; a[1] = sb1; a[2] = s00; a[3] = s01; a[4] = s11;
+      // sums over the pair groups of this warp (fixed shuffle tree), then over the warps in fixed order
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[5 + c] = sa[c];
-    }
-    __syncthreads();
-    // reduce over g in fixed order; per-feature outputs
-    const double W1 = 2.0 * Na * p.wi;
-    const double cab = W1 + p.wc0 - 2.0;  // coefficient of abar*bbar^T (== -1 when wc0 == wm0)
-    double* hb = q.hbar + (size_t)b * 2 * L;
-    double* sig = q.si + (size_t)b * 4 * L;
-    double* csh = q.cshift + (size_t)b * 2 * L;
-    double* pr = q.pxyr + (size_t)b * 8 * L;
-    uint8_t* vis = q.visible + (size_t)b * L;
-    for (int j = tid; j < L; j += NT) {
-      double t[13];
-#pragma unroll
-      for (int c = 0; c < 13; ++c) t[c] = 0.0;
-      for (int g = 0; g < G; ++g) {
-        const double* a = acc + (size_t)(g * L + j) * 13;
-#pragma unroll
-        for (int c = 0; c < 13; ++c) t[c] += a[c];
+      for (int c = 0; c < 13; ++c) {
+        for (int o = 16; o >= bw; o >>= 1) t[c] += __shfl_xor_sync(0xffffffffu, t[c], o);
       }
-      const double zx0 = z0[2 * j], zy0 = z0[2 * j + 1];
-      const double bb0 = p.wi * t[0], bb1 = p.wi * t[1];
-      const double hx = p.Wsum * zx0 + bb0, hy = p.Wsum * zy0 + bb1;
-      hb[2 * j] = hx;
-      hb[2 * j + 1] = hy;
-      const bool v = (hx != 0.0) && (hy != 0.0);  // :1727
-      vis[j] = v ? 1 : 0;
-      if (!v) flags |= SRUKF_FLAG_INVISIBLE;
-      // si = R of the 2Na x 2 QR (:1771-1775) == Cholesky factor of wi * sum b b^T
-      double g00 = p.wi * t[2], g01 = p.wi * t[3], g11 = p.wi * t[4];
-      double r00 = sqrt(g00);
-      double r01 = (r00 > 0.0) ? g01 / r00 : 0.0;
-      double r11 = sqrt(fmax(g11 - r01 * r01, 0.0));
-      sig[4 * j + 0] = r00; sig[4 * j + 1] = r01; sig[4 * j + 2] = 0.0; sig[4 * j + 3] = r11;
-      // sum_i w_i (z_i - hbar): multiplies the accumulated state shift in :2030
-      csh[2 * j] = (p.wc0 - p.wm0) * (zx0 - hx) + (1.0 - p.Wsum) * hx;
-      csh[2 * j + 1] = (p.wc0 - p.wm0) * (zy0 - hy) + (1.0 - p.Wsum) * hy;
-      // robot rows of Pxy (:2028-2037) about the predicted means
+      if (g == 0) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        double abar = xs[n - 4 + c] - rs[c];  // = wi * sum a_i (+ (Wsum-1) r0, zero analytically)
-        pr[(size_t)c * 2 * L + 2 * j] = p.wi * t[5 + 2 * c] + cab * abar * bb0;
-        pr[(size_t)c * 2 * L + 2 * j + 1] = p.wi * t[6 + 2 * c] + cab * abar * bb1;
+        for (int c = 0; c < 13; ++c) part[(warp * 8 + jl) * 13 + c] = t[c];
       }
+      __syncthreads();
+      if (tid < bw) {   // warp 0, g == 0: this thread's own feature j = j0 + tid, zx0 / zy0 are in its registers
+#pragma unroll
+        for (int c = 0; c < 13; ++c) {
+          double a = 0.0;
+          for (int w = 0; w < NWP; ++w) a += part[(w * 8 + tid) * 13 + c];
+          t[c] = a;
+        }
+        const double bb0 = p.wi * t[0], bb1 = p.wi * t[1];
+        const double hx = p.Wsum * zx0 + bb0, hy = p.Wsum * zy0 + bb1;
+        hb[2 * j] = hx;
+        hb[2 * j + 1] = hy;
+        const bool v = (hx != 0.0) && (hy != 0.0);  // :1727
+        vis[j] = v ? 1 : 0;
+        if (!v) flags |= SRUKF_FLAG_INVISIBLE;
+        // si = R of the 2Na x 2 QR (:1771-1775) == Cholesky factor of wi * sum b b^T
+        const double g00 = p.wi * t[2], g01 = p.wi * t[3], g11 = p.wi * t[4];
+        const double r00 = sqrt(g00);
+        const double r01 = (r00 > 0.0) ? g01 / r00 : 0.0;
+        const double r11 = sqrt(fmax(g11 - r01 * r01, 0.0));
+        sig[4 * j + 0] = r00; sig[4 * j + 1] = r01; sig[4 * j + 2] = 0.0; sig[4 * j + 3] = r11;
+        // sum_i w_i (z_i - hbar): multiplies the accumulated state shift in :2030
+        csh[2 * j] = (p.wc0 - p.wm0) * (zx0 - hx) + (1.0 - p.Wsum) * hx;
+        csh[2 * j + 1] = (p.wc0 - p.wm0) * (zy0 - hy) + (1.0 - p.Wsum) * hy;
+        // robot rows of Pxy (:2028-2037) about the predicted means
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double abar = xs[n - 4 + c] - rs[c];  // = wi * sum a_i (+ (Wsum-1) r0, zero analytically)
+          pr[(size_t)c * 2 * L + 2 * j] = p.wi * t[5 + 2 * c] + cab * abar * bb0;
+          pr[(size_t)c * 2 * L + 2 * j + 1] = p.wi * t[6 + 2 * c] + cab * abar * bb1;
+        }
+      }
+      __syncthreads();   // part is reused by the next feature block
+      j0 += bw;
     }
   }
   // flags
@@ -372,6 +405,12 @@ __global__ void __launch_bounds__(NT) k_predict(DevParams p, StepPtrs q, int sav
 //   Measured alternatives (profiles/r01_update_tuning.md): one 1-D bulk copy per row (~130 cycles per copy,
 //   copy-count bound) and cp.async by all warps (~1.2k issue cycles per chunk stolen from the DMMA warps).
 // -------------------------------------------------------------------------------------------------
+#ifndef SRUKF_CANON_WARP
+#define SRUKF_CANON_WARP 0
+#endif
+#ifndef SRUKF_PREFETCH_P
+#define SRUKF_PREFETCH_P 0
+#endif
 constexpr int NB = 32;      // panel width (columns per contraction pass)
 constexpr int KC = 8;       // K rows per pipeline stage at full width
 #ifndef SRUKF_NSTAGE
@@ -559,7 +598,7 @@ __device__ __forceinline__ void mma_chunk_any(double (&acc)[MQ][NTM][2], int qlo
 // Tile shapes: <8 warps, 5 strips, 4 tiles> (32 columns per pass, 2 CTAs/SM) or <16 warps, 3 strips, 7 tiles>
 // (56 columns per pass, 1 CTA/SM: half as many passes over S -- the kernel is bound by streaming S, not by DMMA).
 template <int NW, int MQ, int NTM, int KCG, int NSG>
-__global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_gain(DevParams p, StepPtrs q) {
+__global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : 1) k_gain(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
   constexpr int NBG = 8 * NTM;                       // measurement columns per pass
   constexpr int BPB = (SRUKF_PAD == 4) ? NBG + 4 : ((NBG % 16 == 0) ? NBG + 8 : NBG + 16);  // dZ box width == smem pitch, == 4 mod 8
@@ -791,7 +830,11 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
                                              int nbe, int J0, int n, double eps, uint32_t& flags) {
   constexpr int NTH = NW * 32;
   const int tid = threadIdx.x, lane = tid & 31;
+#if SRUKF_CANON_WARP
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: plain shuffles inside `if (warp == 0)`
+#else
+  const int warp = tid >> 5;   // (the shuffled, "provably uniform" form measured 8 % slower: 75.4 -> 81.6 ms per step)
+#endif
   const int nsub = nbe / 8;
   for (int sb = 0; sb < nsub; ++sb) {
     const int c0 = 8 * sb;
@@ -895,12 +938,16 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
 // the S_old and Ut sources) and compared at the end: on violation, or when a pivot is modified beyond the EPSILON
 // floor, the filter is queued for the reference-order fallback (k_downdate) which recomputes it from S_old.
 // -------------------------------------------------------------------------------------------------
-template <int NW, bool TIMING>
-__global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams p, StepPtrs q) {
+template <int NW, bool TIMING, int MQ = MAXQ>
+__global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2 : 1)) k_update(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31;
+#if SRUKF_CANON_WARP
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+#else
+  const int warp = tid >> 5;
+#endif
   const int b = q.chunk0 + blockIdx.x;
   const int n = p.n, np = p.np, Lc = p.Lc;
   const double* Sold = q.S + (size_t)b * p.nbp;
@@ -928,6 +975,9 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     for (int i = tid; i < np; i += NTH) PdNew[i] = PdOld[i];
     return;
   }
+#if SRUKF_PREFETCH_P
+  for (int idx = tid; idx < 2 * np; idx += NTH) prefetch_l2(Sold + (size_t)(idx >> 1) * np + 16 * (idx & 1));   // panel 0
+#endif
   Ring ring;
   ring_init<NW, UNS>(ring, bars);
   double gmax = -1.0e300, zmax = 0.0, tmax = 0.0;
@@ -953,7 +1003,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     const int rowsB = Lc, rowsC = J0;
     const int cA = 0, cB = (rowsB + rpc - 1) / rpc, cC = (rowsC + rpc - 1) / rpc;
     const int nchunks = cB + cC;
-    double acc[MAXQ][NB / 8][2];
+    double acc[MQ][NB / 8][2];
     // rows of chunk t: first row (within its source) and count
     auto chunk_rows = [&](int t, int& row0) -> int {
       if (t < cA + cB) { row0 = (t - cA) * rpc; return (rowsB - row0 < rpc) ? rowsB - row0 : rpc; }
@@ -984,7 +1034,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
         const int st = ring_wait<UNS>(ring);
         if (TIMING && timing) { long long t1_ = clock64(); tkl[2] += t1_ - tk0; tk0 = t1_; }
         const double* xs_ = Xs + (size_t)st * sdoubles;
-        if (!(p.dbg_skip_mma & 1)) mma_chunk_any<NW, MAXQ, NB / 8, false>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nullptr, nrows / 4, lane, warp);
+        if (!(p.dbg_skip_mma & 1)) mma_chunk_any<NW, MQ, NB / 8, false>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nullptr, nrows / 4, lane, warp);
         if (TIMING && timing) { long long t1_ = clock64(); tkl[3] += t1_ - tk0; tk0 = t1_; }
         ring_release<UNS>(ring);
         if (TIMING && timing) { tkl[4] += clock64() - tk0; tkl[5] += 1; }
@@ -992,7 +1042,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     };
     auto negate = [&]() {
 #pragma unroll
-      for (int qq = 0; qq < MAXQ; ++qq)
+      for (int qq = 0; qq < MQ; ++qq)
 #pragma unroll
         for (int t = 0; t < NB / 8; ++t) { acc[qq][t][0] = -acc[qq][t][0]; acc[qq][t][1] = -acc[qq][t][1]; }
     };
@@ -1007,7 +1057,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     // accumulators start at -P_old(i, J): tiles below the panel's diagonal come straight from the lower triangle
     // of the old buffer, diagonal tiles mix lower entries and Pd, tiles above the diagonal are never used
 #pragma unroll
-    for (int qq = 0; qq < MAXQ; ++qq) {
+    for (int qq = 0; qq < MQ; ++qq) {
       const int rs = warp + NW * qq;
       const int i = J0 + 8 * rs + (lane >> 2);
       const double* prow = Sold + (size_t)i * np;
@@ -1033,7 +1083,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
     // G(i, J) is visible now: store the carried covariance of the new factor, P_new = G (+ E on the diagonal,
     // added after the pivots are known), and track max diag / max off-diag of G for beta^2 (:2204-2205)
 #pragma unroll
-    for (int qq = 0; qq < MAXQ; ++qq) {
+    for (int qq = 0; qq < MQ; ++qq) {
       const int rs = warp + NW * qq;
       if (rs < nstrip) {
         const int i = J0 + 8 * rs + (lane >> 2);
@@ -1058,13 +1108,22 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : 1) k_update(DevParams
         }
       }
     }
+#if SRUKF_PREFETCH_P
+    // the accumulators of the NEXT panel start from P_old(i, J+1): ask L2 for those 256-byte row pieces now, one
+    // contraction and one panel factorisation ahead of their use (the loads stalled ~14 % of the warp samples on DRAM)
+    if (J0 + NB < np) {
+      const int R1 = R - NB;
+      const double* pnext = Sold + (size_t)(J0 + NB) * np + (J0 + NB);
+      for (int idx = tid; idx < 2 * R1; idx += NTH) prefetch_l2(pnext + (size_t)(idx >> 1) * np + 16 * (idx & 1));
+    }
+#endif
     consume(cA + cB, nchunks);  // + S_new^T S_new
     negate();                   // acc = C(i, J)
     SRUKF_TICK(0)
     __syncthreads();            // every warp is done with the ring: reuse it as the panel
     SRUKF_TICK(1)
 #pragma unroll
-    for (int qq = 0; qq < MAXQ; ++qq) {
+    for (int qq = 0; qq < MQ; ++qq) {
       const int rs = warp + NW * qq;
       if (rs < nstrip) {
         const int ri = 8 * rs + (lane >> 2);
@@ -1954,8 +2013,11 @@ __global__ void k_sigma_points(int Na, double gamma, const double* __restrict__ 
   for (int idx = threadIdx.x; idx < Na * P; idx += blockDim.x) {
     const int r = idx / P, c = idx - r * P;
     double v = mub[r];
-    if (c >= 1 && c <= Na) v = mub[r] * 1 + srb[(size_t)(c - 1) * Na + r] * gamma + 0;
-    else if (c > Na) v = mub[r] * 1 + srb[(size_t)(c - 1 - Na) * Na + r] * ((-1) * gamma) + 0;
+    // addWeighted: src1*alpha + src2*beta + gamma with separately rounded products (no FMA contraction), as OpenCV does
+    if (c >= 1 && c <= Na)
+      v = __dadd_rn(__dadd_rn(__dmul_rn(mub[r], 1.0), __dmul_rn(srb[(size_t)(c - 1) * Na + r], gamma)), 0.0);
+    else if (c > Na)
+      v = __dadd_rn(__dadd_rn(__dmul_rn(mub[r], 1.0), __dmul_rn(srb[(size_t)(c - 1 - Na) * Na + r], (-1) * gamma)), 0.0);
     sg[idx] = v;
   }
 }
@@ -2028,14 +2090,22 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
 // -------------------------------------------------------------------------------------------------
 // host-side launchers (called from srukf_capi.cu)
 // -------------------------------------------------------------------------------------------------
-int tile_warps(const DevParams& p) {  // warps per CTA of k_update; 0 = unsupported size
-  if (const char* e = getenv("SRUKF_UPDATE_WARPS")) { if (atoi(e) == 16 && p.np <= 8 * 16 * MAXQ) return 16; }
+// Warps per CTA of k_update (0 = unsupported size).  One CTA per filter, 8 rows x MAXQ strips per warp: small maps get
+// small CTAs (2 or 4 warps), so that an SM holds 8 or 4 filters at a time instead of two mostly idle 8-warp CTAs.
+int tile_warps(const DevParams& p) {
+  if (const char* e = getenv("SRUKF_UPDATE_WARPS")) {
+    const int w = atoi(e);
+    if ((w == 2 || w == 4 || w == 8 || w == 16) && p.np <= 8 * w * MAXQ) return w;
+    if (w == 10 && p.np <= 8 * 10 * 4) return 10;   // 10 warps x 4 strips: 20 warps per SM at L = 50
+  }
+  if (p.np <= 8 * 2 * MAXQ) return 2;
+  if (p.np <= 8 * 4 * MAXQ) return 4;
   if (p.np <= 8 * 8 * MAXQ) return 8;
   if (p.np <= 8 * 16 * MAXQ) return 16;
   return 0;
 }
 // k_gain variant: 0 = <8,5,4> (np <= 320, 2 CTAs/SM), 1 = <16,3,7> (np <= 384, 1 CTA/SM, half the passes),
-// 2 = <16,5,4> (np <= 640)
+// 2 = <16,5,4> (np <= 640), 3 = <2,5,4> (np <= 80, 8 CTAs/SM), 4 = <4,5,4> (np <= 160, 4 CTAs/SM)
 #ifndef SRUKF_GAIN_KC
 #define SRUKF_GAIN_KC 24
 #endif
@@ -2045,6 +2115,8 @@ int tile_warps(const DevParams& p) {  // warps per CTA of k_update; 0 = unsuppor
 constexpr int GKC1 = SRUKF_GAIN_KC, GNS1 = SRUKF_GAIN_NS;   // K rows per chunk / ring depth of the 16-warp, 7-tile variant
 int gain_variant(const DevParams& p) {
   if (const char* e = getenv("SRUKF_GAIN_VARIANT")) return atoi(e);
+  if (p.np <= 8 * 2 * 5) return 3;
+  if (p.np <= 8 * 4 * 5) return 4;
   if (p.np <= 8 * 16 * 3) return 1;
   return 2;
 }
@@ -2053,11 +2125,9 @@ int gain_dz_box(const DevParams& p) {
   return gain_variant(p) == 1 ? 72 : 40;
 }
 size_t predict_smem_bytes(const DevParams& p) {
-  size_t slots = (p.L <= NT) ? (size_t)(NT / p.L) * p.L : (size_t)p.L;
-  size_t work = slots * 13;
-  size_t t4 = (size_t)(p.n + 10) * 4 + (size_t)p.nf * 4;
-  if (t4 > work) work = t4;
-  return sizeof(double) * ((size_t)p.n + (size_t)p.P * 8 + 2 * (size_t)p.L + 40 + work);
+  size_t work = (size_t)(p.n + 10) * 4 + (size_t)p.nf * 4;     // motion step: T and E_f
+  if (work < (size_t)(NT / 32) * 8 * 13) work = (size_t)(NT / 32) * 8 * 13;   // measurement step: per-warp partial sums
+  return sizeof(double) * ((size_t)p.n + (size_t)p.P * 8 + 40 + work);
 }
 size_t gain_smem_bytes(const DevParams& p) {
   const bool v1 = gain_variant(p) == 1;
@@ -2091,7 +2161,9 @@ cudaError_t configure_kernels(const DevParams&) {
 #define SRUKF_SET(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
   SRUKF_SET((k_predict<true, true>)) SRUKF_SET((k_predict<true, false>)) SRUKF_SET((k_predict<false, true>))
   SRUKF_SET((k_gain<8, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<16, 3, 7, GKC1, GNS1>)) SRUKF_SET((k_gain<16, 5, 4, 8, NSTAGE>))
+  SRUKF_SET((k_gain<2, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<4, 5, 4, 8, NSTAGE>))
   SRUKF_SET((k_update<8, false>)) SRUKF_SET((k_update<16, false>)) SRUKF_SET((k_update<8, true>)) SRUKF_SET((k_update<16, true>))
+  SRUKF_SET((k_update<2, false>)) SRUKF_SET((k_update<4, false>)) SRUKF_SET((k_update<10, false, 4>))
   SRUKF_SET(k_downdate) SRUKF_SET(k_init_features) SRUKF_SET(k_add_features) SRUKF_SET(k_delete_feature)
   SRUKF_SET(k_chol_update) SRUKF_SET(k_mchol_batch)
 #undef SRUKF_SET
@@ -2110,17 +2182,26 @@ void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_
   switch (gain_variant(p)) {
     case 0: k_gain<8, 5, 4, 8, NSTAGE><<<nblocks, 256, gain_smem_bytes(p), st>>>(p, q); break;
     case 1: k_gain<16, 3, 7, GKC1, GNS1><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
+    case 3: k_gain<2, 5, 4, 8, NSTAGE><<<nblocks, 64, gain_smem_bytes(p), st>>>(p, q); break;
+    case 4: k_gain<4, 5, 4, 8, NSTAGE><<<nblocks, 128, gain_smem_bytes(p), st>>>(p, q); break;
     default: k_gain<16, 5, 4, 8, NSTAGE><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
   }
 }
 void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
   const bool timing = q.dbg != nullptr;
-  if (tile_warps(p) == 8) {
-    if (timing) k_update<8, true><<<nblocks, 256, update_smem_bytes(p), st>>>(p, q);
-    else k_update<8, false><<<nblocks, 256, update_smem_bytes(p), st>>>(p, q);
-  } else {
-    if (timing) k_update<16, true><<<nblocks, 512, update_smem_bytes(p), st>>>(p, q);
-    else k_update<16, false><<<nblocks, 512, update_smem_bytes(p), st>>>(p, q);
+  const size_t smem = update_smem_bytes(p);
+  switch (tile_warps(p)) {
+    case 2: k_update<2, false><<<nblocks, 64, smem, st>>>(p, q); break;
+    case 4: k_update<4, false><<<nblocks, 128, smem, st>>>(p, q); break;
+    case 10: k_update<10, false, 4><<<nblocks, 320, smem, st>>>(p, q); break;
+    case 8:
+      if (timing) k_update<8, true><<<nblocks, 256, smem, st>>>(p, q);
+      else k_update<8, false><<<nblocks, 256, smem, st>>>(p, q);
+      break;
+    default:
+      if (timing) k_update<16, true><<<nblocks, 512, smem, st>>>(p, q);
+      else k_update<16, false><<<nblocks, 512, smem, st>>>(p, q);
+      break;
   }
 }
 void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, int use_worklist, cudaStream_t st) {
