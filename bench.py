@@ -146,7 +146,9 @@ def config_dict(B: int, L: int, unique: int, world: int, downdate_mode: int) -> 
             "filters_per_gpu": B, "landmarks": L, "state_dim": n, "sigma_points": 2 * (n + 5) + 1,
             "distinct_worlds": int(unique), "parallelism": f"filters sharded over {world} GPU(s)",
             "l2": f"inputs larger than L2: {B * ntri * 8 / 2**30:.1f} GiB of packed S per GPU streamed per step",
-            "downdate_mode": downdate_mode}
+            "downdate_mode": downdate_mode,
+            **({"forced_fallback_ppm": int(os.environ["SRUKF_FORCE_FALLBACK_PPM"])}
+               if os.environ.get("SRUKF_FORCE_FALLBACK_PPM") else {})}
 
 
 def cpu_reference_run(L: int, filters: int, steps: int, warmup: int, threads: int, seed_first: int = 0):
@@ -239,6 +241,116 @@ def run_reference(args, ctx, out):
     out.emit(json.dumps(line))
 
 
+def load_priors(g, sc, B):
+    """upload the distinct worlds' priors and replicate them over the batch on the device"""
+    import torch
+    from cv_monoslam_b200.slam import tri_pack
+    xw = torch.from_numpy(sc.x0).cuda()
+    Sw = torch.from_numpy(tri_pack(sc.S0)).cuda()
+    wof = torch.from_numpy(sc.meta["world_of"]).cuda()
+    slab = 4096
+    for b0 in range(0, B, slab):
+        nb = min(slab, B - b0)
+        idx = wof[b0:b0 + nb]
+        xs, Ss = xw[idx].contiguous(), Sw[idx].contiguous()
+        torch.cuda.current_stream().synchronize()   # the handle's stream is not ordered after torch's gather
+        g.set_state_dev(b0, nb, xs.data_ptr(), Ss.data_ptr())
+
+
+def sweep_point(L, B, steps, warmup, peak, parity_max_L, dev, gentle=False):
+    """BASELINE config 4, one state dimension: device-resident throughput of B filters + a parity spot check."""
+    import torch
+    from cv_monoslam_b200 import CSLAMBatch, capi
+    import synth
+    n = 6 * L + 4
+    # The reference's independent per-feature downdates re-subtract the common robot information L times, so its
+    # stability margin shrinks with L (profiles/r01_sweep_config4.md); `gentle` scales the synthetic control and odometry
+    # noise down for the very large maps so that the run measures the fused path, not the reference-order fallback.
+    noise = synth.Noise(control=(0.003, 0.001, 0.003), odo_sigma=(3e-4, 1.5e-4, 3e-4)) if gentle else synth.Noise()
+    sc = synth.make_scenario(L, B, steps + warmup, unique=4, dense_state=False, noise=noise)
+    g = CSLAMBatch(B, L, device=dev)
+    load_priors(g, sc, B)
+    du, dz, dm = (torch.from_numpy(a).cuda() for a in (sc.u, sc.z, sc.matched))
+    torch.cuda.synchronize()
+    st = torch.cuda.ExternalStream(g.stream(), device=dev)
+    for s in range(warmup):
+        g.SLAM_dev(du[s].data_ptr(), dz[s].data_ptr(), dm[s].data_ptr())
+    g.sync()
+    g.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for s in range(warmup, warmup + steps):
+        g.SLAM_dev(du[s].data_ptr(), dz[s].data_ptr(), dm[s].data_ptr())
+    e1.record(st)
+    g.sync()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    kms, _ = g.kernel_times()
+    g.set_profiling(False)
+    fl = g.flags()
+    finite = bool(np.isfinite(g.get_x()).all())
+    g.close()
+    del du, dz, dm
+    w = flops_downdate(n, L) + flops_gain(n, L) + flops_predict(n, L)
+    rate = B / (ms * 1e-3)
+    # ---- parity spot check on the same worlds: 2 filters x 2 frames against the CPU oracle (up to parity_max_L; the
+    #      oracle's reference-order update costs 2L dense factorisations per frame), beyond that against the library's own
+    #      reference-arithmetic path (downdate_mode 2: unblocked DFMA modified Cholesky in global memory)
+    nchk, fr = 2, 2
+    scp = synth.make_scenario(L, nchk, fr, unique=nchk, noise=noise)
+    gp = CSLAMBatch(nchk, L, device=dev)
+    gp.set_state(scp.x0, scp.S0)
+    for s in range(fr):
+        gp.SLAM(scp.u[s], scp.z[s], scp.matched[s])
+    xg, Sg = gp.get_state()
+    gp.close()
+    if L <= parity_max_L:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O  # checker of the sweep's spot check, not the thing measured
+        x, S = scp.x0.copy(), scp.S0.copy()
+        O.batch_step(O.default_params(downdate_mode=1), x, S, scp.u, scp.z, scp.matched, nchk)
+        against = "cpu oracle (reference order)"
+    else:
+        g2 = CSLAMBatch(nchk, L, capi.default_params(downdate_mode=2), device=dev)
+        g2.set_state(scp.x0, scp.S0)
+        for s in range(fr):
+            g2.SLAM(scp.u[s], scp.z[s], scp.matched[s])
+        x, S = g2.get_state()
+        g2.close()
+        against = "library downdate_mode 2 (unblocked modified Cholesky, DFMA)"
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))   # noqa: E731
+    ex = max(rel(xg[i], x[i]) for i in range(nchk))
+    eP = max(rel(Sg[i].T @ Sg[i], S[i].T @ S[i]) for i in range(nchk))
+    return {"metric": "srukf_filter_steps_per_sec", "value": rate, "unit": "filter-steps/s", "landmarks": L, "state_dim": n,
+            "sigma_points": 2 * (n + 5) + 1, "filters": B, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "noise": "gentle (control and odometry noise / 8)" if gentle else "default",
+            "kernel_ms_per_step": {"k_predict": float(kms[0]) / steps, "k_gain": float(kms[1]) / steps,
+                                   "k_update": float(kms[2]) / steps},
+            "mflop_per_filter_step": w / 1e6, "frac_fp64_peak": rate * w / (peak * 1e12), "peak_tflops": peak,
+            "flag_or": int(np.bitwise_or.reduce(fl)), "n_fallback": int((fl & 32 != 0).sum()), "finite": finite,
+            "parity": {"filters": nchk, "frames": fr, "against": against, "relerr_x": ex, "relerr_P": eP,
+                       "ok": bool(ex <= 1e-9 and eP <= 1e-9)}}
+
+
+def run_sweep(args, out):
+    """--sweep: BASELINE config 4 (state-dimension sweep on one GPU); one JSON line per L."""
+    import torch
+    assert torch.cuda.is_available(), "bench.py --sweep needs a CUDA device (there is no CPU fallback)"
+    from cv_monoslam_b200.slam import fp64_peak_tflops
+    peak = fp64_peak_tflops(0)
+    cfg = []
+    for item in args.sweep.split(","):
+        L = int(item.split(":")[0])
+        n = 6 * L + 4
+        npad = (n + 7) // 8 * 8
+        per = 16.0 * npad * npad          # two np x np squares per filter dominate the footprint (SURVEY 8(d): <= 100 GB)
+        B = int(item.split(":")[1]) if ":" in item else int(min(262144, max(1024, 2 ** int(np.log2(100e9 / per)))))
+        cfg.append((L, B))
+    for L, B in cfg:
+        out.emit(json.dumps(sweep_point(L, B, args.steps, args.warmup, peak, args.sweep_parity_max_l, 0,
+                                        gentle=L > args.sweep_gentle_above)))
+
+
 class StdoutGuard:
     """Everything written to fd 1 while the benchmark runs (e.g. NCCL's version banner, written from C) goes to
     stderr; only the final JSON line reaches stdout."""
@@ -278,11 +390,26 @@ def run(out):
     ap.add_argument("--unique", type=int, default=8, help="distinct synthetic worlds (priors) replicated over the batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--downdate-mode", type=int, default=0)
+    ap.add_argument("--adversarial-frac", type=float, default=0.0,
+                    help="force this share of the filters through the reference-order fallback every step (sets "
+                         "SRUKF_FORCE_FALLBACK_PPM for the library): what the guard costs when it fires")
+    ap.add_argument("--sweep", default=None, metavar="L[:B],...",
+                    help="BASELINE config 4: state-dimension sweep on one GPU, e.g. 10,20,33,50,66,100 (B sized to ~60 GB "
+                         "unless given); prints one JSON line per L with a parity spot check")
+    ap.add_argument("--sweep-gentle-above", type=int, default=100,
+                    help="sweep points with more landmarks than this use the gentler synthetic noise")
+    ap.add_argument("--sweep-parity-max-l", type=int, default=100,
+                    help="largest L whose sweep spot check runs the CPU oracle (beyond: the library's reference-arithmetic path)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.adversarial_frac > 0:
+        os.environ["SRUKF_FORCE_FALLBACK_PPM"] = str(int(round(args.adversarial_frac * 1e6)))
 
     from cv_monoslam_b200 import dist
+    if args.sweep:
+        run_sweep(args, out)
+        return
     if args.impl == "reference":
         ctx = dist.Ctx(int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), 0, None)
         run_reference(args, ctx, out)
@@ -295,8 +422,6 @@ def run(out):
     torch.cuda.set_device(dev)
     from cv_monoslam_b200 import CSLAMBatch, capi
     import synth
-    from cv_monoslam_b200.slam import tri_pack
-
     B, L = args.filters, args.landmarks
     n = 6 * L + 4
     ntri = n * (n + 1) // 2
@@ -306,18 +431,7 @@ def run(out):
     sc = synth.make_scenario(L, B, T, unique=args.unique, first_filter=first, dense_state=False)
 
     g = CSLAMBatch(B, L, capi.default_params(downdate_mode=args.downdate_mode), device=dev)
-    # priors: upload the distinct worlds, replicate on the device
-    xw = torch.from_numpy(sc.x0).cuda()
-    Sw = torch.from_numpy(tri_pack(sc.S0)).cuda()
-    wof = torch.from_numpy(sc.meta["world_of"]).cuda()
-    slab = 4096
-    for b0 in range(0, B, slab):
-        nb = min(slab, B - b0)
-        idx = wof[b0:b0 + nb]
-        xs, Ss = xw[idx].contiguous(), Sw[idx].contiguous()
-        torch.cuda.current_stream().synchronize()   # the handle's stream is not ordered after torch's gather
-        g.set_state_dev(b0, nb, xs.data_ptr(), Ss.data_ptr())
-    del xs, Ss
+    load_priors(g, sc, B)   # priors: upload the distinct worlds, replicate on the device
     stream = torch.cuda.ExternalStream(g.stream(), device=dev)
 
     # ---- pass 1: inputs resident in HBM ----------------------------------------------------------------
@@ -384,6 +498,7 @@ def run(out):
     stats["finite_state"] = bool(np.isfinite(hx_np).all())
     flags = g.flags()
     stats["flag_or"] = int(np.bitwise_or.reduce(flags))
+    stats["n_fallback"] = int(((flags & 32) != 0).sum())   # filters that went through the reference-order fallback at least once
 
     # ---- CPU baseline (rank 0, N == 1 only) ---------------------------------------------------------------
     cpu = None

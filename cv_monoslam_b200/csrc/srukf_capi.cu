@@ -22,6 +22,7 @@ struct StepPtrs {
   const CUtensorMap* tmaps; int sbuf; int tm_dz; int dz_filter0;
   double* Pd; double* Pd2; int carry_p;
   double* G2; int n_new;
+  double* Gp;
   int* nact;
 };
 // tensor-map table layout and box geometry (must match srukf_kernels.cu)
@@ -36,6 +37,7 @@ constexpr int TP = SRUKF_TW + SRUKF_PAD;
 int gain_dz_box(const DevParams& p);
 int gain_variant(const DevParams& p);
 int tile_warps(const DevParams& p);
+int gain_row_ctas(const DevParams& p);
 cudaError_t configure_kernels(const DevParams& p);
 size_t predict_smem_bytes(const DevParams& p);
 size_t gain_smem_bytes(const DevParams& p);
@@ -109,6 +111,7 @@ struct srukf_handle {
   int chunk = 0;           // filters per pipeline pass of srukf_step
   double *dZ = nullptr, *U = nullptr, *G = nullptr;
   double* G2 = nullptr;    // scratch of the NEED_REORDER update (allocated on first use)
+  double* Gp = nullptr;    // carried covariance of the reference-order fallback, one packed matrix per fallback CTA
   int gslots = 0;          // CTAs (and G scratch slots) of the reference-order fallback kernel
   int* worklist = nullptr;
   int* nact = nullptr;     // [chunk] per-filter count of features used by k_gain
@@ -219,6 +222,7 @@ static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
     d.dist_series = (s.cam_k2 == 0.0 && d.dist_inward && s.cam_k1 * r2max <= 2.5e-4 && s.newton_iters >= 6) ? 1 : 0;
     if (getenv("SRUKF_NO_DIST_FASTPATH")) { d.dist_series = 0; d.dist_inward = 0; }
   }
+  { const char* e_ = getenv("SRUKF_FORCE_FALLBACK_PPM"); d.force_fb_ppm = e_ ? atoi(e_) : 0; }
   { const char* e_ = getenv("SRUKF_DBG_SKIP_MMA"); d.dbg_skip_mma = e_ ? atoi(e_) : 0; }  // bit 0: skip DMMAs, bit 1: skip k_gain's loads
   double wm0, wc0, wi, wi_sr, gamma;
   sample_weights(s, d.Na, wm0, wc0, wi, wi_sr, gamma);
@@ -291,7 +295,12 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   if (predict_smem_bytes(p) > 227 * 1024 || tile_warps(p) == 0 || update_smem_bytes(p) > 227 * 1024 ||
       gain_smem_bytes(p) > 227 * 1024) {
     delete h;
-    return fail(SRUKF_EINVAL, "srukf_create: L too large for one CTA (supported: L <= 106)");
+    return fail(SRUKF_EINVAL, "srukf_create: L too large for one CTA per filter (supported: L <= 212, n = 1276)");
+  }
+  if (gain_row_ctas(p) > 1 && p.wc0 != p.wm0) {
+    delete h;
+    return fail(SRUKF_EINVAL, "srukf_create: weight type 1 (FLAG_4_WEIGHT2) is limited to L <= 106: its feature-sequential "
+                              "state shift (SLAM.cpp:2030) needs all rows of U in one CTA");
   }
   if (prm.downdate_mode < 0 || prm.downdate_mode > 2) { delete h; return fail(SRUKF_EINVAL, "srukf_create: downdate_mode must be 0..2"); }
   cudaError_t e;
@@ -339,6 +348,7 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   CUH(cudaMalloc(&h->dZ, sizeof(double) * (size_t)chunk * p.np * p.Lc));
   CUH(cudaMalloc(&h->U, sizeof(double) * (size_t)chunk * p.Lc * p.np));
   CUH(cudaMalloc(&h->G, sizeof(double) * (size_t)h->gslots * p.ntri));
+  if (prm.downdate_mode == 0) CUH(cudaMalloc(&h->Gp, sizeof(double) * (size_t)h->gslots * p.ntri));
   CUH(cudaMalloc(&h->worklist, sizeof(int) * ((size_t)chunk + 1)));
   CUH(cudaMalloc(&h->nact, sizeof(int) * (size_t)chunk));
   CUH(cudaMemsetAsync(h->nact, 0, sizeof(int) * (size_t)chunk, h->stream));
@@ -368,7 +378,7 @@ int srukf_destroy(srukf_t* h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
   for (cudaEvent_t e : {h->ev_in[0], h->ev_in[1], h->ev_done[0], h->ev_done[1], h->ev_xs, h->ev_xd}) if (e) cudaEventDestroy(e);
-  void* ptrs[] = {h->u_in[1], h->z_in[1], h->m_in[1], h->x_stage, h->nact, h->G2, h->Pd, h->Pd2, h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+  void* ptrs[] = {h->Gp, h->u_in[1], h->z_in[1], h->m_in[1], h->x_stage, h->nact, h->G2, h->Pd, h->Pd2, h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -385,7 +395,7 @@ static StepPtrs base_ptrs(srukf_t* h) {
   q.S2 = h->S2; q.worklist = h->worklist; q.rel0 = 0; q.dbg = h->dbg;
   q.tmaps = h->tmaps; q.sbuf = h->sbuf; q.tm_dz = TM_DZ; q.dz_filter0 = 0;
   q.Pd = h->Pd; q.Pd2 = h->Pd2; q.carry_p = (h->prm.downdate_mode == 0) ? 1 : 0;
-  q.G2 = h->G2; q.n_new = 0; q.nact = h->nact;
+  q.G2 = h->G2; q.n_new = 0; q.nact = h->nact; q.Gp = h->Gp;
   return q;
 }
 

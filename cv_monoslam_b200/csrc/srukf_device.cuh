@@ -33,6 +33,7 @@ struct DevParams {
   int dist_series;   // k2 == 0 and |k1| ru^2 <= 2.5e-4 everywhere in the image: closed-form series root (no iteration)
   int dist_inward;   // k1 >= 0 and k2 >= 0: distortion moves a pixel towards the principal point, so a pixel that passed
                      // the [10, W-10] x [10, H-10] test (or was zeroed by it) cannot leave the image: second test skipped
+  int force_fb_ppm;  // measurement only (SRUKF_FORCE_FALLBACK_PPM): parts per million of the filters forced through the fallback
   int dbg_skip_mma;  // diagnostics only (SRUKF_DBG_SKIP_MMA): bit 0 stream the K chunks but skip the DMMAs, bit 1 k_gain without loads
 };
 
@@ -130,7 +131,6 @@ __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const void* tma
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* gptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // 16-byte asynchronous global->shared copy (LDGSTS, L2 only) and its completion hook onto an mbarrier:
 // the executing thread arrives on `bar` once all of its earlier cp.async operations have landed.

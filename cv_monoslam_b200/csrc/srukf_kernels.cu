@@ -55,6 +55,7 @@ struct StepPtrs {
   int carry_p;
   double* G2;             // [gslots][ntri + 2 nbp] scratch of the NEED_REORDER downdate (mode 3; lazily allocated)
   int n_new;              // m_nFilters: the last n_new features were added on the previous frame (mode 3)
+  double* Gp;             // [gslots][ntri] carried covariance of the reference-order fallback (fused mode only)
   int* nact;              // [chunk] features k_gain actually used (matched && visible && det(si) != 0): k_update and
                           // k_downdate take "no update this frame" (:2050) from the same count
 };
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
   double* xs = sm;                 // n
   double* rs = xs + n;             // P x 8 : rx ry rz rtheta c/det s/det det/det -
   double* red = rs + (size_t)P * 8; // 40
-  double* work = red + 40;          // (n+10)*4 + nf*4 (motion step only)
+  double* work = red + 40;          // (n+10)*4 (motion step) / per-warp partial sums (measurement step)
   double* xg = q.x + (size_t)b * n;
   double* Sg = q.S + (size_t)b * p.nbp;
   const int np = p.np;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
     }
     // square-root factor: E rows and the stacked robot-only rows
     double* T = work;                    // (n + 10) x 4
-    double* Ef = T + (size_t)(n + 10) * 4;  // nf x 4: new robot columns of the feature rows
+    double ee[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // this thread's share of E_f^T E_f (lower triangle, row-major)
     const double hs = p.wi_sr * 0.70710678118654752440;  // wi_sr / sqrt(2)
     for (int k = tid; k < n; k += NT) {
       const double* rp = rs + (size_t)(k + 1) * 8;
@@ -194,7 +195,13 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
       if (k < nf) {
         double* row = Sg + bp_idx(k, nf, np);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { row[c] = e[c]; Ef[k * 4 + c] = e[c]; }
+        for (int c = 0; c < 4; ++c) row[c] = e[c];
+        if (q.carry_p) {
+#pragma unroll
+          for (int r = 0, m = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c, ++m) ee[m] = fma(e[r], e[c], ee[m]);
+        }
       } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) T[(k - nf) * 4 + c] = e[c];
@@ -216,15 +223,18 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
     if (q.carry_p) {
       // robot block of the carried covariance P = S^T S for the new factor [[S_ff, E_f], [0, R_rr]]:
       //   P_rr = E_f^T E_f + R_rr^T R_rr   (the robot-feature rows S_ff^T E_f are formed by k_gain on the tensor pipe)
-      if (tid < 16) {
-        const int r = tid >> 2, c = tid & 3;
-        if (r >= c) {
-          double a = 0.0;
-          for (int k = 0; k < nf; ++k) a = fma(Ef[k * 4 + r], Ef[k * 4 + c], a);
-          for (int m = 0; m <= c; ++m) a = fma(T[m * 4 + r], T[m * 4 + c], a);
-          if (r == c) q.Pd[(size_t)b * np + nf + r] = a;
-          else Sg[(size_t)(nf + r) * np + nf + c] = a;
-        }
+      // E_f^T E_f: per-thread partial sums over the feature rows, reduced in fixed order (nothing of E_f is kept in
+      // shared memory, so the kernel's footprint does not grow with a second n x 4 array)
+#pragma unroll
+      for (int m = 0; m < 10; ++m) ee[m] = block_sum<NT>(ee[m], red);
+      if (tid == 0) {
+        for (int r = 0, m = 0; r < 4; ++r)
+          for (int c = 0; c <= r; ++c, ++m) {
+            double a = ee[m];
+            for (int mm = 0; mm <= c; ++mm) a = fma(T[mm * 4 + r], T[mm * 4 + c], a);
+            if (r == c) q.Pd[(size_t)b * np + nf + r] = a;
+            else Sg[(size_t)(nf + r) * np + nf + c] = a;
+          }
       }
     }
     if (save_rsig) {
@@ -408,9 +418,6 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
 #ifndef SRUKF_CANON_WARP
 #define SRUKF_CANON_WARP 0
 #endif
-#ifndef SRUKF_PREFETCH_P
-#define SRUKF_PREFETCH_P 0
-#endif
 constexpr int NB = 32;      // panel width (columns per contraction pass)
 constexpr int KC = 8;       // K rows per pipeline stage at full width
 #ifndef SRUKF_NSTAGE
@@ -439,9 +446,16 @@ constexpr int TM_S1 = 8;    // +0..7: S buffer 1
 constexpr int TM_UT = 16;   // +0..7: Ut scratch
 // 24: dZ scratch (chunk), box 8 rows x BP_B columns; 25: dZ of the whole batch (split API) -- see StepPtrs::tm_dz
 
+
 __host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 __host__ __device__ __forceinline__ int ntiles(int width) { return (width + TW - 1) / TW; }
 __host__ __device__ __forceinline__ int stage_doubles_for(int np) { return KC * ntiles(np) * TP; }
+// k_gain: doubles per ring stage of S rows: kc rows x boxes over the widest column range one CTA streams (np, or the
+// 8 * strips_per_cta rows of a row-split CTA) + one box for the robot columns of a row-split CTA
+__host__ __device__ __forceinline__ int gain_stage_doubles(int np, int kc, int strips_per_cta) {
+  const int w = (np < 8 * strips_per_cta) ? np : 8 * strips_per_cta;
+  return kc * (ntiles(w) + ((np > 8 * strips_per_cta) ? 1 : 0)) * TP;
+}
 #ifndef SRUKF_UPD_ROWS
 #define SRUKF_UPD_ROWS 16
 #endif
@@ -456,7 +470,7 @@ constexpr int UNS = SRUKF_UPD_NSTAGE;   // ring depth of k_update
 // Every chunk costs each warp ~190 instructions of ring / dispatch bookkeeping next to its 40-160 DMMAs, so two deep
 // stages of 16 rows beat three of 8 (k_update 93.3 -> 82.4 ms per step of 65,536 filters at L = 50); the ring still
 // fits under the panel's shared memory with two CTAs per SM.
-__host__ __device__ __forceinline__ int upd_stage_doubles_for(int np) { return SRUKF_UPD_ROWS * ntiles(np) * TP; }
+__host__ __device__ __forceinline__ int upd_stage_doubles(int np, int rows) { return rows * ntiles(np) * TP; }
 
 struct Ring {
   uint64_t* full;    // [NSTAGE]  expect_tx by the producer thread + TMA complete_tx
@@ -520,10 +534,12 @@ __device__ __forceinline__ void ring_release(Ring& r) {
 //   MASK: only A(k, col) with col >= k is taken (the entries left of the diagonal of S's square buffer hold the
 //   carried covariance, not zeros); this touches the first KC/8 strips of a chunk.
 //   b2base != nullptr: the LAST of the NTT column tiles takes its B fragment from b2base (pitch TP) instead.
+//   koff: chunk column 0 is state column (chunk's first K row + koff): 0 when the chunk starts on the diagonal, > 0 when
+//   a row-split CTA's columns start to the right of it (then the mask never fires for the first koff rows).
 template <int NW, int MQ, int NTM, int QLO, int QHI, int NTT, bool MASK>
 __device__ __forceinline__ void mma_chunk(double (&acc)[MQ][NTM][2], const double* abase, int tstride, int s0,
                                           const double* bbase, int bpitch, const double* b2base, int nks, int lane,
-                                          int warp) {
+                                          int warp, int koff = 0) {
   int aoff[QHI > QLO ? QHI - QLO : 1];
 #pragma unroll
   for (int q = QLO; q < QHI; ++q) {
@@ -542,7 +558,7 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MQ][NTM][2], const doubl
 #pragma unroll
     for (int q = QLO; q < QHI; ++q) {
       double a = ar[aoff[q - QLO]];
-      if (MASK && 8 * (warp + NW * q - s0) + (lane >> 2) < kk) a = 0.0;   // left of the diagonal: carried covariance, not S
+      if (MASK && 8 * (warp + NW * q - s0) + (lane >> 2) + koff < kk) a = 0.0;   // left of the diagonal: carried covariance, not S
 #pragma unroll
       for (int tt = 0; tt < NTT; ++tt) dmma(acc[q][tt][0], acc[q][tt][1], a, bf[tt]);
     }
@@ -552,11 +568,11 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MQ][NTM][2], const doubl
 template <int NW, int MQ, int NTM, int NTT, bool MASK>
 __device__ __forceinline__ void mma_chunk_rt(double (&acc)[MQ][NTM][2], int qlo, int qhi, const double* abase,
                                              int tstride, int s0, const double* bbase, int bpitch,
-                                             const double* b2base, int nks, int lane, int warp) {
-#define SRUKF_CASE(LO, HI)                                                                                          \
-  case LO * 8 + HI:                                                                                               \
-    if constexpr (HI <= MQ)                                                                                       \
-      mma_chunk<NW, MQ, NTM, LO, HI, NTT, MASK>(acc, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp); \
+                                             const double* b2base, int nks, int lane, int warp, int koff) {
+#define SRUKF_CASE(LO, HI)                                                                                                \
+  case LO * 8 + HI:                                                                                                     \
+    if constexpr (HI <= MQ)                                                                                             \
+      mma_chunk<NW, MQ, NTM, LO, HI, NTT, MASK>(acc, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp, koff); \
     break;
   switch (qlo * 8 + qhi) {
     SRUKF_CASE(0, 1) SRUKF_CASE(0, 2) SRUKF_CASE(0, 3) SRUKF_CASE(0, 4) SRUKF_CASE(0, 5)
@@ -571,12 +587,12 @@ __device__ __forceinline__ void mma_chunk_rt(double (&acc)[MQ][NTM][2], int qlo,
 template <int NW, int MQ, int NTM, bool MASK>
 __device__ __forceinline__ void mma_chunk_any(double (&acc)[MQ][NTM][2], int qlo, int qhi, int nt, const double* abase,
                                               int tstride, int s0, const double* bbase, int bpitch,
-                                              const double* b2base, int nks, int lane, int warp) {
-#define SRUKF_NT(N)                                                                                                   \
-  if constexpr (N <= NTM)                                                                                             \
-    if (nt == N) {                                                                                                    \
-      mma_chunk_rt<NW, MQ, NTM, N, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp); \
-      return;                                                                                                         \
+                                              const double* b2base, int nks, int lane, int warp, int koff = 0) {
+#define SRUKF_NT(N)                                                                                                         \
+  if constexpr (N <= NTM)                                                                                                   \
+    if (nt == N) {                                                                                                          \
+      mma_chunk_rt<NW, MQ, NTM, N, MASK>(acc, qlo, qhi, abase, tstride, s0, bbase, bpitch, b2base, nks, lane, warp, koff); \
+      return;                                                                                                               \
     }
   SRUKF_NT(NTM) SRUKF_NT(1) SRUKF_NT(2) SRUKF_NT(3) SRUKF_NT(4) SRUKF_NT(5) SRUKF_NT(6) SRUKF_NT(7)
 #undef SRUKF_NT
@@ -606,7 +622,13 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : 1) k_gain(DevPa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = q.chunk0 + blockIdx.x;
   const int n = p.n, nf = p.nf, L = p.L, L2 = 2 * p.L, np = p.np, Lc = p.Lc;
-  const int sdoubles = KCG * ntiles(np) * TP;   // KCG rows of S per chunk
+  // Row split for maps wider than one CTA's 8 * NW * MQ output rows: CTA blockIdx.y owns the output strips
+  // [strip0, strip_end) (state rows 8 strip0 ..), streams only the S rows and columns those strips need, and writes
+  // its own rows of Ut / x; gridDim.y == 1 (strip0 == 0) for np <= 8 NW MQ.
+  const int nblk = np / 8;                            // 8-row blocks of S == output strips
+  const int strip0 = blockIdx.y * (NW * MQ);
+  const int strip_end = (strip0 + NW * MQ < nblk) ? strip0 + NW * MQ : nblk;
+  const int sdoubles = gain_stage_doubles(np, KCG, NW * MQ);   // KCG rows of S per chunk (+ one box for the robot columns)
   size_t off = 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * NSG * sizeof(uint64_t));
   double* sii = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * 4 * (Lc / 2);   // per column pair
@@ -655,12 +677,13 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : 1) k_gain(DevPa
   // KalmanUpdate returns early without matches, :2050 (k_update copies S through); the carried covariance still
   // needs its new robot-feature rows
   const bool none = (*nact == 0);
-  if (tid == 0) q.nact[blockIdx.x] = *nact;
+  if (tid == 0 && blockIdx.y == 0) q.nact[blockIdx.x] = *nact;
   if (none && !q.carry_p) return;
   const bool seq_shift = (p.wc0 != p.wm0);
   const double wg = p.wi * p.gamma;
-  const int nblk = np / 8;                            // 8-row blocks of S == K chunks == output strips
-  const int nq_w = (nblk > warp) ? (nblk - warp - 1) / NW + 1 : 0;
+  const int wstrip = strip0 + warp;                   // this warp's first strip
+  const int nq_w = (strip_end > wstrip) ? (strip_end - wstrip - 1) / NW + 1 : 0;
+  const int cend = 8 * strip_end;                     // first state column this CTA does not need
   // With a carried covariance the robot-feature rows P(robot r, feature f) = sum_{k<=f} S(k,f) S(k, nf+r) (the new
   // robot columns of S, written by k_predict) are the same triangular product with 8 more B columns taken from the
   // S chunk itself: they ride along as one extra column tile of the last pass (or a pass of their own).
@@ -678,15 +701,22 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : 1) k_gain(DevPa
     for (int qq = 0; qq < MQ; ++qq)
 #pragma unroll
       for (int t = 0; t < NTM; ++t) acc[qq][t][0] = acc[qq][t][1] = 0.0;
-    // only blocks whose rows can touch a feature row matter: S rows >= nf (robot) have zero dZ
-    const int nchunk = (nf + KCG - 1) / KCG;
-    auto produce = [&](int t) {  // elected thread: S rows 8t..8t+7 from column 8t on (boxes of 64+8 columns) + dZ rows
-      const int nbx = ntiles(np - KCG * t);
-      const int st = ring_acquire<NSG>(ring, (uint32_t)((nbx * KCG * TP + (ncol ? KCG * BPB : 0)) * sizeof(double)));
+    // only blocks whose rows can touch a feature row of this CTA matter: S rows >= nf (robot) have zero dZ, and S is
+    // upper triangular (row k reaches output rows >= k only)
+    const int krows = (nf < cend) ? nf : cend;
+    const int nchunk = (krows + KCG - 1) / KCG;
+    const int xs0 = (nf / 8) * 8;   // first column of the box that holds the new robot columns S(:, nf..nf+3)
+    auto chunk_c0 = [&](int t) { return (KCG * t > 8 * strip0) ? KCG * t : 8 * strip0; };   // first state column of chunk t
+    auto produce = [&](int t) {  // elected thread: S rows KCG t.. from column c0 on (boxes of 64+4 columns) + dZ rows
+      const int c0 = chunk_c0(t);
+      const int nbx = ntiles(cend - c0);
+      const bool xbox = xtile && (nf + 4 > c0 + nbx * TW || nf < c0);   // robot columns outside this CTA's boxes: one more box
+      const int st = ring_acquire<NSG>(ring, (uint32_t)(((nbx + (xbox ? 1 : 0)) * KCG * TP + (ncol ? KCG * BPB : 0)) * sizeof(double)));
       double* xd = Xs + (size_t)st * sdoubles;
       // S is streamed once per pass: ask L2 to keep it; dZ is read once
       for (int j = 0; j < nbx; ++j)
-        tma_load_3d_hint(xd + (size_t)j * KCG * TP, tmS, KCG * t + TW * j, KCG * t, b, ring.full + st, pol_keep);
+        tma_load_3d_hint(xd + (size_t)j * KCG * TP, tmS, c0 + TW * j, KCG * t, b, ring.full + st, pol_keep);
+      if (xbox) tma_load_3d_hint(xd + (size_t)nbx * KCG * TP, tmS, xs0, KCG * t, b, ring.full + st, pol_keep);
       if (ncol)
         for (int hh = 0; hh < KCG / 8; ++hh)   // the dZ map has 8-row boxes
           tma_load_3d_hint(Bs + ((size_t)st * KCG + 8 * hh) * BPB, tmZ, cg, KCG * t + 8 * hh, q.dz_filter0 + blockIdx.x,
@@ -702,21 +732,27 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : 1) k_gain(DevPa
         ring_next(ring);
       }
       const int st = (p.dbg_skip_mma & 2) ? (t % NSG) : ring_wait<NSG>(ring);
-      const double* xa = Xs + (size_t)st * sdoubles;     // column 0 == state row KCG*t
+      const double* xa = Xs + (size_t)st * sdoubles;     // column 0 == state column c0 (== row KCG*t unless row-split)
       const double* xb = Bs + (size_t)st * KCG * BPB;
-      // output strip s = warp + NW*q receives S rows k <= its own: active slots are q >= qlo
-      const int s0 = (KCG / 8) * t;
-      const int qlo = (s0 > warp) ? (s0 - warp + NW - 1) / NW : 0;
-      const int xrel = nf - KCG * t;  // chunk column of S(:, nf): new robot columns (columns >= n are zero)
-      const double* b2 = xtile ? xa + (size_t)(xrel / TW) * (KCG * TP) + (xrel % TW) : nullptr;
-      if (!(p.dbg_skip_mma & 1)) mma_chunk_any<NW, MQ, NTM, true>(acc, qlo, nq_w, nt, xa, KCG * TP, s0, xb, BPB, b2, KCG / 4, lane, warp);
+      // output strip s = wstrip + NW*q receives S rows k <= its own: active slots are q >= qlo
+      const int c0 = chunk_c0(t);
+      const int s0 = c0 / 8;
+      const int qlo = (s0 > wstrip) ? (s0 - wstrip + NW - 1) / NW : 0;
+      const double* b2 = nullptr;
+      if (xtile) {   // new robot columns S(:, nf..) (columns >= n are zero): inside the boxes, or in the extra box
+        const int nbx = ntiles(cend - c0);
+        const bool xbox = (nf + 4 > c0 + nbx * TW || nf < c0);
+        const int xrel = nf - c0;
+        b2 = xbox ? xa + (size_t)nbx * (KCG * TP) + (nf - xs0) : xa + (size_t)(xrel / TW) * (KCG * TP) + (xrel % TW);
+      }
+      if (!(p.dbg_skip_mma & 1)) mma_chunk_any<NW, MQ, NTM, true>(acc, qlo, nq_w, nt, xa, KCG * TP, s0, xb, BPB, b2, KCG / 4, lane, wstrip, c0 - KCG * t);
       if (!(p.dbg_skip_mma & 2)) ring_release<NSG>(ring);
     }
     // epilogue: apply wi*gamma and si^-1 to each column pair, store Ut[c][f] (transposed), accumulate the shift
 #pragma unroll
     for (int qq = 0; qq < MQ; ++qq) {
-      const int s = warp + NW * qq;
-      if (s < nblk) {
+      const int s = wstrip + NW * qq;
+      if (s < strip_end) {
         const int f = 8 * s + (lane >> 2);
         double dxp = 0.0;
 #pragma unroll
@@ -756,11 +792,16 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : 1) k_gain(DevPa
   if (!seq_shift) {
     // x_f += U_f g
     __syncthreads();
-    for (int f = tid; f < nf; f += NTH) {
+    for (int f = 8 * strip0 + tid; f < nf && f < cend; f += NTH) {   // this CTA's rows
       const double xn = xg[f] + dxs[f];
       xg[f] = xn;
       if (!isfinite(xn)) flags |= SRUKF_FLAG_NAN;
     }
+  }
+  if (blockIdx.y != 0) {   // robot rows, padding and the robot part of x belong to the first CTA of the filter
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0 && flags) atomicOr(q.flags + b, flags);
+    return;
   }
   // robot rows: U_r = Pxy_r sii ; padding rows/columns of Ut are zero
   for (int i = tid; i < 4 * (Lc / 2); i += NTH) {
@@ -825,10 +866,11 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : 1) k_gain(DevPa
 //   T  (one thread per row) rows below: C(i,j) -= sum_{k<j in sub} L(i,k) W(j,k), L(i,j) = C(i,j) * (1/d_j)
 // Afterwards Cp holds L; S_new(j, i) = sqrt(d_j) L(i, j) (:2321) is written by the caller.
 // -------------------------------------------------------------------------------------------------
-template <int NW>
+template <int NW, int NBT>
 __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm, double* sdsm, double* esm, int R,
                                              int nbe, int J0, int n, double eps, uint32_t& flags) {
   constexpr int NTH = NW * 32;
+  constexpr int CPP = NBT + 1, WDP = NBT + 1;   // odd pitches: one row per lane / thread is bank-conflict free
   const int tid = threadIdx.x, lane = tid & 31;
 #if SRUKF_CANON_WARP
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: plain shuffles inside `if (warp == 0)`
@@ -843,10 +885,10 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
       //      diagonal block and goes straight on to the pivot chain D, which the other warps' strips overlap ----
       for (int rs = (warp == 0) ? sb : sb + warp; rs < R / 8; rs += (warp == 0) ? R : NW - 1) {
         const int i = 8 * rs + (lane >> 2);
-        double* ctile = Cp + (size_t)i * CP_PITCH + c0 + 2 * (lane & 3);
+        double* ctile = Cp + (size_t)i * CPP + c0 + 2 * (lane & 3);
         double a0 = ctile[0], a1 = ctile[1];
-        const double* arow = Cp + (size_t)i * CP_PITCH + (lane & 3);
-        const double* brow = Wd + (size_t)(c0 + (lane >> 2)) * WD_PITCH + (lane & 3);
+        const double* arow = Cp + (size_t)i * CPP + (lane & 3);
+        const double* brow = Wd + (size_t)(c0 + (lane >> 2)) * WDP + (lane & 3);
         for (int k0 = 0; k0 < c0; k0 += 4) dmma(a0, a1, -arow[k0], brow[k0]);
         ctile[0] = a0;
         ctile[1] = a1;
@@ -857,7 +899,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
     if (warp == 0) {
       const int li = lane & 7;
       double r[8];
-      const double* myrow = Cp + (size_t)(c0 + li) * CP_PITCH + c0;
+      const double* myrow = Cp + (size_t)(c0 + li) * CPP + c0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) r[k] = myrow[k];
       double dmine = 1.0, rmine = 1.0, emine = 0.0, w[8];
@@ -885,8 +927,8 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
         esm[c0 + lane] = emine;
         if (modified && J0 + c0 + lane < n) flags |= (dmine > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
         if (!isfinite(sd) || !isfinite(emine)) flags |= SRUKF_FLAG_NAN;   // fmax(eps, |NaN|) = eps hides a NaN pivot: E = d - c_jj does not
-        double* wrow = Wd + (size_t)(c0 + lane) * WD_PITCH + c0;
-        double* crow = Cp + (size_t)(c0 + lane) * CP_PITCH + c0;
+        double* wrow = Wd + (size_t)(c0 + lane) * WDP + c0;
+        double* crow = Cp + (size_t)(c0 + lane) * CPP + c0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           wrow[j] = w[j];                       // unscaled C(i,j) (only j <= i is used)
@@ -897,19 +939,19 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
     __syncthreads();
     // ---- T: rows below the 8x8 block ----
     for (int i = c0 + 8 + tid; i < R; i += NTH) {
-      double* crow = Cp + (size_t)i * CP_PITCH + c0;
+      double* crow = Cp + (size_t)i * CPP + c0;
       double cf[8], l[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         double a = crow[j];
-        const double* wj = Wd + (size_t)(c0 + j) * WD_PITCH + c0;
+        const double* wj = Wd + (size_t)(c0 + j) * WDP + c0;
 #pragma unroll
         for (int k = 0; k < j; ++k) a = fma(-l[k], wj[k], a);
         cf[j] = a;
         l[j] = a * dsm[c0 + j];
       }
       if (i < nbe) {   // rows of the panel's own diagonal block feed later sub-panels as W
-        double* wrow = Wd + (size_t)i * WD_PITCH + c0;
+        double* wrow = Wd + (size_t)i * WDP + c0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) wrow[j] = cf[j];
       }
@@ -938,9 +980,14 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
 // the S_old and Ut sources) and compared at the end: on violation, or when a pivot is modified beyond the EPSILON
 // floor, the filter is queued for the reference-order fallback (k_downdate) which recomputes it from S_old.
 // -------------------------------------------------------------------------------------------------
-template <int NW, bool TIMING, int MQ = MAXQ>
-__global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2 : 1)) k_update(DevParams p, StepPtrs q) {
+// Template: NW warps, MQ strips per warp (np <= 8 NW MQ), NBT panel columns, URW K rows per ring stage at full width.
+// <8, 5, 32, 16> is the L = 50 configuration (2 CTAs per SM); <16, 10, 16, 8> carries maps up to np = 1280 (L = 212):
+// narrower panels keep the panel (np x 17 doubles) and the accumulators (10 x 2 tiles) inside one SM.
+template <int NW, bool TIMING, int MQ = MAXQ, int NBT = NB, int URW = SRUKF_UPD_ROWS>
+__global__ void __launch_bounds__(NW * 32, (NW < 8) ? 16 / NW : ((NW == 8) ? ((MQ <= 2) ? 3 : 2) : 1))
+    k_update(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
+  constexpr int CPP = NBT + 1, WDP = NBT + 1;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31;
 #if SRUKF_CANON_WARP
@@ -956,14 +1003,14 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
   const double* PdOld = q.Pd + (size_t)b * np;
   double* PdNew = q.Pd2 + (size_t)b * np;
   const CUtensorMap* tmUt = q.tmaps + TM_UT;
-  const int sdoubles = upd_stage_doubles_for(np);
+  const int sdoubles = upd_stage_doubles(np, URW);
   size_t off = 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * UNS * sizeof(uint64_t));
-  double* Wd = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB * WD_PITCH;
-  double* dsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;    // 1 / pivot d_j
-  double* sdsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;   // sqrt(d_j)
-  double* esm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;    // E_j = d_j - c_jj
-  double* gdiag = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NB;  // G(j,j) of the panel
+  double* Wd = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NBT * WDP;
+  double* dsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NBT;    // 1 / pivot d_j
+  double* sdsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NBT;   // sqrt(d_j)
+  double* esm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NBT;    // E_j = d_j - c_jj
+  double* gdiag = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NBT;  // G(j,j) of the panel
   double* red = reinterpret_cast<double*>(smraw + off); off = (off + sizeof(double) * 40 + 127) & ~(size_t)127;
   double* Xs = reinterpret_cast<double*>(smraw + off);  // ring: UNS stages, aliased by the panel Cp
   double* Cp = Xs;
@@ -975,9 +1022,6 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
     for (int i = tid; i < np; i += NTH) PdNew[i] = PdOld[i];
     return;
   }
-#if SRUKF_PREFETCH_P
-  for (int idx = tid; idx < 2 * np; idx += NTH) prefetch_l2(Sold + (size_t)(idx >> 1) * np + 16 * (idx & 1));   // panel 0
-#endif
   Ring ring;
   ring_init<NW, UNS>(ring, bars);
   double gmax = -1.0e300, zmax = 0.0, tmax = 0.0;
@@ -988,8 +1032,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
   long long tlast = timing ? clock64() : 0;
 #define SRUKF_TICK(i) if (TIMING && timing) { long long tnow_ = clock64(); tph[i] += tnow_ - tlast; tlast = tnow_; }
 
-  for (int J0 = 0; J0 < np; J0 += NB) {
-    const int nbe = (np - J0 < NB) ? (np - J0) : NB;
+  for (int J0 = 0; J0 < np; J0 += NBT) {
+    const int nbe = (np - J0 < NBT) ? (np - J0) : NBT;
     const int R = np - J0;
     const int nt = nbe / 8;
     const int nbx = ntiles(R);         // TMA boxes per chunk
@@ -1001,9 +1045,10 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
     if (rpc > SRUKF_UPD_MAXROWS) rpc = SRUKF_UPD_MAXROWS;   // tensor maps exist for boxes of 8..64 rows
     // chunk list: [B: Ut rows | C: finished S_new rows 0..J0-1]
     const int rowsB = Lc, rowsC = J0;
-    const int cA = 0, cB = (rowsB + rpc - 1) / rpc, cC = (rowsC + rpc - 1) / rpc;
-    const int nchunks = cB + cC;
-    double acc[MQ][NB / 8][2];
+    const int cA = 0;
+    const int cB = (rowsB + rpc - 1) / rpc, cC = (rowsC + rpc - 1) / rpc;
+    const int nchunks = cA + cB + cC;
+    double acc[MQ][NBT / 8][2];
     // rows of chunk t: first row (within its source) and count
     auto chunk_rows = [&](int t, int& row0) -> int {
       if (t < cA + cB) { row0 = (t - cA) * rpc; return (rowsB - row0 < rpc) ? rowsB - row0 : rpc; }
@@ -1016,8 +1061,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
       long long tk0 = (TIMING && timing) ? clock64() : 0;
       const int st = ring_acquire<UNS>(ring, (uint32_t)(nbx * nrows * TP * sizeof(double)));
       if (TIMING && timing) { long long t1_ = clock64(); tkl[0] += t1_ - tk0; tk0 = t1_; }
-      const CUtensorMap* tm = ((t < cB) ? tmUt : tmNew) + (nrows / 8 - 1);
-      const int c2 = (t < cB) ? (int)blockIdx.x : b;
+      const CUtensorMap* tm = ((t < cA + cB) ? tmUt : tmNew) + (nrows / 8 - 1);
+      const int c2 = (t < cA + cB) ? (int)blockIdx.x : b;
       double* dst = Xs + (size_t)st * sdoubles;
       for (int j = 0; j < nbx; ++j) tma_load_3d(dst + (size_t)j * nrows * TP, tm, J0 + TW * j, row0, c2, ring.full + st);
       if (TIMING && timing) { tkl[1] += clock64() - tk0; }
@@ -1034,7 +1079,18 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
         const int st = ring_wait<UNS>(ring);
         if (TIMING && timing) { long long t1_ = clock64(); tkl[2] += t1_ - tk0; tk0 = t1_; }
         const double* xs_ = Xs + (size_t)st * sdoubles;
-        if (!(p.dbg_skip_mma & 1)) mma_chunk_any<NW, MQ, NB / 8, false>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nullptr, nrows / 4, lane, warp);
+        if (!(p.dbg_skip_mma & 1)) {
+          if constexpr (MQ <= MAXQ) {
+            mma_chunk_any<NW, MQ, NBT / 8, false>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nullptr, nrows / 4, lane, warp);
+          } else {   // strip slots [0,5) and [5,10): the second group's strips start NW * 5 further down
+            static_assert(MQ == 2 * MAXQ, "MQ is 5 or 10");
+            auto& lo = *reinterpret_cast<double(*)[MAXQ][NBT / 8][2]>(&acc[0]);
+            auto& hi = *reinterpret_cast<double(*)[MAXQ][NBT / 8][2]>(&acc[MAXQ]);
+            mma_chunk_any<NW, MAXQ, NBT / 8, false>(lo, 0, nq_w < MAXQ ? nq_w : MAXQ, nt, xs_, nrows * TP, 0, xs_, TP, nullptr, nrows / 4, lane, warp);
+            if (nq_w > MAXQ)
+              mma_chunk_any<NW, MAXQ, NBT / 8, false>(hi, 0, nq_w - MAXQ, nt, xs_, nrows * TP, 0, xs_, TP, nullptr, nrows / 4, lane, warp + NW * MAXQ);
+          }
+        }
         if (TIMING && timing) { long long t1_ = clock64(); tkl[3] += t1_ - tk0; tk0 = t1_; }
         ring_release<UNS>(ring);
         if (TIMING && timing) { tkl[4] += clock64() - tk0; tkl[5] += 1; }
@@ -1044,7 +1100,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
 #pragma unroll
       for (int qq = 0; qq < MQ; ++qq)
 #pragma unroll
-        for (int t = 0; t < NB / 8; ++t) { acc[qq][t][0] = -acc[qq][t][0]; acc[qq][t][1] = -acc[qq][t][1]; }
+        for (int t = 0; t < NBT / 8; ++t) { acc[qq][t][0] = -acc[qq][t][0]; acc[qq][t][1] = -acc[qq][t][1]; }
     };
     for (int t = 0; t < UNS - 1 && t < nchunks; ++t) {
       if (ring_my_turn<NW>(ring)) {
@@ -1062,7 +1118,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
       const int i = J0 + 8 * rs + (lane >> 2);
       const double* prow = Sold + (size_t)i * np;
 #pragma unroll
-      for (int tt = 0; tt < NB / 8; ++tt) {
+      for (int tt = 0; tt < NBT / 8; ++tt) {
         double v0 = 0.0, v1 = 0.0;
         if (rs < nstrip && tt < nt) {
           const int j = J0 + 8 * tt + 2 * (lane & 3);
@@ -1079,7 +1135,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
       }
     }
 
-    consume(0, cB);          // acc = -(P - U U^T) = -G(i, J)
+    consume(cA, cA + cB);    // acc = -(P - U U^T) = -G(i, J)
     // G(i, J) is visible now: store the carried covariance of the new factor, P_new = G (+ E on the diagonal,
     // added after the pivots are known), and track max diag / max off-diag of G for beta^2 (:2204-2205)
 #pragma unroll
@@ -1089,7 +1145,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
         const int i = J0 + 8 * rs + (lane >> 2);
         double* prow = Snew + (size_t)i * np;
 #pragma unroll
-        for (int tt = 0; tt < NB / 8; ++tt) {
+        for (int tt = 0; tt < NBT / 8; ++tt) {
           if (tt < nt) {
             const int j = J0 + 8 * tt + 2 * (lane & 3);
             const double g0 = -acc[qq][tt][0], g1 = -acc[qq][tt][1];
@@ -1108,15 +1164,6 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
         }
       }
     }
-#if SRUKF_PREFETCH_P
-    // the accumulators of the NEXT panel start from P_old(i, J+1): ask L2 for those 256-byte row pieces now, one
-    // contraction and one panel factorisation ahead of their use (the loads stalled ~14 % of the warp samples on DRAM)
-    if (J0 + NB < np) {
-      const int R1 = R - NB;
-      const double* pnext = Sold + (size_t)(J0 + NB) * np + (J0 + NB);
-      for (int idx = tid; idx < 2 * R1; idx += NTH) prefetch_l2(pnext + (size_t)(idx >> 1) * np + 16 * (idx & 1));
-    }
-#endif
     consume(cA + cB, nchunks);  // + S_new^T S_new
     negate();                   // acc = C(i, J)
     SRUKF_TICK(0)
@@ -1128,9 +1175,9 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
       if (rs < nstrip) {
         const int ri = 8 * rs + (lane >> 2);
 #pragma unroll
-        for (int tt = 0; tt < NB / 8; ++tt)
+        for (int tt = 0; tt < NBT / 8; ++tt)
           if (tt < nt) {
-            double* dst = Cp + (size_t)ri * CP_PITCH + 8 * tt + 2 * (lane & 3);
+            double* dst = Cp + (size_t)ri * CPP + 8 * tt + 2 * (lane & 3);
             dst[0] = acc[qq][tt][0];
             dst[1] = acc[qq][tt][1];
           }
@@ -1138,13 +1185,13 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
     }
     __syncthreads();
     SRUKF_TICK(2)
-    factor_panel<NW>(Cp, Wd, dsm, sdsm, esm, R, nbe, J0, n, p.epsilon, flags);
+    factor_panel<NW, NBT>(Cp, Wd, dsm, sdsm, esm, R, nbe, J0, n, p.epsilon, flags);
     if (tid < nbe) PdNew[J0 + tid] = gdiag[tid] + esm[tid];   // diag(P_new) = diag(G) + E, :2288
     SRUKF_TICK(3)
     // ---- rows J0.. of S_new: S_new(J0+j, J0+i) = sd_j L(i,j) for i > j, sd_j on the diagonal
     //      (entries left of the diagonal are zero in both S buffers and are never written) ----
     for (int i = tid; i < R; i += NTH) {
-      const double* crow = Cp + (size_t)i * CP_PITCH;
+      const double* crow = Cp + (size_t)i * CPP;
       double* dcol = Snew + (size_t)J0 * np + J0 + i;
       const int jmax = (i < nbe - 1) ? i : nbe - 1;
       const bool real = (J0 + i < n);
@@ -1177,9 +1224,12 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : ((NW <= 10) ? 2
   const double beta2 = fmax(fmax(gmax, zmax / nu), 1e-15);
   if (tid == 0 && tmax * tmax > beta2) flags |= SRUKF_FLAG_GMW_MODIFIED;
   flags = __reduce_or_sync(0xffffffffu, flags);
-  if (lane == 0 && flags) {
-    atomicOr(q.flags + b, flags);
-    if ((flags & SRUKF_FLAG_GMW_MODIFIED) && !p.dbg_skip_mma) {  // only warp 0 can raise it: one queue entry per filter and step
+  // measurement knob (SRUKF_FORCE_FALLBACK_PPM): send a pseudo-random share of the filters through the reference-order
+  // fallback although their guard did not fire (the result is the reference's own sequence, so parity still holds)
+  const bool forced = p.force_fb_ppm > 0 && warp == 0 && ((unsigned)b * 2654435761u) % 1000000u < (unsigned)p.force_fb_ppm;
+  if (lane == 0 && (flags || forced)) {
+    if (flags) atomicOr(q.flags + b, flags);
+    if (((flags & SRUKF_FLAG_GMW_MODIFIED) || forced) && !p.dbg_skip_mma) {  // only warp 0 can raise it: one queue entry per filter and step
       atomicOr(q.flags + b, SRUKF_FLAG_FALLBACK);
       int slot = atomicAdd(q.worklist, 1);
       q.worklist[1 + slot] = blockIdx.x;
@@ -1372,7 +1422,58 @@ __global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mo
       for (int i = tid; i < p.nbp; i += NT) Sg[i] = So[i];
       __syncthreads();
     }
-    if (mode == 2) {
+    if (mode == 1 && use_worklist && q.carry_p && q.Gp) {
+      // Reference order with the covariance carried instead of re-formed: the reference's S^T S of the factor it just
+      // produced is L D L^T = G + E (:2288), so P <- P - u u^T, S <- modifiedCholesky(P), P <- P + E reproduces
+      // :2116-2153 without the n^3 product per column.  P_old comes from the old buffer (lower triangle + Pd).
+      const double* So = q.S + (size_t)b * p.nbp;
+      const double* PdOld = q.Pd + (size_t)b * np;
+      double* Pc = q.Gp + (size_t)blockIdx.x * p.ntri;
+      double* evec = red + 40;
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int k = warp; k < n; k += NT / 32) {
+        double* col = Pc + tri_off(k, n);
+        for (int i = k + lane; i < n; i += 32) col[i - k] = (i == k) ? PdOld[k] : So[(size_t)i * np + k];
+      }
+      __syncthreads();
+      for (int j = 0; j < L; ++j) {
+        if (!(q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j])) continue;
+        for (int c = 0; c < 2; ++c) {
+          const double* urow = Ut + (size_t)(2 * j + c) * np;
+          for (int k = warp; k < n; k += NT / 32) {   // dst = src1 - u u^T (:2149)
+            double* col = Pc + tri_off(k, n);
+            double* gcol = G + tri_off(k, n);
+            const double uk = urow[k];
+            for (int i = k + lane; i < n; i += 32) {
+              const double v = fma(-uk, urow[i], col[i - k]);
+              col[i - k] = v;
+              gcol[i - k] = v;
+            }
+          }
+          __syncthreads();
+          mchol_core(n, np, p.epsilon, G, Sg, wcol, red, flags, evec);
+          __syncthreads();
+          for (int k = tid; k < n; k += NT) Pc[tri_off(k, n)] += evec[k];   // P = G + E
+          __syncthreads();
+        }
+      }
+      // the carried covariance of the redone filter, in the layout of the fused path
+      double* PdNew = q.Pd2 + (size_t)b * np;
+      for (int k = warp; k < n; k += NT / 32) {
+        const double* col = Pc + tri_off(k, n);
+        for (int i = k + lane; i < n; i += 32) {
+          if (i == k) PdNew[k] = col[0];
+          else Sg[(size_t)i * np + k] = col[i - k];
+        }
+      }
+      for (int i = n + tid; i < np; i += NT) PdNew[i] = 1.0;
+      for (int i = tid; i < n; i += NT)
+        if (!isfinite(Sg[bp_idx(i, i, np)])) flags |= SRUKF_FLAG_NAN;
+      flags = __reduce_or_sync(0xffffffffu, flags);
+      if ((tid & 31) == 0 && flags) atomicOr(q.flags + b, flags);
+      __syncthreads();
+      continue;
+    } else if (mode == 2) {
       form_G(p, Sg, Ut, 0, 2 * L, G);
       __syncthreads();
       mchol_inplace(p, G, Sg, wcol, red, flags);
@@ -2090,20 +2191,25 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
 // -------------------------------------------------------------------------------------------------
 // host-side launchers (called from srukf_capi.cu)
 // -------------------------------------------------------------------------------------------------
-// Warps per CTA of k_update (0 = unsupported size).  One CTA per filter, 8 rows x MAXQ strips per warp: small maps get
-// small CTAs (2 or 4 warps), so that an SM holds 8 or 4 filters at a time instead of two mostly idle 8-warp CTAs.
+// Warps per CTA of k_update (0 = unsupported size).  One CTA per filter.  8 warps up to np = 320; the strips per warp
+// (MQ = 1, 2, 3 or 5 accumulator slots) follow the map size, so small maps need fewer registers and more CTAs fit an
+// SM (4 / 3 / 2).  Smaller CTAs (2 or 4 warps, SRUKF_UPDATE_WARPS) measured slower (L = 20: 68.5 vs 28.8 ms per step of
+// 131,072 filters).  Maps beyond 8 * 16 * 5 = 640 rows take the 16-warp / 10-strip / 16-column-panel variant (np <= 1280).
 int tile_warps(const DevParams& p) {
   if (const char* e = getenv("SRUKF_UPDATE_WARPS")) {
     const int w = atoi(e);
     if ((w == 2 || w == 4 || w == 8 || w == 16) && p.np <= 8 * w * MAXQ) return w;
-    if (w == 10 && p.np <= 8 * 10 * 4) return 10;   // 10 warps x 4 strips: 20 warps per SM at L = 50
   }
-  if (p.np <= 8 * 2 * MAXQ) return 2;
-  if (p.np <= 8 * 4 * MAXQ) return 4;
   if (p.np <= 8 * 8 * MAXQ) return 8;
-  if (p.np <= 8 * 16 * MAXQ) return 16;
+  if (p.np <= 8 * 16 * 2 * MAXQ) return 16;
   return 0;
 }
+int update_mq(const DevParams& p) {   // accumulator slots of the 8-warp variant
+  if (getenv("SRUKF_UPDATE_MQ5")) return MAXQ;
+  const int strips = p.np / 8;
+  return strips <= 8 ? 1 : (strips <= 16 ? 2 : (strips <= 24 ? 3 : MAXQ));
+}
+bool update_wide(const DevParams& p) { return p.np > 8 * 16 * MAXQ; }   // the <16, 10, 16, 8> variant
 // k_gain variant: 0 = <8,5,4> (np <= 320, 2 CTAs/SM), 1 = <16,3,7> (np <= 384, 1 CTA/SM, half the passes),
 // 2 = <16,5,4> (np <= 640), 3 = <2,5,4> (np <= 80, 8 CTAs/SM), 4 = <4,5,4> (np <= 160, 4 CTAs/SM)
 #ifndef SRUKF_GAIN_KC
@@ -2125,24 +2231,36 @@ int gain_dz_box(const DevParams& p) {
   return gain_variant(p) == 1 ? 72 : 40;
 }
 size_t predict_smem_bytes(const DevParams& p) {
-  size_t work = (size_t)(p.n + 10) * 4 + (size_t)p.nf * 4;     // motion step: T and E_f
+  size_t work = (size_t)(p.n + 10) * 4;                        // motion step: T
   if (work < (size_t)(NT / 32) * 8 * 13) work = (size_t)(NT / 32) * 8 * 13;   // measurement step: per-warp partial sums
   return sizeof(double) * ((size_t)p.n + (size_t)p.P * 8 + 40 + work);
 }
+// output strips (8 state rows each) one k_gain CTA owns: NW * MQ of the variant; wider maps are row-split over gridDim.y
+int gain_strips_per_cta(const DevParams& p) {
+  switch (gain_variant(p)) {
+    case 0: return 8 * 5;
+    case 1: return 16 * 3;
+    case 3: return 2 * 5;
+    case 4: return 4 * 5;
+    default: return 16 * 5;
+  }
+}
+int gain_row_ctas(const DevParams& p) { return (p.np / 8 + gain_strips_per_cta(p) - 1) / gain_strips_per_cta(p); }
 size_t gain_smem_bytes(const DevParams& p) {
   const bool v1 = gain_variant(p) == 1;
   const size_t kc = v1 ? GKC1 : 8, ns = v1 ? GNS1 : NSTAGE;   // template arguments KCG / NSG of the variant
   size_t off = align16(2 * ns * sizeof(uint64_t));
   off += sizeof(double) * (8 * (p.Lc / 2) + p.np);
   off = (off + sizeof(int) * (p.L + 1) + 127) & ~(size_t)127;
-  return off + sizeof(double) * ns * kc * ((size_t)ntiles(p.np) * TP + gain_dz_box(p));
+  return off + sizeof(double) * ns * ((size_t)gain_stage_doubles(p.np, (int)kc, gain_strips_per_cta(p)) + kc * gain_dz_box(p));
 }
 size_t update_smem_bytes(const DevParams& p) {
+  const int nbt = update_wide(p) ? 16 : NB, urw = update_wide(p) ? 8 : SRUKF_UPD_ROWS;
   size_t off = align16(2 * UNS * sizeof(uint64_t));
-  off += sizeof(double) * (NB * WD_PITCH + 4 * NB);
+  off += sizeof(double) * (nbt * (nbt + 1) + 4 * nbt);
   off = (off + sizeof(double) * 40 + 127) & ~(size_t)127;
-  size_t ring = (size_t)UNS * upd_stage_doubles_for(p.np);  // stage size is fixed: SRUKF_UPD_ROWS rows at full width
-  size_t panel = (size_t)p.np * CP_PITCH;
+  size_t ring = (size_t)UNS * upd_stage_doubles(p.np, urw);  // stage size is fixed: urw rows at full width
+  size_t panel = (size_t)p.np * (nbt + 1);
   return off + sizeof(double) * (ring > panel ? ring : panel);
 }
 size_t downdate_smem_bytes(const DevParams& p) { return sizeof(double) * (2 * (size_t)p.n + 40); }
@@ -2163,7 +2281,8 @@ cudaError_t configure_kernels(const DevParams&) {
   SRUKF_SET((k_gain<8, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<16, 3, 7, GKC1, GNS1>)) SRUKF_SET((k_gain<16, 5, 4, 8, NSTAGE>))
   SRUKF_SET((k_gain<2, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<4, 5, 4, 8, NSTAGE>))
   SRUKF_SET((k_update<8, false>)) SRUKF_SET((k_update<16, false>)) SRUKF_SET((k_update<8, true>)) SRUKF_SET((k_update<16, true>))
-  SRUKF_SET((k_update<2, false>)) SRUKF_SET((k_update<4, false>)) SRUKF_SET((k_update<10, false, 4>))
+  SRUKF_SET((k_update<2, false>)) SRUKF_SET((k_update<4, false>)) SRUKF_SET((k_update<16, false, 10, 16, 8>))
+  SRUKF_SET((k_update<8, false, 1>)) SRUKF_SET((k_update<8, false, 2>)) SRUKF_SET((k_update<8, false, 3>))
   SRUKF_SET(k_downdate) SRUKF_SET(k_init_features) SRUKF_SET(k_add_features) SRUKF_SET(k_delete_feature)
   SRUKF_SET(k_chol_update) SRUKF_SET(k_mchol_batch)
 #undef SRUKF_SET
@@ -2179,12 +2298,13 @@ void launch_predict(const DevParams& p, const StepPtrs& q, int nblocks, bool mot
   else k_predict<false, true><<<nblocks, NT, smem, st>>>(p, q, 0);
 }
 void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
+  const dim3 grid(nblocks, gain_row_ctas(p));
   switch (gain_variant(p)) {
-    case 0: k_gain<8, 5, 4, 8, NSTAGE><<<nblocks, 256, gain_smem_bytes(p), st>>>(p, q); break;
-    case 1: k_gain<16, 3, 7, GKC1, GNS1><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
-    case 3: k_gain<2, 5, 4, 8, NSTAGE><<<nblocks, 64, gain_smem_bytes(p), st>>>(p, q); break;
-    case 4: k_gain<4, 5, 4, 8, NSTAGE><<<nblocks, 128, gain_smem_bytes(p), st>>>(p, q); break;
-    default: k_gain<16, 5, 4, 8, NSTAGE><<<nblocks, 512, gain_smem_bytes(p), st>>>(p, q); break;
+    case 0: k_gain<8, 5, 4, 8, NSTAGE><<<grid, 256, gain_smem_bytes(p), st>>>(p, q); break;
+    case 1: k_gain<16, 3, 7, GKC1, GNS1><<<grid, 512, gain_smem_bytes(p), st>>>(p, q); break;
+    case 3: k_gain<2, 5, 4, 8, NSTAGE><<<grid, 64, gain_smem_bytes(p), st>>>(p, q); break;
+    case 4: k_gain<4, 5, 4, 8, NSTAGE><<<grid, 128, gain_smem_bytes(p), st>>>(p, q); break;
+    default: k_gain<16, 5, 4, 8, NSTAGE><<<grid, 512, gain_smem_bytes(p), st>>>(p, q); break;
   }
 }
 void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
@@ -2193,13 +2313,18 @@ void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStrea
   switch (tile_warps(p)) {
     case 2: k_update<2, false><<<nblocks, 64, smem, st>>>(p, q); break;
     case 4: k_update<4, false><<<nblocks, 128, smem, st>>>(p, q); break;
-    case 10: k_update<10, false, 4><<<nblocks, 320, smem, st>>>(p, q); break;
     case 8:
       if (timing) k_update<8, true><<<nblocks, 256, smem, st>>>(p, q);
-      else k_update<8, false><<<nblocks, 256, smem, st>>>(p, q);
+      else switch (update_mq(p)) {
+        case 1: k_update<8, false, 1><<<nblocks, 256, smem, st>>>(p, q); break;
+        case 2: k_update<8, false, 2><<<nblocks, 256, smem, st>>>(p, q); break;
+        case 3: k_update<8, false, 3><<<nblocks, 256, smem, st>>>(p, q); break;
+        default: k_update<8, false><<<nblocks, 256, smem, st>>>(p, q); break;
+      }
       break;
     default:
-      if (timing) k_update<16, true><<<nblocks, 512, smem, st>>>(p, q);
+      if (update_wide(p)) k_update<16, false, 10, 16, 8><<<nblocks, 512, smem, st>>>(p, q);
+      else if (timing) k_update<16, true><<<nblocks, 512, smem, st>>>(p, q);
       else k_update<16, false><<<nblocks, 512, smem, st>>>(p, q);
       break;
   }
