@@ -23,6 +23,7 @@ struct StepPtrs {
   double* Pd; double* Pd2; int carry_p;
   double* G2; int n_new;
   double* Gp;
+  double* Ed;
   int* nact;
 };
 // tensor-map table layout and box geometry (must match srukf_kernels.cu)
@@ -90,9 +91,11 @@ struct srukf_handle {
   SrukfParams prm{};
   cudaStream_t stream = nullptr;
   // state: S lives in the internal square layout; k_update ping-pongs between the two buffers
-  double *x = nullptr, *S = nullptr, *S2 = nullptr;   // S = current, S2 = the other one
-  int sbuf = 0;                                       // index of the current buffer in the tensor-map table
-  double *Pd = nullptr, *Pd2 = nullptr;               // diagonals of the carried covariance (fused mode)
+  // state: ONE np x np square per filter in the internal layout (factor in the upper triangle, carried covariance in
+  // the lower one); k_update works in place (a panel's P_old is read before its positions are rewritten)
+  double *x = nullptr, *S = nullptr;
+  double* Pd = nullptr;                               // diagonal of the carried covariance (fused mode)
+  double* Ed = nullptr;                               // E_j = d_j - c_jj of the last update: lets the fallback rebuild P_old
   CUtensorMap* tmaps = nullptr;                       // device table of TMA tensor maps
   // per-step inputs (device copies for the host-pointer API)
   double *u = nullptr, *z = nullptr; uint8_t* matched = nullptr;
@@ -264,7 +267,8 @@ static int build_tensor_maps(srukf_handle* h, double* sbuf0, double* sbuf1) {
   int rc;
   for (int r = 0; r < TM_ROWSETS; ++r) {
     if ((rc = encode_map(&hm[TM_S0 + r], sbuf0, p.np, p.np, p.B, TP, 8 * (r + 1)))) return rc;
-    if ((rc = encode_map(&hm[TM_S1 + r], sbuf1 ? sbuf1 : sbuf0, p.np, p.np, p.B, TP, 8 * (r + 1)))) return rc;
+    hm[TM_S1 + r] = hm[TM_S0 + r];   // in-place update: "old" and "new" factor are the same buffer
+    (void)sbuf1;
     if ((rc = encode_map(&hm[TM_UT + r], h->U, p.np, p.Lc, h->chunk, TP, 8 * (r + 1)))) return rc;
   }
   const uint32_t bpb = (uint32_t)gain_dz_box(p);
@@ -312,12 +316,9 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   CUH(cudaMalloc(&h->x, sizeof(double) * B * n));
   CUH(cudaMalloc(&h->S, sizeof(double) * (size_t)B * p.nbp));
   if (prm.downdate_mode == 0) {
-    CUH(cudaMalloc(&h->S2, sizeof(double) * (size_t)B * p.nbp));
-    CUH(cudaMemsetAsync(h->S2, 0, sizeof(double) * (size_t)B * p.nbp, h->stream));
-    CUH(cudaMalloc(&h->Pd, sizeof(double) * (size_t)B * p.np));
-    CUH(cudaMalloc(&h->Pd2, sizeof(double) * (size_t)B * p.np));
-    CUH(cudaMemsetAsync(h->Pd, 0, sizeof(double) * (size_t)B * p.np, h->stream));
-    CUH(cudaMemsetAsync(h->Pd2, 0, sizeof(double) * (size_t)B * p.np, h->stream));
+    CUH(cudaMalloc(&h->Pd, sizeof(double) * 2 * (size_t)B * p.np));   // [Pd | Ed]: k_update reaches Ed through its Pd pointer
+    h->Ed = h->Pd + (size_t)B * p.np;
+    CUH(cudaMemsetAsync(h->Pd, 0, sizeof(double) * 2 * (size_t)B * p.np, h->stream));
   }
   CUH(cudaMalloc(&h->u, sizeof(double) * B * 3));
   CUH(cudaMalloc(&h->z, sizeof(double) * B * L2));
@@ -364,7 +365,7 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   CUH(cudaStreamSynchronize(h->stream));
 #undef CUH
   {
-    int rc_ = build_tensor_maps(h, h->S, h->S2);
+    int rc_ = build_tensor_maps(h, h->S, nullptr);
     if (rc_) { srukf_destroy(h); return rc_; }
   }
   *out = h;
@@ -378,7 +379,7 @@ int srukf_destroy(srukf_t* h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
   for (cudaEvent_t e : {h->ev_in[0], h->ev_in[1], h->ev_done[0], h->ev_done[1], h->ev_xs, h->ev_xd}) if (e) cudaEventDestroy(e);
-  void* ptrs[] = {h->Gp, h->u_in[1], h->z_in[1], h->m_in[1], h->x_stage, h->nact, h->G2, h->Pd, h->Pd2, h->tmaps, h->dbg, h->S2, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+  void* ptrs[] = {h->Gp, h->u_in[1], h->z_in[1], h->m_in[1], h->x_stage, h->nact, h->G2, h->Pd, h->tmaps, h->dbg, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -392,9 +393,9 @@ static StepPtrs base_ptrs(srukf_t* h) {
   q.x = h->x; q.S = h->S; q.u = h->u; q.z = h->z; q.matched = h->matched;
   q.hbar = h->hbar; q.si = h->si; q.visible = h->visible; q.cshift = h->cshift; q.pxyr = h->pxyr;
   q.rsig = h->rsig; q.dZ = h->dZ; q.U = h->U; q.G = h->G; q.flags = h->flags; q.chunk0 = 0;
-  q.S2 = h->S2; q.worklist = h->worklist; q.rel0 = 0; q.dbg = h->dbg;
-  q.tmaps = h->tmaps; q.sbuf = h->sbuf; q.tm_dz = TM_DZ; q.dz_filter0 = 0;
-  q.Pd = h->Pd; q.Pd2 = h->Pd2; q.carry_p = (h->prm.downdate_mode == 0) ? 1 : 0;
+  q.S2 = h->S; q.worklist = h->worklist; q.rel0 = 0; q.dbg = h->dbg;
+  q.tmaps = h->tmaps; q.sbuf = 0; q.tm_dz = TM_DZ; q.dz_filter0 = 0;
+  q.Pd = h->Pd; q.Pd2 = h->Pd; q.Ed = h->Ed; q.carry_p = (h->prm.downdate_mode == 0) ? 1 : 0;
   q.G2 = h->G2; q.n_new = 0; q.nact = h->nact; q.Gp = h->Gp;
   return q;
 }
@@ -564,7 +565,7 @@ static int ensure_split_buffers(srukf_t* h) {
     CU(cudaMalloc(&h->dZ_all, sizeof(double) * (size_t)p.B * p.np * p.Lc));
     CU(cudaMemsetAsync(h->dZ_all, 0, sizeof(double) * (size_t)p.B * p.np * p.Lc, h->stream));
     // buffers by allocation order: the current one is index h->sbuf
-    int rc_ = build_tensor_maps(h, h->sbuf ? h->S2 : h->S, h->sbuf ? h->S : h->S2);
+    int rc_ = build_tensor_maps(h, h->S, nullptr);
     if (rc_) return rc_;
   }
   return SRUKF_OK;
@@ -655,13 +656,8 @@ static void run_update(srukf_t* h, StepPtrs q, int b0, int nb) {
   prof_end(h);
 }
 
-// after a fused update over the whole batch the roles of the two S buffers swap
-static void flip_buffers(srukf_t* h) {
-  if (h->prm.downdate_mode == 0) {
-    double* t = h->S; h->S = h->S2; h->S2 = t; h->sbuf ^= 1;
-    t = h->Pd; h->Pd = h->Pd2; h->Pd2 = t;
-  }
-}
+// (the fused update works in place: there is no second S buffer to swap)
+static void flip_buffers(srukf_t*) {}
 
 int srukf_kalman_update(srukf_t* h, const double* z, const uint8_t* matched) {
   if (!h || !z || !matched) return fail(SRUKF_EINVAL, "srukf_kalman_update: null argument");

@@ -39,7 +39,7 @@ struct StepPtrs {
   double* G;              // [gslots][ntri]    scratch of the unblocked fallback
   uint32_t* flags;        // [B]
   int chunk0;             // first filter of this chunk (scratch arrays are chunk-relative)
-  double* S2;             // [B][nbp] the other S buffer (k_update writes it)
+  double* S2;             // == S: k_update works in place (kept as a separate name for "the factor being written")
   int* worklist;          // [0] = count, [1..] = chunk-relative filter indices needing the fallback
   int rel0;               // first chunk-relative filter of a k_downdate launch (non-worklist)
   unsigned long long* dbg; // optional [16] phase-cycle counters of k_update (diagnostics; may be null)
@@ -56,6 +56,7 @@ struct StepPtrs {
   double* G2;             // [gslots][ntri + 2 nbp] scratch of the NEED_REORDER downdate (mode 3; lazily allocated)
   int n_new;              // m_nFilters: the last n_new features were added on the previous frame (mode 3)
   double* Gp;             // [gslots][ntri] carried covariance of the reference-order fallback (fused mode only)
+  double* Ed;             // [B][np] E_j = d_j - c_jj of the last fused update (the fallback rebuilds P_old from it)
   int* nact;              // [chunk] features k_gain actually used (matched && visible && det(si) != 0): k_update and
                           // k_downdate take "no update this frame" (:2050) from the same count
 };
@@ -963,6 +964,10 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
 }
 
 // -------------------------------------------------------------------------------------------------
+// IN PLACE: Sold == Snew.  Panel J reads P_old(i, J) (lower-triangle positions (i, j), i >= J0, and Pd) into the
+// accumulators before anything of this panel is written; it then writes G(i, J) to the same lower positions and rows J
+// of S_new to upper positions whose old content (S_old) nothing reads any more.  Earlier panels wrote other columns
+// (lower) and rows < J0 (upper), which this panel only reads as finished S_new rows.
 // k_update -- GSLCholeskyUpdate (DOWNDATING, NEEDNOT_REORDER; SLAM.cpp:2106-2121,2139-2153) for all matched
 // features at once: S_new = modifiedCholesky(S_old^T S_old - U U^T)  (SLAM.cpp:2197-2327).
 //
@@ -1017,9 +1022,12 @@ __global__ void __launch_bounds__(NW * 32, (NW < 8) ? 16 / NW : ((NW == 8) ? ((M
   uint32_t flags = 0;
 
   const int nact = q.nact[blockIdx.x];   // k_gain's count: a feature with a singular si contributes U = 0 (si.inv() = 0)
-  if (nact == 0) {  // KalmanUpdate returned early (:2050): factor and covariance are carried over unchanged
-    for (int i = tid; i < p.nbp; i += NTH) Snew[i] = Sold[i];
-    for (int i = tid; i < np; i += NTH) PdNew[i] = PdOld[i];
+  if (nact == 0) {  // KalmanUpdate returned early (:2050): factor and covariance stay as they are (nothing to copy in place)
+    if (Snew != Sold) {   // two-buffer callers only.  (Dropping this dead branch changes ptxas's allocation of the whole
+                          // kernel: 128 registers with 208 bytes of spills instead of 0 -- measured, so it stays.)
+      for (int i = tid; i < p.nbp; i += NTH) Snew[i] = Sold[i];
+      for (int i = tid; i < np; i += NTH) PdNew[i] = PdOld[i];
+    }
     return;
   }
   Ring ring;
@@ -1186,7 +1194,10 @@ __global__ void __launch_bounds__(NW * 32, (NW < 8) ? 16 / NW : ((NW == 8) ? ((M
     __syncthreads();
     SRUKF_TICK(2)
     factor_panel<NW, NBT>(Cp, Wd, dsm, sdsm, esm, R, nbe, J0, n, p.epsilon, flags);
-    if (tid < nbe) PdNew[J0 + tid] = gdiag[tid] + esm[tid];   // diag(P_new) = diag(G) + E, :2288
+    if (tid < nbe) {
+      PdNew[J0 + tid] = gdiag[tid] + esm[tid];   // diag(P_new) = diag(G) + E, :2288
+      PdNew[(size_t)p.B * np + J0 + tid] = esm[tid];   // Ed lives right behind Pd ([2][B][np] in one allocation)
+    }
     SRUKF_TICK(3)
     // ---- rows J0.. of S_new: S_new(J0+j, J0+i) = sd_j L(i,j) for i > j, sd_j on the diagonal
     //      (entries left of the diagonal are zero in both S buffers and are never written) ----
@@ -1417,23 +1428,25 @@ __global__ void __launch_bounds__(NT) k_downdate(DevParams p, StepPtrs q, int mo
     double* G = q.G + (size_t)blockIdx.x * p.ntri;
     uint32_t flags = 0;
     if (q.nact[rel] == 0) continue;  // :2050 (k_gain's count; with every si singular all U columns are zero)
-    if (use_worklist) {       // rebuild from the untouched old factor
-      const double* So = q.S + (size_t)b * p.nbp;
-      for (int i = tid; i < p.nbp; i += NT) Sg[i] = So[i];
-      __syncthreads();
-    }
     if (mode == 1 && use_worklist && q.carry_p && q.Gp) {
       // Reference order with the covariance carried instead of re-formed: the reference's S^T S of the factor it just
       // produced is L D L^T = G + E (:2288), so P <- P - u u^T, S <- modifiedCholesky(P), P <- P + E reproduces
-      // :2116-2153 without the n^3 product per column.  P_old comes from the old buffer (lower triangle + Pd).
+      // :2116-2153 without the n^3 product per column.
+      // The fused update ran in place, so P_old itself is gone; it is rebuilt from what the fused pass left:
+      // P_old = G + U U^T with G = (lower triangle, Pd - E) of the buffer (E saved per pivot by k_update).
       const double* So = q.S + (size_t)b * p.nbp;
-      const double* PdOld = q.Pd + (size_t)b * np;
+      const double* PdNow = q.Pd + (size_t)b * np;
+      const double* Ed = q.Ed + (size_t)b * np;
       double* Pc = q.Gp + (size_t)blockIdx.x * p.ntri;
       double* evec = red + 40;
       const int warp = tid >> 5, lane = tid & 31;
       for (int k = warp; k < n; k += NT / 32) {
         double* col = Pc + tri_off(k, n);
-        for (int i = k + lane; i < n; i += 32) col[i - k] = (i == k) ? PdOld[k] : So[(size_t)i * np + k];
+        for (int i = k + lane; i < n; i += 32) {
+          double uu = 0.0;
+          for (int c = 0; c < 2 * L; ++c) uu = fma(Ut[(size_t)c * np + i], Ut[(size_t)c * np + k], uu);
+          col[i - k] = ((i == k) ? PdNow[k] - Ed[k] : So[(size_t)i * np + k]) + uu;
+        }
       }
       __syncthreads();
       for (int j = 0; j < L; ++j) {

@@ -79,7 +79,11 @@ int srukf_predict_motion(srukf_t *h, const double *u);
 /* CSLAM::predictMeasurement (SLAM.cpp:1604-1608). */
 int srukf_predict_measurement(srukf_t *h);
 /* m_allPredictSet / map_p->predictLocation, map_p->Si, map_p->isVisible (SLAM.cpp:1724-1738):
- * hbar [B][L][2], si [B][L][4] (2x2 row-major upper triangular), visible [B][L]; any may be NULL. */
+ * hbar [B][L][2], si [B][L][4] (2x2 row-major upper triangular), visible [B][L]; any may be NULL.
+ * Sign convention: si is the Cholesky factor of the 2x2 innovation Gram matrix (positive diagonal).  The reference's
+ * GSL Householder QR (:1771-1775) returns the same matrix up to the sign of each row (R(0,0) = -sign(alpha) |x|,
+ * typically negative); Si^T Si, the gain, U and the chi-square gate are independent of it.  A caller that derives a
+ * search window from 2*Si(0,0) (dataAssociation, :1952-1955) should use |Si(k,k)|. */
 int srukf_get_prediction(srukf_t *h, double *hbar, double *si, uint8_t *visible);
 /* Feature initialisation at frame 1: CSLAM::addFeatures with an empty map (SLAM.cpp:818-871), i.e.
  * passSigmaThroughMapingFunction (:1177-1250), QrAndCholeskyForInitilization (:1260-1300) and getPermutationMatrix
