@@ -39,6 +39,7 @@ int gain_dz_box(const DevParams& p);
 int gain_variant(const DevParams& p);
 int tile_warps(const DevParams& p);
 int gain_row_ctas(const DevParams& p);
+bool predict_free(const DevParams& p);
 cudaError_t configure_kernels(const DevParams& p);
 size_t predict_smem_bytes(const DevParams& p);
 size_t gain_smem_bytes(const DevParams& p);
@@ -225,6 +226,7 @@ static void fill_dev_params(DevParams& d, const SrukfParams& s, int B, int L) {
     d.dist_series = (s.cam_k2 == 0.0 && d.dist_inward && s.cam_k1 * r2max <= 2.5e-4 && s.newton_iters >= 6) ? 1 : 0;
     if (getenv("SRUKF_NO_DIST_FASTPATH")) { d.dist_series = 0; d.dist_inward = 0; }
   }
+  d.pred_free = (predict_free(d) && !getenv("SRUKF_PREDICT_BARRIERS")) ? 1 : 0;
   { const char* e_ = getenv("SRUKF_FORCE_FALLBACK_PPM"); d.force_fb_ppm = e_ ? atoi(e_) : 0; }
   { const char* e_ = getenv("SRUKF_DBG_SKIP_MMA"); d.dbg_skip_mma = e_ ? atoi(e_) : 0; }  // bit 0: skip DMMAs, bit 1: skip k_gain's loads
   double wm0, wc0, wi, wi_sr, gamma;

@@ -33,6 +33,7 @@ struct DevParams {
   int dist_series;   // k2 == 0 and |k1| ru^2 <= 2.5e-4 everywhere in the image: closed-form series root (no iteration)
   int dist_inward;   // k1 >= 0 and k2 >= 0: distortion moves a pixel towards the principal point, so a pixel that passed
                      // the [10, W-10] x [10, H-10] test (or was zeroed by it) cannot leave the image: second test skipped
+  int pred_free;     // k_predict: per-warp partial sums of all features fit in shared memory (no block barriers)
   int force_fb_ppm;  // measurement only (SRUKF_FORCE_FALLBACK_PPM): parts per million of the filters forced through the fallback
   int dbg_skip_mma;  // diagnostics only (SRUKF_DBG_SKIP_MMA): bit 0 stream the K chunks but skip the DMMAs, bit 1 k_gain without loads
 };

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
     double* dZ = q.dZ + (size_t)blockIdx.x * np * Lc;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int NWP = NT / 32;
-    double* part = work;   // [NWP][8][13] per-warp partial sums of the current feature block
+    double* part = work;   // [NWP][L or 8][13] per-warp partial sums
     const double W1 = 2.0 * Na * p.wi;
     const double cab = W1 + p.wc0 - 2.0;  // coefficient of abar*bbar^T (== -1 when wc0 == wm0)
     double* hb = q.hbar + (size_t)b * 2 * L;
@@ -279,6 +279,46 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
     double* csh = q.cshift + (size_t)b * 2 * L;
     double* pr = q.pxyr + (size_t)b * 8 * L;
     uint8_t* vis = q.visible + (size_t)b * L;
+    // Per-warp partial sums: when they fit (8 warps x L x 13 doubles next to the sigma-pose table with two CTAs per SM)
+    // every warp runs through all feature blocks without a barrier and the sums are reduced once at the end; the pair
+    // groups rotate over the warps from block to block so that the warps' totals are equal.  Otherwise (large L) one
+    // block's sums at a time, behind block barriers.
+    const bool pfree = p.pred_free != 0;
+    const int pslots = pfree ? L : 8;
+    double* z0s = part + (size_t)NWP * pslots * 13;   // [2L] projections of sigma point 0 (pfree only)
+    auto emit = [&](int j, int slot, double zx0, double zy0) {
+      double t[13];
+#pragma unroll
+      for (int c = 0; c < 13; ++c) {
+        double a = 0.0;
+        for (int w = 0; w < NWP; ++w) a += part[(size_t)(w * pslots + slot) * 13 + c];
+        t[c] = a;
+      }
+      const double bb0 = p.wi * t[0], bb1 = p.wi * t[1];
+      const double hx = p.Wsum * zx0 + bb0, hy = p.Wsum * zy0 + bb1;
+      hb[2 * j] = hx;
+      hb[2 * j + 1] = hy;
+      const bool v = (hx != 0.0) && (hy != 0.0);  // :1727
+      vis[j] = v ? 1 : 0;
+      if (!v) flags |= SRUKF_FLAG_INVISIBLE;
+      // si = R of the 2Na x 2 QR (:1771-1775) == Cholesky factor of wi * sum b b^T
+      const double g00 = p.wi * t[2], g01 = p.wi * t[3], g11 = p.wi * t[4];
+      const double r00 = sqrt(g00);
+      const double r01 = (r00 > 0.0) ? g01 / r00 : 0.0;
+      const double r11 = sqrt(fmax(g11 - r01 * r01, 0.0));
+      sig[4 * j + 0] = r00; sig[4 * j + 1] = r01; sig[4 * j + 2] = 0.0; sig[4 * j + 3] = r11;
+      // sum_i w_i (z_i - hbar): multiplies the accumulated state shift in :2030
+      csh[2 * j] = (p.wc0 - p.wm0) * (zx0 - hx) + (1.0 - p.Wsum) * hx;
+      csh[2 * j + 1] = (p.wc0 - p.wm0) * (zy0 - hy) + (1.0 - p.Wsum) * hy;
+      // robot rows of Pxy (:2028-2037) about the predicted means
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double abar = xs[n - 4 + c] - rs[c];  // = wi * sum a_i (+ (Wsum-1) r0, zero analytically)
+        pr[(size_t)c * 2 * L + 2 * j] = p.wi * t[5 + 2 * c] + cab * abar * bb0;
+        pr[(size_t)c * 2 * L + 2 * j + 1] = p.wi * t[6 + 2 * c] + cab * abar * bb1;
+      }
+    };
+    int blk = 0;
     for (int j0 = 0; j0 < L;) {
       const int rem = L - j0;
       const int lb = (rem >= 8) ? 3 : ((rem >= 4) ? 2 : ((rem >= 2) ? 1 : 0));
@@ -303,7 +343,7 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
       double snx[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) snx[c] = 0.0;
-      const int kfirst = warp * gl + g;
+      const int kfirst = ((warp + (pfree ? blk : 0)) % NWP) * gl + g;
       if (kfirst <= kown) {
         const double* srow = Sg + (size_t)kfirst * np + 6 * j;
 #pragma unroll
@@ -361,43 +401,22 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
         for (int o = 16; o >= bw; o >>= 1) t[c] += __shfl_xor_sync(0xffffffffu, t[c], o);
       }
       if (g == 0) {
+        double* pp = part + (size_t)(warp * pslots + (pfree ? j : jl)) * 13;
 #pragma unroll
-        for (int c = 0; c < 13; ++c) part[(warp * 8 + jl) * 13 + c] = t[c];
+        for (int c = 0; c < 13; ++c) pp[c] = t[c];
+        if (pfree && warp == 0) { z0s[2 * j] = zx0; z0s[2 * j + 1] = zy0; }
       }
-      __syncthreads();
-      if (tid < bw) {   // warp 0, g == 0: this thread's own feature j = j0 + tid, zx0 / zy0 are in its registers
-#pragma unroll
-        for (int c = 0; c < 13; ++c) {
-          double a = 0.0;
-          for (int w = 0; w < NWP; ++w) a += part[(w * 8 + tid) * 13 + c];
-          t[c] = a;
-        }
-        const double bb0 = p.wi * t[0], bb1 = p.wi * t[1];
-        const double hx = p.Wsum * zx0 + bb0, hy = p.Wsum * zy0 + bb1;
-        hb[2 * j] = hx;
-        hb[2 * j + 1] = hy;
-        const bool v = (hx != 0.0) && (hy != 0.0);  // :1727
-        vis[j] = v ? 1 : 0;
-        if (!v) flags |= SRUKF_FLAG_INVISIBLE;
-        // si = R of the 2Na x 2 QR (:1771-1775) == Cholesky factor of wi * sum b b^T
-        const double g00 = p.wi * t[2], g01 = p.wi * t[3], g11 = p.wi * t[4];
-        const double r00 = sqrt(g00);
-        const double r01 = (r00 > 0.0) ? g01 / r00 : 0.0;
-        const double r11 = sqrt(fmax(g11 - r01 * r01, 0.0));
-        sig[4 * j + 0] = r00; sig[4 * j + 1] = r01; sig[4 * j + 2] = 0.0; sig[4 * j + 3] = r11;
-        // sum_i w_i (z_i - hbar): multiplies the accumulated state shift in :2030
-        csh[2 * j] = (p.wc0 - p.wm0) * (zx0 - hx) + (1.0 - p.Wsum) * hx;
-        csh[2 * j + 1] = (p.wc0 - p.wm0) * (zy0 - hy) + (1.0 - p.Wsum) * hy;
-        // robot rows of Pxy (:2028-2037) about the predicted means
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double abar = xs[n - 4 + c] - rs[c];  // = wi * sum a_i (+ (Wsum-1) r0, zero analytically)
-          pr[(size_t)c * 2 * L + 2 * j] = p.wi * t[5 + 2 * c] + cab * abar * bb0;
-          pr[(size_t)c * 2 * L + 2 * j + 1] = p.wi * t[6 + 2 * c] + cab * abar * bb1;
-        }
+      if (!pfree) {   // small partial-sum array: reduce and emit this block now, behind block barriers
+        __syncthreads();
+        if (tid < bw) emit(j, tid, zx0, zy0);   // warp 0, g == 0: this thread's own feature j = j0 + tid
+        __syncthreads();   // part is reused by the next feature block
       }
-      __syncthreads();   // part is reused by the next feature block
       j0 += bw;
+      ++blk;
+    }
+    if (pfree) {   // every warp ran through all feature blocks without a barrier; one reduction at the end
+      __syncthreads();
+      for (int j = tid; j < L; j += NT) emit(j, j, z0s[2 * j], z0s[2 * j + 1]);
     }
   }
   // flags
@@ -2243,9 +2262,19 @@ int gain_dz_box(const DevParams& p) {
   if (SRUKF_PAD == 4) return gain_variant(p) == 1 ? 60 : 36;
   return gain_variant(p) == 1 ? 72 : 40;
 }
+// measurement step of k_predict without block barriers: the per-warp partial sums of ALL features stay in shared memory
+// (8 x L x 13 doubles + 2L) if the kernel then still fits twice on an SM
+bool predict_free(const DevParams& p) {
+  const size_t base = (size_t)p.n + (size_t)p.P * 8 + 40;
+  const size_t need = (size_t)(NT / 32) * p.L * 13 + 2 * (size_t)p.L;
+  return sizeof(double) * (base + need) <= 110 * 1024;
+}
 size_t predict_smem_bytes(const DevParams& p) {
   size_t work = (size_t)(p.n + 10) * 4;                        // motion step: T
-  if (work < (size_t)(NT / 32) * 8 * 13) work = (size_t)(NT / 32) * 8 * 13;   // measurement step: per-warp partial sums
+  size_t part = (size_t)(NT / 32) * 8 * 13;                    // measurement step: per-warp partial sums of one block ..
+  if (predict_free(p) && part < (size_t)(NT / 32) * p.L * 13 + 2 * (size_t)p.L)
+    part = (size_t)(NT / 32) * p.L * 13 + 2 * (size_t)p.L;     // .. or of all features (barrier-free mode)
+  if (work < part) work = part;
   return sizeof(double) * ((size_t)p.n + (size_t)p.P * 8 + 40 + work);
 }
 // output strips (8 state rows each) one k_gain CTA owns: NW * MQ of the variant; wider maps are row-split over gridDim.y
