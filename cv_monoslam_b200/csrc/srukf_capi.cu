@@ -24,10 +24,11 @@ struct StepPtrs {
   double* G2; int n_new;
   double* Gp;
   double* Ed;
+  double* Useq;
   int* nact;
 };
 // tensor-map table layout and box geometry (must match srukf_kernels.cu)
-constexpr int TM_S0 = 0, TM_S1 = 8, TM_UT = 16, TM_DZ = 24, TM_DZ_ALL = 25, TM_COUNT = 26, TM_ROWSETS = 8;
+constexpr int TM_S0 = 0, TM_S1 = 8, TM_UT = 16, TM_DZ = 24, TM_DZ_ALL = 25, TM_USEQ = 26, TM_COUNT = 34, TM_ROWSETS = 8;
 #ifndef SRUKF_TW
 #define SRUKF_TW 64
 #endif
@@ -49,6 +50,8 @@ void launch_predict(const DevParams& p, const StepPtrs& q, int nblocks, bool mot
 void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st);
 void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st);
 void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, int use_worklist, cudaStream_t st);
+void launch_update_seq(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st);
+bool update_seq_available(const DevParams& p);
 void launch_import(const DevParams& p, int nb, int fmt, const double* ext, double* bp, cudaStream_t st);
 void launch_export(const DevParams& p, int nb, int fmt, const double* bp, double* ext, cudaStream_t st);
 void launch_form_P(const DevParams& p, int b0, int nb, double* S, double* Pd, cudaStream_t st);
@@ -116,6 +119,7 @@ struct srukf_handle {
   double *dZ = nullptr, *U = nullptr, *G = nullptr;
   double* G2 = nullptr;    // scratch of the NEED_REORDER update (allocated on first use)
   double* Gp = nullptr;    // carried covariance of the reference-order fallback, one packed matrix per fallback CTA
+  double* Useq = nullptr;  // U rows of the column group a bisection pass works on, [gslots][Lc][np]
   int gslots = 0;          // CTAs (and G scratch slots) of the reference-order fallback kernel
   int* worklist = nullptr;
   int* nact = nullptr;     // [chunk] per-filter count of features used by k_gain
@@ -272,6 +276,8 @@ static int build_tensor_maps(srukf_handle* h, double* sbuf0, double* sbuf1) {
     hm[TM_S1 + r] = hm[TM_S0 + r];   // in-place update: "old" and "new" factor are the same buffer
     (void)sbuf1;
     if ((rc = encode_map(&hm[TM_UT + r], h->U, p.np, p.Lc, h->chunk, TP, 8 * (r + 1)))) return rc;
+    if (h->Useq) { if ((rc = encode_map(&hm[TM_USEQ + r], h->Useq, p.np, p.Lc, h->gslots, TP, 8 * (r + 1)))) return rc; }
+    else hm[TM_USEQ + r] = hm[TM_UT + r];
   }
   const uint32_t bpb = (uint32_t)gain_dz_box(p);
   if ((rc = encode_map(&hm[TM_DZ], h->dZ, p.Lc, p.np, h->chunk, bpb, 8))) return rc;
@@ -348,10 +354,17 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   if (chunk >= 592) chunk -= chunk % 296;  // whole waves of two CTAs per SM
   h->chunk = (int)chunk;
   h->gslots = (int)(chunk < 148 ? chunk : 148);
+  if (prm.downdate_mode == 0 && update_seq_available(p) && chunk > 148) h->gslots = (int)(chunk < 296 ? chunk : 296);
   CUH(cudaMalloc(&h->dZ, sizeof(double) * (size_t)chunk * p.np * p.Lc));
   CUH(cudaMalloc(&h->U, sizeof(double) * (size_t)chunk * p.Lc * p.np));
   CUH(cudaMalloc(&h->G, sizeof(double) * (size_t)h->gslots * p.ntri));
-  if (prm.downdate_mode == 0) CUH(cudaMalloc(&h->Gp, sizeof(double) * (size_t)h->gslots * p.ntri));
+  if (prm.downdate_mode == 0) {
+    CUH(cudaMalloc(&h->Gp, sizeof(double) * (size_t)h->gslots * p.ntri));
+    if (update_seq_available(p)) {
+      CUH(cudaMalloc(&h->Useq, sizeof(double) * (size_t)h->gslots * p.Lc * p.np));
+      CUH(cudaMemsetAsync(h->Useq, 0, sizeof(double) * (size_t)h->gslots * p.Lc * p.np, h->stream));
+    }
+  }
   CUH(cudaMalloc(&h->worklist, sizeof(int) * ((size_t)chunk + 1)));
   CUH(cudaMalloc(&h->nact, sizeof(int) * (size_t)chunk));
   CUH(cudaMemsetAsync(h->nact, 0, sizeof(int) * (size_t)chunk, h->stream));
@@ -381,7 +394,7 @@ int srukf_destroy(srukf_t* h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
   for (cudaEvent_t e : {h->ev_in[0], h->ev_in[1], h->ev_done[0], h->ev_done[1], h->ev_xs, h->ev_xd}) if (e) cudaEventDestroy(e);
-  void* ptrs[] = {h->Gp, h->u_in[1], h->z_in[1], h->m_in[1], h->x_stage, h->nact, h->G2, h->Pd, h->tmaps, h->dbg, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+  void* ptrs[] = {h->Useq, h->Gp, h->u_in[1], h->z_in[1], h->m_in[1], h->x_stage, h->nact, h->G2, h->Pd, h->tmaps, h->dbg, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -398,7 +411,7 @@ static StepPtrs base_ptrs(srukf_t* h) {
   q.S2 = h->S; q.worklist = h->worklist; q.rel0 = 0; q.dbg = h->dbg;
   q.tmaps = h->tmaps; q.sbuf = 0; q.tm_dz = TM_DZ; q.dz_filter0 = 0;
   q.Pd = h->Pd; q.Pd2 = h->Pd; q.Ed = h->Ed; q.carry_p = (h->prm.downdate_mode == 0) ? 1 : 0;
-  q.G2 = h->G2; q.n_new = 0; q.nact = h->nact; q.Gp = h->Gp;
+  q.G2 = h->G2; q.n_new = 0; q.nact = h->nact; q.Gp = h->Gp; q.Useq = h->Useq;
   return q;
 }
 
@@ -645,7 +658,10 @@ static void run_update(srukf_t* h, StepPtrs q, int b0, int nb) {
   if (h->prm.downdate_mode == 0) {
     cudaMemsetAsync(h->worklist, 0, sizeof(int), h->stream);
     launch_update(h->p, q, nb, h->stream);
-    launch_downdate(h->p, q, h->gslots, 1, 1, h->stream);  // reference-order redo of flagged filters (usually none)
+    // redo of the filters the guard queued (usually none): bisection over column groups on the tensor pipe, or the
+    // literal per-column sequence where that kernel is not built (wide maps)
+    if (h->Useq) launch_update_seq(h->p, q, h->gslots, h->stream);
+    else launch_downdate(h->p, q, h->gslots < 148 ? h->gslots : 148, 1, 1, h->stream);
     h->launches += 2;
   } else {
     for (int r0 = 0; r0 < nb; r0 += h->gslots) {

@@ -57,6 +57,7 @@ struct StepPtrs {
   int n_new;              // m_nFilters: the last n_new features were added on the previous frame (mode 3)
   double* Gp;             // [gslots][ntri] carried covariance of the reference-order fallback (fused mode only)
   double* Ed;             // [B][np] E_j = d_j - c_jj of the last fused update (the fallback rebuilds P_old from it)
+  double* Useq;           // [gslots][Lc][np] U rows of the group a bisection pass of k_update_seq works on
   int* nact;              // [chunk] features k_gain actually used (matched && visible && det(si) != 0): k_update and
                           // k_downdate take "no update this frame" (:2050) from the same count
 };
@@ -465,6 +466,7 @@ constexpr int TM_S0 = 0;    // +0..7: S buffer 0, boxes of 8/16/../64 rows x TP 
 constexpr int TM_S1 = 8;    // +0..7: S buffer 1
 constexpr int TM_UT = 16;   // +0..7: Ut scratch
 // 24: dZ scratch (chunk), box 8 rows x BP_B columns; 25: dZ of the whole batch (split API) -- see StepPtrs::tm_dz
+constexpr int TM_USEQ = 26; // +0..7: per-CTA U-row scratch of k_update_seq
 
 
 __host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -1423,6 +1425,332 @@ __device__ void reorder_project(const DevParams& p, int M, double* G, double* G2
 }
 
 // -------------------------------------------------------------------------------------------------
+// k_update_seq -- the guard's fallback on the tensor pipe.
+//
+// A filter lands here when the one-shot factorisation of P - U U^T (all 2L columns at once, k_update) could not be
+// proven equal to the reference's column-by-column sequence (SLAM.cpp:2116-2153).  The equivalence argument of k_update
+// holds for ANY group of consecutive columns: if the modified Cholesky of P - U_g U_g^T needs no pivot modification
+// beyond the EPSILON floor and GMW's theta^2/beta^2 candidate never exceeds a pivot, the group's one-shot result IS the
+// sequential result.  So the columns are processed in groups by bisection: a group is one pass of the same blocked
+// DMMA factorisation as k_update (in place, its U rows gathered into a per-CTA scratch); a pass that trips the guard
+// is undone (the carried covariance is restored from a packed copy) and the group is split; a single column that
+// still trips the guard is the reference's literal step, G = P - u u^T and the unblocked modified Cholesky
+// (mchol_core).  A filter with one genuinely bad column costs ~2 log2(2L) passes and one literal column instead of 2L
+// literal columns.  One CTA per queued filter (grid-stride over the work list), 8 or 16 warps as k_update.
+// -------------------------------------------------------------------------------------------------
+// lower triangle + diagonal of the square buffer <-> packed columns
+__device__ __noinline__ void seq_pack_P(int n, int np, const double* Sb, const double* Pd, double* Pc) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int k = warp; k < n; k += nw) {
+    double* col = Pc + tri_off(k, n);
+    for (int i = k + lane; i < n; i += 32) col[i - k] = (i == k) ? Pd[k] : Sb[(size_t)i * np + k];
+  }
+}
+__device__ __noinline__ void seq_unpack_P(int n, int np, const double* Pc, double* Sb, double* Pd) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int k = warp; k < n; k += nw) {
+    const double* col = Pc + tri_off(k, n);
+    for (int i = k + lane; i < n; i += 32) {
+      if (i == k) Pd[k] = col[0];
+      else Sb[(size_t)i * np + k] = col[i - k];
+    }
+  }
+}
+// P_old = G + U U^T with G = (lower triangle, Pd - E) left by the fused pass; written to the buffer and to Pc
+__device__ __noinline__ void seq_rebuild_P(int n, int np, int ncolsU, double* Sb, double* Pd, const double* Ed,
+                                           const double* Ut, double* Pc) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int k = warp; k < n; k += nw) {
+    double* col = Pc + tri_off(k, n);
+    for (int i = k + lane; i < n; i += 32) {
+      double uu = 0.0;
+      for (int c = 0; c < ncolsU; ++c) uu = fma(Ut[(size_t)c * np + i], Ut[(size_t)c * np + k], uu);
+      const double v = ((i == k) ? Pd[k] - Ed[k] : Sb[(size_t)i * np + k]) + uu;
+      col[i - k] = v;
+      if (i != k) Sb[(size_t)i * np + k] = v;
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < n; k += blockDim.x) Pd[k] = Pc[tri_off(k, n)];
+}
+// the reference's literal step for one column (:2149-2152): Pc <- Pc - u u^T, S <- modifiedCholesky(Pc), Pc <- Pc + E
+__device__ __noinline__ void seq_literal_column(int n, int np, double eps, const double* u, double* Pc, double* G, double* Sb,
+                                                double* Pd, double* wcol, double* red, uint32_t& flags) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;   // NT threads (k_update_seq is built for 8 warps)
+  for (int k = warp; k < n; k += NT / 32) {
+    double* col = Pc + tri_off(k, n);
+    double* gcol = G + tri_off(k, n);
+    const double uk = u[k];
+    for (int i = k + lane; i < n; i += 32) {
+      const double v = fma(-uk, u[i], col[i - k]);
+      col[i - k] = v;
+      gcol[i - k] = v;
+    }
+  }
+  __syncthreads();
+  double* evec = red + 40;
+  mchol_core(n, np, eps, G, Sb, wcol, red, flags, evec);
+  __syncthreads();
+  for (int k = tid; k < n; k += NT) Pc[tri_off(k, n)] += evec[k];
+  __syncthreads();
+  seq_unpack_P(n, np, Pc, Sb, Pd);
+  __syncthreads();
+}
+
+template <int NW, int MQ, int NBT, int URW>
+__global__ void __launch_bounds__(NW * 32, 1) k_update_seq(DevParams p, StepPtrs q) {
+  constexpr int NTH = NW * 32;
+  constexpr int CPP = NBT + 1, WDP = NBT + 1;
+  static_assert(MQ <= MAXQ && NW * 32 == NT, "the bisection fallback is built for the 8-warp, 5-slot variant");
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.n, np = p.np, L = p.L;
+  const CUtensorMap* tmS = q.tmaps + TM_S0;
+  const CUtensorMap* tmU = q.tmaps + TM_USEQ;
+  const int sdoubles = upd_stage_doubles(np, URW);
+  size_t off = 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * UNS * sizeof(uint64_t));
+  double* Wd = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NBT * WDP;
+  double* dsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NBT;
+  double* sdsm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NBT;
+  double* esm = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NBT;
+  double* gdiag = reinterpret_cast<double*>(smraw + off); off += sizeof(double) * NBT;
+  double* red = reinterpret_cast<double*>(smraw + off); off = (off + sizeof(double) * 40 + 127) & ~(size_t)127;
+  double* Xs = reinterpret_cast<double*>(smraw + off);   // ring, aliased by the panel Cp and by the literal step's vectors
+  double* Cp = Xs;
+  {
+    const size_t ring = (size_t)UNS * sdoubles, panel = (size_t)np * CPP;
+    off += sizeof(double) * (ring > panel ? ring : panel);
+  }
+  int* cols = reinterpret_cast<int*>(smraw + off); off += sizeof(int) * (size_t)p.Lc;   // U columns of the active features
+  int* stk = reinterpret_cast<int*>(smraw + off);                                       // [2][32] bisection stack + [8] scalars
+  int* sc = stk + 64;   // sc[0] = number of columns, sc[1] = stack depth, sc[2] = pass verdict
+  Ring ring;
+  ring_init<NW, UNS>(ring, bars);
+
+  double* Pc = q.Gp + (size_t)blockIdx.x * p.ntri;
+  double* Gs = q.G + (size_t)blockIdx.x * p.ntri;
+  double* Useq = q.Useq + (size_t)blockIdx.x * p.Lc * np;
+  const int nitems = q.worklist[0];
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int rel = q.worklist[1 + item];
+    const int b = q.chunk0 + rel;
+    if (q.nact[rel] == 0) continue;
+    double* Sb = q.S + (size_t)b * p.nbp;
+    double* Pd = q.Pd + (size_t)b * np;
+    const double* Ut = q.U + (size_t)rel * p.Lc * np;
+    uint32_t flags = 0;
+    if (tid == 0) {
+      int nc = 0;
+      for (int j = 0; j < L; ++j)
+        if (q.matched[(size_t)b * L + j] && q.visible[(size_t)b * L + j]) { cols[nc++] = 2 * j; cols[nc++] = 2 * j + 1; }
+      sc[0] = nc;
+      // the full group has already failed in k_update (or is forced to count as failed): start with its halves
+      const int mid = nc / 2;
+      int d = 0;
+      if (nc - mid > 0) { stk[d] = mid; stk[32 + d] = nc; ++d; }
+      if (mid > 0) { stk[d] = 0; stk[32 + d] = mid; ++d; }
+      sc[1] = d;
+    }
+    seq_rebuild_P(n, np, 2 * L, Sb, Pd, q.Ed + (size_t)b * np, Ut, Pc);
+    __syncthreads();
+    const int nc = sc[0];
+    // measurement knob: pretend one pseudo-random column is a genuinely bad one
+    const int forced_col = (p.force_fb_ppm > 0 && !(q.flags[b] & SRUKF_FLAG_GMW_MODIFIED)) ? (int)(((unsigned)b * 40503u) % (unsigned)nc) : -1;
+
+    while (sc[1] > 0) {
+      __syncthreads();
+      const int d = sc[1] - 1;
+      const int lo = stk[d], hi = stk[32 + d];
+      __syncthreads();
+      if (tid == 0) sc[1] = d;
+      const int m = hi - lo;
+      const int rowsB = (m + 7) & ~7;
+      // gather the group's U columns (rows of Ut) into the scratch, zero rows up to a multiple of 8
+      for (int i = tid; i < rowsB * np; i += NTH) {
+        const int r = i / np, c = i - r * np;
+        Useq[i] = (r < m) ? Ut[(size_t)cols[lo + r] * np + c] : 0.0;
+      }
+      fence_proxy_async();
+      __syncthreads();
+
+      // ---------------- one pass: the panel loop of k_update, in place, U rows from Useq ----------------
+      double gmax = -1.0e300, zmax = 0.0, tmax = 0.0;
+      uint32_t pflags = 0;
+      for (int J0 = 0; J0 < np; J0 += NBT) {
+        const int nbe = (np - J0 < NBT) ? (np - J0) : NBT;
+        const int R = np - J0;
+        const int nt = nbe / 8;
+        const int nbx = ntiles(R);
+        const int nstrip = R / 8;
+        const int nq_w = (nstrip > warp) ? (nstrip - warp - 1) / NW + 1 : 0;
+        int rpc = (sdoubles / (nbx * TP)) & ~7;
+        if (rpc > SRUKF_UPD_MAXROWS) rpc = SRUKF_UPD_MAXROWS;
+        const int rowsC = J0;
+        const int cB = (rowsB + rpc - 1) / rpc, cC = (rowsC + rpc - 1) / rpc;
+        const int nchunks = cB + cC;
+        double acc[MQ][NBT / 8][2];
+        auto chunk_rows = [&](int t, int& row0) -> int {
+          if (t < cB) { row0 = t * rpc; return (rowsB - row0 < rpc) ? rowsB - row0 : rpc; }
+          row0 = (t - cB) * rpc;
+          return (rowsC - row0 < rpc) ? rowsC - row0 : rpc;
+        };
+        auto produce = [&](int t) {
+          int row0;
+          const int nrows = chunk_rows(t, row0);
+          const int st = ring_acquire<UNS>(ring, (uint32_t)(nbx * nrows * TP * sizeof(double)));
+          const CUtensorMap* tm = ((t < cB) ? tmU : tmS) + (nrows / 8 - 1);
+          const int c2 = (t < cB) ? (int)blockIdx.x : b;
+          double* dst = Xs + (size_t)st * sdoubles;
+          for (int j = 0; j < nbx; ++j) tma_load_3d(dst + (size_t)j * nrows * TP, tm, J0 + TW * j, row0, c2, ring.full + st);
+        };
+        auto consume = [&](int t0, int t1) {
+          for (int t = t0; t < t1; ++t) {
+            if (t + UNS - 1 < nchunks) {
+              if (ring_my_turn<NW>(ring)) produce(t + UNS - 1);
+              ring_next(ring);
+            }
+            int row0;
+            const int nrows = chunk_rows(t, row0);
+            const int st = ring_wait<UNS>(ring);
+            const double* xs_ = Xs + (size_t)st * sdoubles;
+            mma_chunk_any<NW, MQ, NBT / 8, false>(acc, 0, nq_w, nt, xs_, nrows * TP, 0, xs_, TP, nullptr, nrows / 4, lane, warp);
+            ring_release<UNS>(ring);
+          }
+        };
+        for (int t = 0; t < UNS - 1 && t < nchunks; ++t) {
+          if (ring_my_turn<NW>(ring)) {
+            fence_proxy_async();
+            produce(t);
+          }
+          ring_next(ring);
+        }
+#pragma unroll
+        for (int qq = 0; qq < MQ; ++qq) {
+          const int rs = warp + NW * qq;
+          const int i = J0 + 8 * rs + (lane >> 2);
+          const double* prow = Sb + (size_t)i * np;
+#pragma unroll
+          for (int tt = 0; tt < NBT / 8; ++tt) {
+            double v0 = 0.0, v1 = 0.0;
+            if (rs < nstrip && tt < nt) {
+              const int j = J0 + 8 * tt + 2 * (lane & 3);
+              if (rs > tt) {
+                const double2 v = *reinterpret_cast<const double2*>(prow + j);
+                v0 = v.x; v1 = v.y;
+              } else if (rs == tt) {
+                v0 = (i > j) ? prow[j] : ((i == j) ? Pd[i] : 0.0);
+                v1 = (i > j + 1) ? prow[j + 1] : ((i == j + 1) ? Pd[i] : 0.0);
+              }
+            }
+            acc[qq][tt][0] = -v0;
+            acc[qq][tt][1] = -v1;
+          }
+        }
+        consume(0, cB);
+#pragma unroll
+        for (int qq = 0; qq < MQ; ++qq) {
+          const int rs = warp + NW * qq;
+          if (rs < nstrip) {
+            const int i = J0 + 8 * rs + (lane >> 2);
+            double* prow = Sb + (size_t)i * np;
+#pragma unroll
+            for (int tt = 0; tt < NBT / 8; ++tt) {
+              if (tt < nt) {
+                const int j = J0 + 8 * tt + 2 * (lane & 3);
+                const double g0 = -acc[qq][tt][0], g1 = -acc[qq][tt][1];
+                if (rs > tt) {
+                  *reinterpret_cast<double2*>(prow + j) = make_double2(g0, g1);
+                  zmax = fmax(zmax, fmax(g0, g1));
+                } else if (rs == tt) {
+                  if (i > j) prow[j] = g0; else if (i == j) gdiag[i - J0] = g0;
+                  if (i > j + 1) prow[j + 1] = g1; else if (i == j + 1) gdiag[i - J0] = g1;
+                  if (i < n) {
+                    if (i == j) gmax = fmax(gmax, g0); else if (i > j) zmax = fmax(zmax, g0);
+                    if (i == j + 1) gmax = fmax(gmax, g1); else if (i > j + 1) zmax = fmax(zmax, g1);
+                  }
+                }
+              }
+            }
+          }
+        }
+        consume(cB, nchunks);
+#pragma unroll
+        for (int qq = 0; qq < MQ; ++qq)
+#pragma unroll
+          for (int t = 0; t < NBT / 8; ++t) { acc[qq][t][0] = -acc[qq][t][0]; acc[qq][t][1] = -acc[qq][t][1]; }
+        __syncthreads();
+#pragma unroll
+        for (int qq = 0; qq < MQ; ++qq) {
+          const int rs = warp + NW * qq;
+          if (rs < nstrip) {
+            const int ri = 8 * rs + (lane >> 2);
+#pragma unroll
+            for (int tt = 0; tt < NBT / 8; ++tt)
+              if (tt < nt) {
+                double* dst = Cp + (size_t)ri * CPP + 8 * tt + 2 * (lane & 3);
+                dst[0] = acc[qq][tt][0];
+                dst[1] = acc[qq][tt][1];
+              }
+          }
+        }
+        __syncthreads();
+        factor_panel<NW, NBT>(Cp, Wd, dsm, sdsm, esm, R, nbe, J0, n, p.epsilon, pflags);
+        if (tid < nbe) Pd[J0 + tid] = gdiag[tid] + esm[tid];
+        for (int i = tid; i < R; i += NTH) {
+          const double* crow = Cp + (size_t)i * CPP;
+          double* dcol = Sb + (size_t)J0 * np + J0 + i;
+          const int jmax = (i < nbe - 1) ? i : nbe - 1;
+          const bool real = (J0 + i < n);
+          for (int j = 0; j <= jmax; ++j) {
+            const double sdj = sdsm[j];
+            const double v = (i == j) ? sdj : sdj * crow[j];
+            dcol[(size_t)j * np] = v;
+            if (i > j && real) tmax = fmax(tmax, fabs(v));
+          }
+        }
+        fence_proxy_async();
+        __syncthreads();
+      }
+      // ---------------- verdict of the pass ----------------
+      gmax = block_max<NTH>(gmax, red);
+      zmax = block_max<NTH>(zmax, red);
+      tmax = block_max<NTH>(tmax, red);
+      double nu = sqrt((double)n * n - 1.0);
+      if (nu < 1.0) nu = 1.0;
+      const double beta2 = fmax(fmax(gmax, zmax / nu), 1e-15);
+      int bad = ((pflags & (SRUKF_FLAG_GMW_MODIFIED | SRUKF_FLAG_NAN)) || (tid == 0 && tmax * tmax > beta2)) ? 1 : 0;
+      if (forced_col >= lo && forced_col < hi) bad = 1;
+      bad = __syncthreads_or(bad);
+      if (!bad) {
+        flags |= pflags;                    // (only the EPSILON-floor flag can be in there)
+        seq_pack_P(n, np, Sb, Pd, Pc);      // commit: the carried covariance after this group
+        __syncthreads();
+      } else {
+        seq_unpack_P(n, np, Pc, Sb, Pd);    // undo: the pass overwrote the covariance in place
+        __syncthreads();
+        if (m == 1) {
+          // wcol | red2 | evec alias the (now free) ring
+          seq_literal_column(n, np, p.epsilon, Ut + (size_t)cols[lo] * np, Pc, Gs, Sb, Pd, Xs, Xs + n, flags);
+        } else if (tid == 0) {
+          const int mid = lo + m / 2;
+          int dd = sc[1];
+          stk[dd] = mid; stk[32 + dd] = hi; ++dd;
+          stk[dd] = lo; stk[32 + dd] = mid; ++dd;
+          sc[1] = dd;
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < n; i += NTH)
+      if (!isfinite(Sb[bp_idx(i, i, np)])) flags |= SRUKF_FLAG_NAN;
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0 && flags) atomicOr(q.flags + b, flags);
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // k_downdate -- GSLCholeskyUpdate, DOWNDATING / NEEDNOT_REORDER (SLAM.cpp:2106-2121,2139-2153), reference order.
 //   mode 1: the reference's sequence: for every matched feature, for each of its 2 U columns,
 //           re-form S^T S, subtract u u^T, re-factorise.
@@ -2305,6 +2633,8 @@ size_t update_smem_bytes(const DevParams& p) {
   size_t panel = (size_t)p.np * (nbt + 1);
   return off + sizeof(double) * (ring > panel ? ring : panel);
 }
+size_t update_seq_smem_bytes(const DevParams& p) { return update_smem_bytes(p) + sizeof(int) * ((size_t)p.Lc + 72); }
+bool update_seq_available(const DevParams& p) { return tile_warps(p) == 8 && !getenv("SRUKF_FALLBACK_LITERAL"); }
 size_t downdate_smem_bytes(const DevParams& p) { return sizeof(double) * (2 * (size_t)p.n + 40); }
 
 // The dynamic shared-memory limit is a per-function, per-device attribute shared by every handle of the process:
@@ -2326,7 +2656,7 @@ cudaError_t configure_kernels(const DevParams&) {
   SRUKF_SET((k_update<2, false>)) SRUKF_SET((k_update<4, false>)) SRUKF_SET((k_update<16, false, 10, 16, 8>))
   SRUKF_SET((k_update<8, false, 1>)) SRUKF_SET((k_update<8, false, 2>)) SRUKF_SET((k_update<8, false, 3>))
   SRUKF_SET(k_downdate) SRUKF_SET(k_init_features) SRUKF_SET(k_add_features) SRUKF_SET(k_delete_feature)
-  SRUKF_SET(k_chol_update) SRUKF_SET(k_mchol_batch)
+  SRUKF_SET(k_chol_update) SRUKF_SET(k_mchol_batch) SRUKF_SET((k_update_seq<8, MAXQ, NB, SRUKF_UPD_ROWS>))
 #undef SRUKF_SET
   if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
@@ -2370,6 +2700,9 @@ void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStrea
       else k_update<16, false><<<nblocks, 512, smem, st>>>(p, q);
       break;
   }
+}
+void launch_update_seq(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
+  k_update_seq<8, MAXQ, NB, SRUKF_UPD_ROWS><<<nblocks, 256, update_seq_smem_bytes(p), st>>>(p, q);
 }
 void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, int use_worklist, cudaStream_t st) {
   k_downdate<<<nblocks, NT, downdate_smem_bytes(p), st>>>(p, q, mode, use_worklist);

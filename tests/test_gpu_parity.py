@@ -537,6 +537,20 @@ def test_adversarial_indefinite_downdate_falls_back_to_reference_order(gpu, orac
         g.close()
 
 
+@pytest.mark.parametrize("L,B,steps", [(8, 6, 3), (50, 2, 1)])
+def test_forced_fallback_takes_the_bisection_path_and_matches_the_oracle(gpu, oracle, L, B, steps, monkeypatch):
+    """SRUKF_FORCE_FALLBACK_PPM (the knob behind bench.py --adversarial-frac) sends every filter through the guard's
+    fallback although nothing is wrong: column groups by bisection on the tensor pipe, one pseudo-random column as the
+    reference's literal step.  The result is the reference-order result, so parity must hold as for the fused path."""
+    monkeypatch.setenv("SRUKF_FORCE_FALLBACK_PPM", "1000000")
+    worst, flags, _ = run_against_oracle(gpu, oracle, L, B, steps)
+    assert ((flags & gpu.FLAG_FALLBACK) != 0).all()
+    assert not (flags & gpu.FLAG_NAN).any()
+    monkeypatch.setenv("SRUKF_FALLBACK_LITERAL", "1")        # the literal per-column fallback gives the same answer
+    worst2, flags2, _ = run_against_oracle(gpu, oracle, L, B, 1)
+    assert ((flags2 & gpu.FLAG_FALLBACK) != 0).all()
+
+
 def test_unblocked_one_shot_mode_matches_fused_mode(gpu, oracle):
     """downdate_mode 2 (one unblocked GMW of S^T S - U U^T) is the plain-DFMA cross-check of the DMMA path."""
     run_against_oracle(gpu, oracle, 6, 4, 4, mode_gpu=2)

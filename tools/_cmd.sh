@@ -1,4 +1,9 @@
-nvidia-smi -L | head -3
-timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "sharding" 2>&1 | tail -2
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02t_bench_n2.json 2> gpurun_out/r02t_bench_n2.err; echo "n2 rc=$?"; cat gpurun_out/r02t_bench_n2.json | cut -c1-600
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 3 > gpurun_out/r02t_ref_n2.json 2> gpurun_out/r02t_ref_n2.err; echo "ref n2 rc=$?"; cat gpurun_out/r02t_ref_n2.json | cut -c1-300
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "adversarial or forced_fallback or sequential or literal" 2>&1 | tail -5
+for f in 0.001 0.01; do
+  timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --adversarial-frac $f > gpurun_out/r02x_adv_$f.json 2> gpurun_out/r02x_adv_$f.err; echo "adv $f rc=$?"
+  python - gpurun_out/r02x_adv_$f.json <<'PY'
+import json, sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); k=d["roofline"]["kernel_ms"]; st=d["steps"]
+print("  value", round(d["value"]), "ms/step", round(d["ms_per_step"],2), {a: round(b/st,2) for a,b in k.items()}, "n_fallback", d["stats"]["n_fallback"], "rmse", d["stats"]["rmse_xy"], "nees", d["stats"]["nees"], "flags", d["stats"]["flag_or"])
+PY
+done
