@@ -281,6 +281,7 @@ def sweep_point(L, B, steps, warmup, peak, parity_max_L, dev, gentle=False):
     e0.record(st)
     for s in range(warmup, warmup + steps):
         g.SLAM_dev(du[s].data_ptr(), dz[s].data_ptr(), dm[s].data_ptr())
+    g.sync()
     e1.record(st)
     g.sync()
     torch.cuda.synchronize()
@@ -452,6 +453,7 @@ def run(out):
     e0.record(stream)
     for s in range(W, W + K):
         g.SLAM_dev(d_u[s].data_ptr(), d_z[s].data_ptr(), d_m[s].data_ptr())
+    g.sync()          # includes the side stream of the guard's fallback: the timed region ends when ALL the work is done
     e1.record(stream)
     g.sync()
     torch.cuda.synchronize()
@@ -483,6 +485,7 @@ def run(out):
     f0.record(stream)
     for s in range(W, W + K):
         e2e_step(s)
+    g.sync()          # copy / read-back / fallback streams have drained
     f1.record(stream)
     g.sync()
     torch.cuda.synchronize()

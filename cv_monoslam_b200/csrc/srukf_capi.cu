@@ -19,7 +19,7 @@ struct StepPtrs {
   double* hbar; double* si; uint8_t* visible; double* cshift; double* pxyr; double* rsig;
   double* dZ; double* U; double* G; uint32_t* flags; int chunk0;
   double* S2; int* worklist; int rel0; unsigned long long* dbg;
-  const CUtensorMap* tmaps; int sbuf; int tm_dz; int dz_filter0;
+  const CUtensorMap* tmaps; int sbuf; int tm_dz; int tm_ut; int dz_filter0;
   double* Pd; double* Pd2; int carry_p;
   double* G2; int n_new;
   double* Gp;
@@ -28,7 +28,7 @@ struct StepPtrs {
   int* nact;
 };
 // tensor-map table layout and box geometry (must match srukf_kernels.cu)
-constexpr int TM_S0 = 0, TM_S1 = 8, TM_UT = 16, TM_DZ = 24, TM_DZ_ALL = 25, TM_USEQ = 26, TM_COUNT = 34, TM_ROWSETS = 8;
+constexpr int TM_S0 = 0, TM_S1 = 8, TM_UT = 16, TM_DZ = 24, TM_DZ_ALL = 25, TM_USEQ = 26, TM_UT2 = 34, TM_COUNT = 42, TM_ROWSETS = 8;
 #ifndef SRUKF_TW
 #define SRUKF_TW 64
 #endif
@@ -120,6 +120,13 @@ struct srukf_handle {
   double* G2 = nullptr;    // scratch of the NEED_REORDER update (allocated on first use)
   double* Gp = nullptr;    // carried covariance of the reference-order fallback, one packed matrix per fallback CTA
   double* Useq = nullptr;  // U rows of the column group a bisection pass works on, [gslots][Lc][np]
+  // The guard's fallback of chunk i runs on fb_stream while the main stream goes on with chunk i+1; for that the chunk
+  // scratch the fallback reads (U, nact, work list) exists twice and the chunks alternate between the two sets.
+  double* U_set[2] = {nullptr, nullptr}; int* nact_set[2] = {nullptr, nullptr}; int* wl_set[2] = {nullptr, nullptr};
+  cudaStream_t fb_stream = nullptr;
+  cudaEvent_t ev_upd[2] = {nullptr, nullptr}, ev_fb[2] = {nullptr, nullptr};
+  struct { int b0, nb; bool pending; } fbp[2] = {{0, 0, false}, {0, 0, false}};
+  int uset = 0;
   int gslots = 0;          // CTAs (and G scratch slots) of the reference-order fallback kernel
   int* worklist = nullptr;
   int* nact = nullptr;     // [chunk] per-filter count of features used by k_gain
@@ -163,6 +170,16 @@ static void prof_collect(srukf_handle* h) {
   }
   h->ev_used = 0;
   h->ev_kind.clear();
+}
+
+// Outstanding side-stream fallbacks: the main stream waits for the ones that touch filters [b0, b0+nb) (b0 < 0: all)
+static void fb_join(srukf_handle* h, int b0 = -1, int nb = 0) {
+  if (!h->fb_stream) return;
+  for (int s = 0; s < 2; ++s) {
+    if (!h->fbp[s].pending) continue;
+    const bool overlap = b0 < 0 || (h->fbp[s].b0 < b0 + nb && b0 < h->fbp[s].b0 + h->fbp[s].nb);
+    if (overlap) { cudaStreamWaitEvent(h->stream, h->ev_fb[s], 0); h->fbp[s].pending = false; }
+  }
 }
 
 extern "C" {
@@ -278,6 +295,8 @@ static int build_tensor_maps(srukf_handle* h, double* sbuf0, double* sbuf1) {
     if ((rc = encode_map(&hm[TM_UT + r], h->U, p.np, p.Lc, h->chunk, TP, 8 * (r + 1)))) return rc;
     if (h->Useq) { if ((rc = encode_map(&hm[TM_USEQ + r], h->Useq, p.np, p.Lc, h->gslots, TP, 8 * (r + 1)))) return rc; }
     else hm[TM_USEQ + r] = hm[TM_UT + r];
+    if (h->U_set[1]) { if ((rc = encode_map(&hm[TM_UT2 + r], h->U_set[1], p.np, p.Lc, h->chunk, TP, 8 * (r + 1)))) return rc; }
+    else hm[TM_UT2 + r] = hm[TM_UT + r];
   }
   const uint32_t bpb = (uint32_t)gain_dz_box(p);
   if ((rc = encode_map(&hm[TM_DZ], h->dZ, p.Lc, p.np, h->chunk, bpb, 8))) return rc;
@@ -371,6 +390,22 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   CUH(cudaMemsetAsync(h->dZ, 0, sizeof(double) * (size_t)chunk * p.np * p.Lc, h->stream));
   CUH(cudaMemsetAsync(h->U, 0, sizeof(double) * (size_t)chunk * p.Lc * p.np, h->stream));
   CUH(cudaMemsetAsync(h->worklist, 0, sizeof(int) * ((size_t)chunk + 1), h->stream));
+  h->U_set[0] = h->U; h->nact_set[0] = h->nact; h->wl_set[0] = h->worklist;
+  if (h->Useq && chunk < B && !getenv("SRUKF_FALLBACK_INLINE")) {   // several chunks per step: overlap the fallback with the next chunk
+    CUH(cudaMalloc(&h->U_set[1], sizeof(double) * (size_t)chunk * p.Lc * p.np));
+    CUH(cudaMalloc(&h->wl_set[1], sizeof(int) * ((size_t)chunk + 1)));
+    CUH(cudaMalloc(&h->nact_set[1], sizeof(int) * (size_t)chunk));
+    CUH(cudaMemsetAsync(h->U_set[1], 0, sizeof(double) * (size_t)chunk * p.Lc * p.np, h->stream));
+    CUH(cudaMemsetAsync(h->wl_set[1], 0, sizeof(int) * ((size_t)chunk + 1), h->stream));
+    CUH(cudaMemsetAsync(h->nact_set[1], 0, sizeof(int) * (size_t)chunk, h->stream));
+    int lo = 0, hi = 0;
+    CUH(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority: the fallback fills what the main kernels leave
+    CUH(cudaStreamCreateWithPriority(&h->fb_stream, cudaStreamNonBlocking, lo));
+    for (int i = 0; i < 2; ++i) {
+      CUH(cudaEventCreateWithFlags(&h->ev_upd[i], cudaEventDisableTiming));
+      CUH(cudaEventCreateWithFlags(&h->ev_fb[i], cudaEventDisableTiming));
+    }
+  }
   if (const char* e_ = getenv("SRUKF_PHASE_TIMING")) {
     if (e_[0] == '1') {
       CUH(cudaMalloc(&h->dbg, sizeof(unsigned long long) * 16));
@@ -391,10 +426,12 @@ int srukf_destroy(srukf_t* h) {
   if (!h) return SRUKF_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->fb_stream) { cudaStreamSynchronize(h->fb_stream); cudaStreamDestroy(h->fb_stream); }
+  for (cudaEvent_t e : {h->ev_upd[0], h->ev_upd[1], h->ev_fb[0], h->ev_fb[1]}) if (e) cudaEventDestroy(e);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
   for (cudaEvent_t e : {h->ev_in[0], h->ev_in[1], h->ev_done[0], h->ev_done[1], h->ev_xs, h->ev_xd}) if (e) cudaEventDestroy(e);
-  void* ptrs[] = {h->Useq, h->Gp, h->u_in[1], h->z_in[1], h->m_in[1], h->x_stage, h->nact, h->G2, h->Pd, h->tmaps, h->dbg, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
+  void* ptrs[] = {h->U_set[1], h->nact_set[1], h->wl_set[1], h->Useq, h->Gp, h->u_in[1], h->z_in[1], h->m_in[1], h->x_stage, h->nact, h->G2, h->Pd, h->tmaps, h->dbg, h->worklist, h->x, h->S, h->u, h->z, h->matched, h->hbar, h->si, h->cshift, h->pxyr, h->visible, h->flags,
                   h->dZ, h->U, h->G, h->rsig, h->dZ_all, h->U_all, h->G_all, h->perf, h->stats_out, h->truth};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -409,7 +446,7 @@ static StepPtrs base_ptrs(srukf_t* h) {
   q.hbar = h->hbar; q.si = h->si; q.visible = h->visible; q.cshift = h->cshift; q.pxyr = h->pxyr;
   q.rsig = h->rsig; q.dZ = h->dZ; q.U = h->U; q.G = h->G; q.flags = h->flags; q.chunk0 = 0;
   q.S2 = h->S; q.worklist = h->worklist; q.rel0 = 0; q.dbg = h->dbg;
-  q.tmaps = h->tmaps; q.sbuf = 0; q.tm_dz = TM_DZ; q.dz_filter0 = 0;
+  q.tmaps = h->tmaps; q.sbuf = 0; q.tm_dz = TM_DZ; q.tm_ut = TM_UT; q.dz_filter0 = 0;
   q.Pd = h->Pd; q.Pd2 = h->Pd; q.Ed = h->Ed; q.carry_p = (h->prm.downdate_mode == 0) ? 1 : 0;
   q.G2 = h->G2; q.n_new = 0; q.nact = h->nact; q.Gp = h->Gp; q.Useq = h->Useq;
   return q;
@@ -418,6 +455,7 @@ static StepPtrs base_ptrs(srukf_t* h) {
 // external S (fmt 0 dense [B][n][n], fmt 1 upper-packed [B][ntri]) <-> internal layout, staged in slabs <= 256 MiB
 static int transfer_S(srukf_t* h, int fmt, const double* src_host, double* dst_host) {
   const DevParams& p = h->p;
+  fb_join(h);
   const size_t per = sizeof(double) * (fmt ? (size_t)p.ntri : (size_t)p.n * p.n);
   int slab = (int)(((size_t)256 << 20) / per);
   if (slab < 1) slab = 1;
@@ -473,6 +511,7 @@ int srukf_init_features(srukf_t* h, const double* x4, const double* S4, const do
                         double sigma_rho) {
   if (!h || !x4 || !S4 || !keypoints) return fail(SRUKF_EINVAL, "srukf_init_features: null argument");
   CU(cudaSetDevice(h->device));
+  fb_join(h);
   const DevParams& p = h->p;
   const size_t B = (size_t)p.B;
   double wm0, wc0, wi, wi_sr, gamma;
@@ -506,6 +545,8 @@ int srukf_add_features(srukf_t* src, srukf_t* dst, const double* keypoints, doub
     return fail(SRUKF_EINVAL, "srukf_add_features: dst must be another handle on the same device with the same B and more features");
   CU(cudaSetDevice(dst->device));
   CU(cudaStreamSynchronize(src->stream));
+  fb_join(src); fb_join(dst);
+  if (src->fb_stream) CU(cudaStreamSynchronize(src->fb_stream));
   const DevParams& p = dst->p;
   const int ns = src->p.n;
   double wm0, wc0, wi, wi_sr, gamma;
@@ -538,6 +579,8 @@ int srukf_delete_feature(srukf_t* src, srukf_t* dst, const int32_t* ids) {
     if (ids[b] < 0 || ids[b] >= src->p.L) return fail(SRUKF_EINVAL, "srukf_delete_feature: feature id out of range");
   CU(cudaSetDevice(dst->device));
   CU(cudaStreamSynchronize(src->stream));
+  fb_join(src); fb_join(dst);
+  if (src->fb_stream) CU(cudaStreamSynchronize(src->fb_stream));
   const DevParams& p = dst->p;
   const int nblocks = p.B < dst->gslots ? p.B : dst->gslots;
   int* d_ids = nullptr;
@@ -590,6 +633,7 @@ int srukf_predict_motion(srukf_t* h, const double* u) {
   if (!h || !u) return fail(SRUKF_EINVAL, "srukf_predict_motion: null argument");
   h->inputs_dirty = true;
   CU(cudaSetDevice(h->device));
+  fb_join(h);
   int rc = ensure_split_buffers(h);
   if (rc) return rc;
   CU(cudaMemcpyAsync(h->u, u, sizeof(double) * (size_t)h->p.B * 3, cudaMemcpyHostToDevice, h->stream));
@@ -650,18 +694,39 @@ int srukf_chi2_gate(srukf_t* h, const double* z, double threshold, uint8_t* acce
 // gain + covariance update over [b0, b0+nb) with scratch indexed from 0
 static void run_update(srukf_t* h, StepPtrs q, int b0, int nb) {
   q.chunk0 = b0;
+  const bool side = h->fb_stream != nullptr && h->prm.downdate_mode == 0;
+  int set = 0;
+  if (side) {
+    set = h->uset;
+    h->uset ^= 1;
+    if (h->fbp[set].pending) {   // the fallback that still reads this scratch set
+      cudaStreamWaitEvent(h->stream, h->ev_fb[set], 0);
+      h->fbp[set].pending = false;
+    }
+    q.U = h->U_set[set]; q.nact = h->nact_set[set]; q.worklist = h->wl_set[set];
+    q.tm_ut = set ? TM_UT2 : TM_UT;
+  }
   prof_begin(h, 1);
   launch_gain(h->p, q, nb, h->stream);
   prof_end(h);
   h->launches++;
   prof_begin(h, 2);
   if (h->prm.downdate_mode == 0) {
-    cudaMemsetAsync(h->worklist, 0, sizeof(int), h->stream);
+    cudaMemsetAsync(q.worklist, 0, sizeof(int), h->stream);
     launch_update(h->p, q, nb, h->stream);
-    // redo of the filters the guard queued (usually none): bisection over column groups on the tensor pipe, or the
-    // literal per-column sequence where that kernel is not built (wide maps)
-    if (h->Useq) launch_update_seq(h->p, q, h->gslots, h->stream);
-    else launch_downdate(h->p, q, h->gslots < 148 ? h->gslots : 148, 1, 1, h->stream);
+    // redo of the filters the guard queued (usually none): bisection over column groups on the tensor pipe (on the side
+    // stream when the step has several chunks), or the literal per-column sequence where that kernel is not built
+    if (side) {
+      cudaEventRecord(h->ev_upd[set], h->stream);
+      cudaStreamWaitEvent(h->fb_stream, h->ev_upd[set], 0);
+      launch_update_seq(h->p, q, h->gslots, h->fb_stream);
+      cudaEventRecord(h->ev_fb[set], h->fb_stream);
+      h->fbp[set].b0 = b0; h->fbp[set].nb = nb; h->fbp[set].pending = true;
+    } else if (h->Useq) {
+      launch_update_seq(h->p, q, h->gslots, h->stream);
+    } else {
+      launch_downdate(h->p, q, h->gslots < 148 ? h->gslots : 148, 1, 1, h->stream);
+    }
     h->launches += 2;
   } else {
     for (int r0 = 0; r0 < nb; r0 += h->gslots) {
@@ -682,6 +747,7 @@ int srukf_kalman_update(srukf_t* h, const double* z, const uint8_t* matched) {
   if (h->phase != 2) return fail(SRUKF_ESTATE, "srukf_kalman_update: call srukf_predict_measurement first");
   h->inputs_dirty = true;
   CU(cudaSetDevice(h->device));
+  fb_join(h);
   const DevParams& p = h->p;
   CU(cudaMemcpyAsync(h->z, z, sizeof(double) * (size_t)p.B * 2 * p.L, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->matched, matched, (size_t)p.B * p.L, cudaMemcpyHostToDevice, h->stream));
@@ -705,6 +771,7 @@ int srukf_kalman_update_reorder(srukf_t* h, const double* z, const uint8_t* matc
   if (h->phase != 2) return fail(SRUKF_ESTATE, "srukf_kalman_update_reorder: call srukf_predict_measurement first");
   h->inputs_dirty = true;
   CU(cudaSetDevice(h->device));
+  fb_join(h);
   const DevParams& p = h->p;
   if (!h->G2) CU(cudaMalloc(&h->G2, sizeof(double) * (size_t)h->gslots * ((size_t)p.ntri + 2 * (size_t)p.nbp)));
   CU(cudaMemcpyAsync(h->z, z, sizeof(double) * (size_t)p.B * 2 * p.L, cudaMemcpyHostToDevice, h->stream));
@@ -740,6 +807,7 @@ int srukf_step_dev(srukf_t* h, const double* d_u, const double* d_z, const uint8
   for (int b0 = 0; b0 < p.B; b0 += h->chunk) {
     int nb = p.B - b0 < h->chunk ? p.B - b0 : h->chunk;
     q.chunk0 = b0;
+    fb_join(h, b0, nb);   // a fallback of the previous frame that is still rewriting these filters
     prof_begin(h, 0);
     launch_predict(p, q, nb, true, true, false, h->stream);
     prof_end(h);
@@ -819,6 +887,7 @@ int srukf_get_x_async(srukf_t* h, double* x_host) {
 int srukf_set_state_dev(srukf_t* h, int b0, int nb, const double* d_x, const double* d_S_packed) {
   if (!h || b0 < 0 || nb <= 0 || b0 + nb > h->p.B) return fail(SRUKF_EINVAL, "srukf_set_state_dev: bad arguments");
   CU(cudaSetDevice(h->device));
+  fb_join(h);
   if (d_x)
     CU(cudaMemcpyAsync(h->x + (size_t)b0 * h->p.n, d_x, sizeof(double) * (size_t)nb * h->p.n, cudaMemcpyDeviceToDevice,
                        h->stream));
@@ -836,6 +905,7 @@ int srukf_set_state_dev(srukf_t* h, int b0, int nb, const double* d_x, const dou
 int srukf_get_cov_block(srukf_t* h, int r0, int nr, double* out) {
   if (!h || !out || r0 < 0 || nr <= 0 || r0 + nr > h->p.n) return fail(SRUKF_EINVAL, "srukf_get_cov_block: bad arguments");
   CU(cudaSetDevice(h->device));
+  fb_join(h);
   double* tmp = nullptr;
   size_t bytes = sizeof(double) * (size_t)h->p.B * nr * nr;
   CU(cudaMalloc(&tmp, bytes));
@@ -851,6 +921,7 @@ int srukf_get_cov_block(srukf_t* h, int r0, int nr, double* out) {
 int srukf_get_flags(srukf_t* h, uint32_t* flags) {
   if (!h || !flags) return fail(SRUKF_EINVAL, "srukf_get_flags: null argument");
   CU(cudaSetDevice(h->device));
+  fb_join(h);
   CU(cudaMemcpyAsync(flags, h->flags, sizeof(uint32_t) * h->p.B, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return SRUKF_OK;
@@ -859,6 +930,7 @@ int srukf_get_flags(srukf_t* h, uint32_t* flags) {
 int srukf_clear_flags(srukf_t* h) {
   if (!h) return fail(SRUKF_EINVAL, "srukf_clear_flags: null handle");
   CU(cudaSetDevice(h->device));
+  fb_join(h);
   CU(cudaMemsetAsync(h->flags, 0, sizeof(uint32_t) * h->p.B, h->stream));
   return SRUKF_OK;
 }
@@ -866,6 +938,7 @@ int srukf_clear_flags(srukf_t* h) {
 int srukf_stats(srukf_t* h, const double* truth, double* out8) {
   if (!h || !truth || !out8) return fail(SRUKF_EINVAL, "srukf_stats: null argument");
   CU(cudaSetDevice(h->device));
+  fb_join(h);
   CU(cudaMemcpyAsync(h->truth, truth, sizeof(double) * (size_t)h->p.B * 3, cudaMemcpyHostToDevice, h->stream));
   launch_stats(h->p, h->x, h->S, h->truth, h->perf, h->flags, h->stats_out, h->stream);
   h->launches += 2;
@@ -953,6 +1026,7 @@ int srukf_cholesky_update(srukf_t* h, const double* U, int k, int up_or_down, in
   if (order == SRUKF_NEED_REORDER && (n_new < 1 || n_new > p.L))
     return fail(SRUKF_EINVAL, "srukf_cholesky_update: NEED_REORDER needs 1 <= n_new <= L");
   CU(cudaSetDevice(h->device));
+  fb_join(h);
   if (M && !h->G2) CU(cudaMalloc(&h->G2, sizeof(double) * (size_t)h->gslots * ((size_t)p.ntri + 2 * (size_t)p.nbp)));
   // u is dim x k per filter (a cv::Mat in the reference); the kernels want its columns contiguous and padded to np
   std::vector<double> ut((size_t)p.B * k * p.np, 0.0);
@@ -989,7 +1063,9 @@ int srukf_fp64_peak(int device, double* tflops) {
 int srukf_sync(srukf_t* h) {
   if (!h) return fail(SRUKF_EINVAL, "srukf_sync: null handle");
   CU(cudaSetDevice(h->device));
+  fb_join(h);
   CU(cudaStreamSynchronize(h->stream));
+  if (h->fb_stream) CU(cudaStreamSynchronize(h->fb_stream));
   if (h->copy_stream) CU(cudaStreamSynchronize(h->copy_stream));
   if (h->d2h_stream) CU(cudaStreamSynchronize(h->d2h_stream));
   CU(cudaGetLastError());

@@ -46,6 +46,8 @@ struct StepPtrs {
   const CUtensorMap* tmaps; // [TM_COUNT] TMA tensor maps of the handle (device memory)
   int sbuf;                // which S buffer is "current" (q.S): 0 or 1
   int tm_dz;               // TM_DZ (chunk scratch) or TM_DZ_ALL (split API)
+  int tm_ut;               // TM_UT or TM_UT2: which of the two U scratch sets this chunk uses (they alternate, so that the
+                           // guard's fallback of chunk i can run on a side stream while chunk i+1 fills the other set)
   int dz_filter0;          // first filter of this launch inside the dZ tensor
   // Carried covariance (fused mode only): P = S^T S lives next to S -- strictly-lower part in the lower triangle
   // of the same square buffer, diagonal in Pd -- so k_update starts each panel from P instead of re-forming
@@ -467,6 +469,7 @@ constexpr int TM_S1 = 8;    // +0..7: S buffer 1
 constexpr int TM_UT = 16;   // +0..7: Ut scratch
 // 24: dZ scratch (chunk), box 8 rows x BP_B columns; 25: dZ of the whole batch (split API) -- see StepPtrs::tm_dz
 constexpr int TM_USEQ = 26; // +0..7: per-CTA U-row scratch of k_update_seq
+constexpr int TM_UT2 = 34;  // +0..7: second Ut scratch set
 
 
 __host__ __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -1028,7 +1031,7 @@ __global__ void __launch_bounds__(NW * 32, (NW < 8) ? 16 / NW : ((NW == 8) ? ((M
   const CUtensorMap* tmNew = q.tmaps + (q.sbuf ? TM_S0 : TM_S1);
   const double* PdOld = q.Pd + (size_t)b * np;
   double* PdNew = q.Pd2 + (size_t)b * np;
-  const CUtensorMap* tmUt = q.tmaps + TM_UT;
+  const CUtensorMap* tmUt = q.tmaps + q.tm_ut;
   const int sdoubles = upd_stage_doubles(np, URW);
   size_t off = 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + off); off = align16(off + 2 * UNS * sizeof(uint64_t));
