@@ -119,7 +119,7 @@ struct srukf_handle {
   double *dZ = nullptr, *U = nullptr, *G = nullptr;
   double* G2 = nullptr;    // scratch of the NEED_REORDER update (allocated on first use)
   double* Gp = nullptr;    // carried covariance of the reference-order fallback, one packed matrix per fallback CTA
-  double* Useq = nullptr;  // U rows of the column group a bisection pass works on, [gslots][Lc][np]
+  double* Useq = nullptr;  // per fallback CTA a square [np][np]: U rows of a bisection pass / work area of the literal step
   // The guard's fallback of chunk i runs on fb_stream while the main stream goes on with chunk i+1; for that the chunk
   // scratch the fallback reads (U, nact, work list) exists twice and the chunks alternate between the two sets.
   double* U_set[2] = {nullptr, nullptr}; int* nact_set[2] = {nullptr, nullptr}; int* wl_set[2] = {nullptr, nullptr};
@@ -293,7 +293,7 @@ static int build_tensor_maps(srukf_handle* h, double* sbuf0, double* sbuf1) {
     hm[TM_S1 + r] = hm[TM_S0 + r];   // in-place update: "old" and "new" factor are the same buffer
     (void)sbuf1;
     if ((rc = encode_map(&hm[TM_UT + r], h->U, p.np, p.Lc, h->chunk, TP, 8 * (r + 1)))) return rc;
-    if (h->Useq) { if ((rc = encode_map(&hm[TM_USEQ + r], h->Useq, p.np, p.Lc, h->gslots, TP, 8 * (r + 1)))) return rc; }
+    if (h->Useq) { if ((rc = encode_map(&hm[TM_USEQ + r], h->Useq, p.np, p.np, h->gslots, TP, 8 * (r + 1)))) return rc; }
     else hm[TM_USEQ + r] = hm[TM_UT + r];
     if (h->U_set[1]) { if ((rc = encode_map(&hm[TM_UT2 + r], h->U_set[1], p.np, p.Lc, h->chunk, TP, 8 * (r + 1)))) return rc; }
     else hm[TM_UT2 + r] = hm[TM_UT + r];
@@ -380,8 +380,8 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   if (prm.downdate_mode == 0) {
     CUH(cudaMalloc(&h->Gp, sizeof(double) * (size_t)h->gslots * p.ntri));
     if (update_seq_available(p)) {
-      CUH(cudaMalloc(&h->Useq, sizeof(double) * (size_t)h->gslots * p.Lc * p.np));
-      CUH(cudaMemsetAsync(h->Useq, 0, sizeof(double) * (size_t)h->gslots * p.Lc * p.np, h->stream));
+      CUH(cudaMalloc(&h->Useq, sizeof(double) * (size_t)h->gslots * p.nbp));   // [np][np] per fallback CTA
+      CUH(cudaMemsetAsync(h->Useq, 0, sizeof(double) * (size_t)h->gslots * p.nbp, h->stream));
     }
   }
   CUH(cudaMalloc(&h->worklist, sizeof(int) * ((size_t)chunk + 1)));

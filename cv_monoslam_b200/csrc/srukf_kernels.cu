@@ -59,7 +59,7 @@ struct StepPtrs {
   int n_new;              // m_nFilters: the last n_new features were added on the previous frame (mode 3)
   double* Gp;             // [gslots][ntri] carried covariance of the reference-order fallback (fused mode only)
   double* Ed;             // [B][np] E_j = d_j - c_jj of the last fused update (the fallback rebuilds P_old from it)
-  double* Useq;           // [gslots][Lc][np] U rows of the group a bisection pass of k_update_seq works on
+  double* Useq;           // [gslots][np][np] U rows of the group a bisection pass of k_update_seq works on / literal-step work area
   int* nact;              // [chunk] features k_gain actually used (matched && visible && det(si) != 0): k_update and
                           // k_downdate take "no update this frame" (:2050) from the same count
 };
@@ -1459,6 +1459,56 @@ __device__ __noinline__ void seq_unpack_P(int n, int np, const double* Pc, doubl
     }
   }
 }
+// The reference's modified Cholesky (SLAM.cpp:2197-2327) of the packed symmetric Pc, LEFT-looking as the reference
+// itself is written (:2237-2261: column j = G(:, j) - C(:, <j) L(j, <j)^T): one thread per row forms its entry of column
+// j as a dot product over the finished columns, which it reads from its own row of the square work area W (n x np,
+// row-major; only reads hit memory, and consecutive j re-read the same cache lines), instead of streaming a trailing
+// matrix through L2 once per pivot as the right-looking mchol_core does (5.7 ms per factorisation at n = 304 from one
+// CTA; this form: ~1 ms).  S (square buffer, upper triangle) receives sqrt(D) L^T; evec the pivot modifications.
+__device__ __noinline__ void mchol_left(int n, int np, double eps, const double* Pc, double* W, double* S, double* Lj,
+                                        double* red, uint32_t& flags, double* evec) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  // :2204-2211
+  double gmax = -1.0e300, zmax = 0.0;
+  for (int k = tid; k < n; k += nth) gmax = fmax(gmax, Pc[tri_off(k, n)]);
+  {
+    const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+    for (int k = warp; k < n; k += nw) {
+      const double* col = Pc + tri_off(k, n);
+      for (int i = k + 1 + lane; i < n; i += 32) zmax = fmax(zmax, col[i - k]);
+    }
+  }
+  gmax = block_max<NT>(gmax, red);
+  zmax = block_max<NT>(zmax, red);
+  double nu = sqrt((double)n * n - 1.0);
+  if (nu < 1.0) nu = 1.0;
+  const double beta2 = fmax(fmax(gmax, zmax / nu), 1e-15);
+  double* Dv = Lj + n;   // pivots d_k
+  for (int j = 0; j < n; ++j) {
+    // L(j, k) = C(j, k) / d_k for the finished columns k < j (:2224-2234)
+    for (int k = tid; k < j; k += nth) Lj[k] = W[(size_t)j * np + k] / Dv[k];
+    __syncthreads();
+    double th = 0.0;
+    for (int i = j + tid; i < n; i += nth) {
+      const double* wi = W + (size_t)i * np;
+      double acc = 0.0;
+      for (int k = 0; k < j; ++k) acc = fma(Lj[k], wi[k], acc);
+      const double c = Pc[tri_off(j, n) + (i - j)] - acc;   // :2237-2261 (the diagonal entry the same way)
+      W[(size_t)i * np + j] = c;
+      if (i > j) th = fmax(th, fabs(c));
+    }
+    th = block_max<NT>(th, red);   // :2264-2276
+    const double cjj = W[(size_t)j * np + j];
+    const double d = fmax(fmax(eps, fabs(cjj)), th * th / beta2);  // :2279-2285
+    if (d != cjj) flags |= (d > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
+    if (tid == 0) { Dv[j] = d; evec[j] = d - cjj; }
+    const double sd = sqrt(d);
+    double* srow = S + (size_t)j * np;
+    for (int i = j + tid; i < n; i += nth) srow[i] = (i == j) ? sd : sd * (W[(size_t)i * np + j] / d);  // :2232, :2321
+    __syncthreads();
+  }
+}
+
 // P_old = G + U U^T with G = (lower triangle, Pd - E) left by the fused pass; written to the buffer and to Pc
 __device__ __noinline__ void seq_rebuild_P(int n, int np, int ncolsU, double* Sb, double* Pd, const double* Ed,
                                            const double* Ut, double* Pc) {
@@ -1477,22 +1527,19 @@ __device__ __noinline__ void seq_rebuild_P(int n, int np, int ncolsU, double* Sb
   for (int k = threadIdx.x; k < n; k += blockDim.x) Pd[k] = Pc[tri_off(k, n)];
 }
 // the reference's literal step for one column (:2149-2152): Pc <- Pc - u u^T, S <- modifiedCholesky(Pc), Pc <- Pc + E
-__device__ __noinline__ void seq_literal_column(int n, int np, double eps, const double* u, double* Pc, double* G, double* Sb,
-                                                double* Pd, double* wcol, double* red, uint32_t& flags) {
+__device__ __noinline__ void seq_literal_column(int n, int np, double eps, const double* u, double* Pc, double* W, double* Sb,
+                                                double* Pd, double* vec, uint32_t& flags) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;   // NT threads (k_update_seq is built for 8 warps)
   for (int k = warp; k < n; k += NT / 32) {
     double* col = Pc + tri_off(k, n);
-    double* gcol = G + tri_off(k, n);
     const double uk = u[k];
-    for (int i = k + lane; i < n; i += 32) {
-      const double v = fma(-uk, u[i], col[i - k]);
-      col[i - k] = v;
-      gcol[i - k] = v;
-    }
+    for (int i = k + lane; i < n; i += 32) col[i - k] = fma(-uk, u[i], col[i - k]);
   }
   __syncthreads();
+  // vec (the free ring): Lj [n] | Dv [n] | red [40] | evec [n]
+  double* red = vec + 2 * n;
   double* evec = red + 40;
-  mchol_core(n, np, eps, G, Sb, wcol, red, flags, evec);
+  mchol_left(n, np, eps, Pc, W, Sb, vec, red, flags, evec);
   __syncthreads();
   for (int k = tid; k < n; k += NT) Pc[tri_off(k, n)] += evec[k];
   __syncthreads();
@@ -1532,8 +1579,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_update_seq(DevParams p, StepPtrs
   ring_init<NW, UNS>(ring, bars);
 
   double* Pc = q.Gp + (size_t)blockIdx.x * p.ntri;
-  double* Gs = q.G + (size_t)blockIdx.x * p.ntri;
-  double* Useq = q.Useq + (size_t)blockIdx.x * p.Lc * np;
+  double* Useq = q.Useq + (size_t)blockIdx.x * np * np;   // [np][np] per CTA: rows < Lc hold a pass's U rows ..
+  double* Wsq = Useq;                                      // .. and the whole square is the literal step's work area
   const int nitems = q.worklist[0];
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int rel = q.worklist[1 + item];
@@ -1734,7 +1781,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_update_seq(DevParams p, StepPtrs
         __syncthreads();
         if (m == 1) {
           // wcol | red2 | evec alias the (now free) ring
-          seq_literal_column(n, np, p.epsilon, Ut + (size_t)cols[lo] * np, Pc, Gs, Sb, Pd, Xs, Xs + n, flags);
+          seq_literal_column(n, np, p.epsilon, Ut + (size_t)cols[lo] * np, Pc, Wsq, Sb, Pd, Xs, flags);
         } else if (tid == 0) {
           const int mid = lo + m / 2;
           int dd = sc[1];
