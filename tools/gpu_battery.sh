@@ -2,7 +2,7 @@
 # Standard GPU battery (run under gpurun): tests, bench (both arms), config 1, ncu launch list + full captures.
 # usage: tools/gpu_battery.sh <tag> [tests] [bench] [ref] [config1] [ncu]
 tag=$1; shift
-what="$*"; [ -z "$what" ] && what="tests bench ref config1 ncu"
+what="$*"; [ -z "$what" ] && what="tests bench ref config1 ncu sweep adv"
 mkdir -p gpurun_out
 for w in $what; do
   case $w in
@@ -15,5 +15,18 @@ for w in $what; do
                ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -o gpurun_out/${tag}_$k -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_$k.log 2>&1
              done; ls -la gpurun_out/${tag}_*.ncu-rep ;;
     smoke)   python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ;;
+    sweep)   timeout 900 python bench.py --sweep 10,20,33,50,66,100,200 --steps 3 --warmup 3 > gpurun_out/${tag}_sweep_config4.jsonl 2> gpurun_out/${tag}_sweep.err; echo "sweep rc=$?"
+             python - gpurun_out/${tag}_sweep_config4.jsonl <<'PY'
+import json, sys
+for l in open(sys.argv[1]):
+    d = json.loads(l)
+    print("  L", d["landmarks"], "n", d["state_dim"], "B", d["filters"], "rate", round(d["value"]), "ms", round(d["ms_per_step"], 2), "frac", round(d["frac_fp64_peak"], 3),
+          {k: round(v, 2) for k, v in d["kernel_ms_per_step"].items()}, "fallback", d["n_fallback"], "parity", d["parity"]["ok"], d["parity"]["relerr_P"], d["noise"])
+PY
+             ;;
+    adv)     for f in 0.001 0.01; do
+               timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --adversarial-frac $f > gpurun_out/${tag}_adv_$f.json 2> gpurun_out/${tag}_adv_$f.err; echo "adv $f rc=$?"; cut -c1-200 gpurun_out/${tag}_adv_$f.json
+             done ;;
+    lib)     cp cv_monoslam_b200/libsrukf_b200.so gpurun_out/${tag}_libsrukf_b200.so ;;
   esac
 done
