@@ -298,6 +298,31 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return red[32];
 }
 
+// N sums at once behind ONE pair of barriers (block_sum costs three per value): warp shuffle trees, then every
+// thread adds the NT/32 warp partials in fixed order.  `scratch` holds N * (NT/32) doubles.
+template <int NT, int N>
+__device__ __forceinline__ void block_sum_n(double (&v)[N], double* scratch) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_down_sync(0xffffffffu, v[c], o);
+  }
+  __syncthreads();
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) scratch[c * (NT / 32) + (tid >> 5)] = v[c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) r += scratch[c * (NT / 32) + w];
+    v[c] = r;
+  }
+}
+
 template <int NT>
 __device__ __forceinline__ double block_max(double v, double* red) {
   int tid = threadIdx.x;

@@ -172,8 +172,11 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
       const double* r = rs + (size_t)i * 8;
       a0 += r[0] - rs[0]; a1 += r[1] - rs[1]; a2 += r[2] - rs[2]; a3 += r[3] - rs[3];
     }
-    a0 = block_sum<NT>(a0, red); a1 = block_sum<NT>(a1, red);
-    a2 = block_sum<NT>(a2, red); a3 = block_sum<NT>(a3, red);
+    {
+      double a4[4] = {a0, a1, a2, a3};
+      block_sum_n<NT, 4>(a4, work);   // `work` is free until T is built below
+      a0 = a4[0]; a1 = a4[1]; a2 = a4[2]; a3 = a4[3];
+    }
     __syncthreads();
     if (tid == 0) {
       xs[n - 4] = p.Wsum * rs[0] + p.wi * a0;
@@ -229,8 +232,7 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
       //   P_rr = E_f^T E_f + R_rr^T R_rr   (the robot-feature rows S_ff^T E_f are formed by k_gain on the tensor pipe)
       // E_f^T E_f: per-thread partial sums over the feature rows, reduced in fixed order (nothing of E_f is kept in
       // shared memory, so the kernel's footprint does not grow with a second n x 4 array)
-#pragma unroll
-      for (int m = 0; m < 10; ++m) ee[m] = block_sum<NT>(ee[m], red);
+      block_sum_n<NT, 10>(ee, T + (size_t)(n + 10) * 4);   // 80 doubles behind T
       if (tid == 0) {
         for (int r = 0, m = 0; r < 4; ++r)
           for (int c = 0; c <= r; ++c, ++m) {
@@ -1547,8 +1549,11 @@ __device__ __noinline__ void seq_literal_column(int n, int np, double eps, const
   __syncthreads();
 }
 
+#ifndef SRUKF_SEQ_CTAS
+#define SRUKF_SEQ_CTAS 1
+#endif
 template <int NW, int MQ, int NBT, int URW>
-__global__ void __launch_bounds__(NW * 32, 1) k_update_seq(DevParams p, StepPtrs q) {
+__global__ void __launch_bounds__(NW * 32, SRUKF_SEQ_CTAS) k_update_seq(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
   constexpr int CPP = NBT + 1, WDP = NBT + 1;
   static_assert(MQ <= MAXQ && NW * 32 == NT, "the bisection fallback is built for the 8-warp, 5-slot variant");
@@ -1581,8 +1586,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_update_seq(DevParams p, StepPtrs
   double* Pc = q.Gp + (size_t)blockIdx.x * p.ntri;
   double* Useq = q.Useq + (size_t)blockIdx.x * np * np;   // [np][np] per CTA: rows < Lc hold a pass's U rows ..
   double* Wsq = Useq;                                      // .. and the whole square is the literal step's work area
+  // Work items are dealt so that the queued filters share SMs in pairs (CTA c and CTA c + gridDim.x / 2 are resident on
+  // the same SM when the grid is two CTAs per SM): two fallbacks overlap each other's latency phases on one SM and the
+  // other SMs stay free for the main stream's kernels.
   const int nitems = q.worklist[0];
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+  const int half = gridDim.x >> 1;
+  const int first = (SRUKF_SEQ_CTAS == 2 && half > 0) ? (((int)blockIdx.x < half) ? 2 * (int)blockIdx.x : 2 * ((int)blockIdx.x - half) + 1)
+                                                      : (int)blockIdx.x;
+  for (int item = first; item < nitems; item += gridDim.x) {
     const int rel = q.worklist[1 + item];
     const int b = q.chunk0 + rel;
     if (q.nact[rel] == 0) continue;
@@ -2648,7 +2659,7 @@ bool predict_free(const DevParams& p) {
   return sizeof(double) * (base + need) <= 110 * 1024;
 }
 size_t predict_smem_bytes(const DevParams& p) {
-  size_t work = (size_t)(p.n + 10) * 4;                        // motion step: T
+  size_t work = (size_t)(p.n + 10) * 4 + 10 * (NT / 32);       // motion step: T + the scratch of one 10-value reduction
   size_t part = (size_t)(NT / 32) * 8 * 13;                    // measurement step: per-warp partial sums of one block ..
   if (predict_free(p) && part < (size_t)(NT / 32) * p.L * 13 + 2 * (size_t)p.L)
     part = (size_t)(NT / 32) * p.L * 13 + 2 * (size_t)p.L;     // .. or of all features (barrier-free mode)

@@ -76,3 +76,21 @@ def test_stats_allreduce_world2_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "OK" in out.stdout
+
+
+def test_bench_arms_share_one_config_and_traffic_comes_from_a_committed_profile(tmp_path, monkeypatch):
+    """bench.py: both arms describe the workload with the same `config` object (the reference arm times a sample of it),
+    and roofline.traffic is read from a committed ncu summary, never a constant"""
+    import bench
+    a = bench.config_dict(65536, 50, 8, 1, 0)
+    b = bench.config_dict(65536, 50, 8, 1, 0)
+    assert a == b and "65536 filters x 50 landmarks" in a["workload"] and a["state_dim"] == 304
+    assert bench.algorithmic_bytes(304, 50) == 8.0 * (304 * 305 + 2 * 304 + 3 + 100)     # SURVEY 8(d)
+    assert abs(bench.flops_downdate(304, 50) + bench.flops_gain(304, 50) + bench.flops_predict(304, 50) - 32.39256e6) < 1e3
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.committed_traffic("k_update", 50) is None
+    (tmp_path / "profiles").mkdir()
+    (tmp_path / "profiles" / "r99_traffic.json").write_text(
+        '{"landmarks": 50, "kernels": {"k_update": {"dram_bytes_per_filter": 123.0}}}')
+    assert bench.committed_traffic("k_update", 50) == (123.0, "profiles/r99_traffic.json")
+    assert bench.committed_traffic("k_update", 20) is None

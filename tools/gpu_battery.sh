@@ -11,8 +11,10 @@ for w in $what; do
     ref)     python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err; echo "ref rc=$?"; cat gpurun_out/${tag}_bench_reference.json ;;
     config1) python tools/config1.py --steps 1000 --gpu --reference 1000 > gpurun_out/${tag}_config1.json 2> gpurun_out/${tag}_config1.err; echo "config1 rc=$?"; cat gpurun_out/${tag}_config1.json ;;
     ncu)     ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
+             # (gpurun brings back at most 64 MiB: source import only for the dominant kernel)
              for k in k_update k_gain k_predict; do
-               ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -o gpurun_out/${tag}_$k -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_$k.log 2>&1
+               src=""; [ $k = k_update ] && src="--import-source on"
+               ncu --set full --clock-control none $src -k regex:$k -s 4 -c 1 -o gpurun_out/${tag}_$k -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_$k.log 2>&1
              done; ls -la gpurun_out/${tag}_*.ncu-rep ;;
     smoke)   python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ;;
     sweep)   timeout 900 python bench.py --sweep 10,20,33,50,66,100,200 --steps 3 --warmup 3 > gpurun_out/${tag}_sweep_config4.jsonl 2> gpurun_out/${tag}_sweep.err; echo "sweep rc=$?"
