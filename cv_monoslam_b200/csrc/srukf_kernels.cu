@@ -2632,7 +2632,7 @@ int update_mq(const DevParams& p) {   // accumulator slots of the 8-warp variant
 }
 bool update_wide(const DevParams& p) { return p.np > 8 * 16 * MAXQ; }   // the <16, 10, 16, 8> variant
 // k_gain variant: 0 = <8,5,4> (np <= 320, 2 CTAs/SM), 1 = <16,3,7> (np <= 384, 1 CTA/SM, half the passes),
-// 2 = <16,5,4> (np <= 640), 3 = <2,5,4> (np <= 80, 8 CTAs/SM), 4 = <4,5,4> (np <= 160, 4 CTAs/SM)
+// 2 = <16,5,4> (np <= 640), 3 = <2,5,4> (np <= 80, 8 CTAs/SM), 4 = <4,5,4> (np <= 160, 4 CTAs/SM), 5 = <16,4,6> (np <= 512)
 #ifndef SRUKF_GAIN_KC
 #define SRUKF_GAIN_KC 24
 #endif
@@ -2645,10 +2645,11 @@ int gain_variant(const DevParams& p) {
   if (p.np <= 8 * 2 * 5) return 3;
   if (p.np <= 8 * 4 * 5) return 4;
   if (p.np <= 8 * 16 * 3) return 1;
+  if (p.np <= 8 * 16 * 4 && SRUKF_PAD == 4) return 5;   // <16,4,6>: 48 columns per pass instead of 32 (np <= 512, L <= 84)
   return 2;
 }
 int gain_dz_box(const DevParams& p) {
-  if (SRUKF_PAD == 4) return gain_variant(p) == 1 ? 60 : 36;
+  if (SRUKF_PAD == 4) return gain_variant(p) == 1 ? 60 : (gain_variant(p) == 5 ? 52 : 36);
   return gain_variant(p) == 1 ? 72 : 40;
 }
 // measurement step of k_predict without block barriers: the per-warp partial sums of ALL features stay in shared memory
@@ -2671,6 +2672,7 @@ int gain_strips_per_cta(const DevParams& p) {
   switch (gain_variant(p)) {
     case 0: return 8 * 5;
     case 1: return 16 * 3;
+    case 5: return 16 * 4;
     case 3: return 2 * 5;
     case 4: return 4 * 5;
     default: return 16 * 5;
@@ -2678,8 +2680,8 @@ int gain_strips_per_cta(const DevParams& p) {
 }
 int gain_row_ctas(const DevParams& p) { return (p.np / 8 + gain_strips_per_cta(p) - 1) / gain_strips_per_cta(p); }
 size_t gain_smem_bytes(const DevParams& p) {
-  const bool v1 = gain_variant(p) == 1;
-  const size_t kc = v1 ? GKC1 : 8, ns = v1 ? GNS1 : NSTAGE;   // template arguments KCG / NSG of the variant
+  const int gv = gain_variant(p);
+  const size_t kc = gv == 1 ? GKC1 : (gv == 5 ? 16 : 8), ns = gv == 1 ? GNS1 : (gv == 5 ? 2 : NSTAGE);   // KCG / NSG of the variant
   size_t off = align16(2 * ns * sizeof(uint64_t));
   off += sizeof(double) * (8 * (p.Lc / 2) + p.np);
   off = (off + sizeof(int) * (p.L + 1) + 127) & ~(size_t)127;
@@ -2712,7 +2714,7 @@ cudaError_t configure_kernels(const DevParams&) {
 #define SRUKF_SET(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
   SRUKF_SET((k_predict<true, true>)) SRUKF_SET((k_predict<true, false>)) SRUKF_SET((k_predict<false, true>))
   SRUKF_SET((k_gain<8, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<16, 3, 7, GKC1, GNS1>)) SRUKF_SET((k_gain<16, 5, 4, 8, NSTAGE>))
-  SRUKF_SET((k_gain<2, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<4, 5, 4, 8, NSTAGE>))
+  SRUKF_SET((k_gain<2, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<4, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<16, 4, 6, 16, 2>))
   SRUKF_SET((k_update<8, false>)) SRUKF_SET((k_update<16, false>)) SRUKF_SET((k_update<8, true>)) SRUKF_SET((k_update<16, true>))
   SRUKF_SET((k_update<2, false>)) SRUKF_SET((k_update<4, false>)) SRUKF_SET((k_update<16, false, 10, 16, 8>))
   SRUKF_SET((k_update<8, false, 1>)) SRUKF_SET((k_update<8, false, 2>)) SRUKF_SET((k_update<8, false, 3>))
@@ -2737,6 +2739,7 @@ void launch_gain(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_
     case 1: k_gain<16, 3, 7, GKC1, GNS1><<<grid, 512, gain_smem_bytes(p), st>>>(p, q); break;
     case 3: k_gain<2, 5, 4, 8, NSTAGE><<<grid, 64, gain_smem_bytes(p), st>>>(p, q); break;
     case 4: k_gain<4, 5, 4, 8, NSTAGE><<<grid, 128, gain_smem_bytes(p), st>>>(p, q); break;
+    case 5: k_gain<16, 4, 6, 16, 2><<<grid, 512, gain_smem_bytes(p), st>>>(p, q); break;
     default: k_gain<16, 5, 4, 8, NSTAGE><<<grid, 512, gain_smem_bytes(p), st>>>(p, q); break;
   }
 }
