@@ -947,6 +947,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
         }
         r[j] = lij;
       }
+      __syncwarp();   // lanes 8..31 read the same rows above (duplicates of lanes 0..7); the writes below follow them
       if (lane < 8) {
         const double sd = sqrt(dmine);
         dsm[c0 + lane] = rmine;   // 1/d_j for the solve of the rows below
