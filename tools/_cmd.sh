@@ -1,6 +1,7 @@
-tools/ab_bench.sh r03g "kc32|kc32|" "kc16|kc16|" 2>&1 | grep -v QUICK
-echo "== sanitizer memcheck (small cases, fused path + forced fallback + wide map)"
-SRUKF_FORCE_FALLBACK_PPM=500000 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/quick_parity.py 3:4:2 8:4:2 > gpurun_out/r03g_memcheck_small.log 2>&1; echo "memcheck small rc=$?"; tail -3 gpurun_out/r03g_memcheck_small.log
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/quick_parity.py 108:2:1 > gpurun_out/r03g_memcheck_wide.log 2>&1; echo "memcheck wide rc=$?"; tail -3 gpurun_out/r03g_memcheck_wide.log
-echo "== sanitizer racecheck (forced fallback kernel)"
-SRUKF_FORCE_FALLBACK_PPM=1000000 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/quick_parity.py 5:2:1 > gpurun_out/r03g_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/r03g_racecheck.log
+N=${1:-2}
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r03i_bench_n$N.json 2> gpurun_out/r03i_bench_n$N.err; echo "n$N rc=$?"; python - gpurun_out/r03i_bench_n$N.json <<'PY'
+import json, sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print("n_gpus", d["n_gpus"], "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "ms/step", round(d["ms_per_step"],2), "stats", d["stats"])
+PY
+tail -3 gpurun_out/r03i_bench_n$N.err
