@@ -373,7 +373,7 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   if (chunk >= 592) chunk -= chunk % 296;  // whole waves of two CTAs per SM
   h->chunk = (int)chunk;
   h->gslots = (int)(chunk < 148 ? chunk : 148);
-  if (prm.downdate_mode == 0 && update_seq_available(p) && chunk > 148) h->gslots = (int)(chunk < 296 ? chunk : 296);
+  if (prm.downdate_mode == 0 && update_seq_available(p) && tile_warps(p) == 8 && chunk > 148) h->gslots = (int)(chunk < 296 ? chunk : 296);
   CUH(cudaMalloc(&h->dZ, sizeof(double) * (size_t)chunk * p.np * p.Lc));
   CUH(cudaMalloc(&h->U, sizeof(double) * (size_t)chunk * p.Lc * p.np));
   CUH(cudaMalloc(&h->G, sizeof(double) * (size_t)h->gslots * p.ntri));

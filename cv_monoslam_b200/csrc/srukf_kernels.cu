@@ -1468,6 +1468,7 @@ __device__ __noinline__ void seq_unpack_P(int n, int np, const double* Pc, doubl
 // row-major; only reads hit memory, and consecutive j re-read the same cache lines), instead of streaming a trailing
 // matrix through L2 once per pivot as the right-looking mchol_core does (5.7 ms per factorisation at n = 304 from one
 // CTA; this form: ~1 ms).  S (square buffer, upper triangle) receives sqrt(D) L^T; evec the pivot modifications.
+template <int NTH>
 __device__ __noinline__ void mchol_left(int n, int np, double eps, const double* Pc, double* W, double* S, double* Lj,
                                         double* red, uint32_t& flags, double* evec) {
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -1481,8 +1482,8 @@ __device__ __noinline__ void mchol_left(int n, int np, double eps, const double*
       for (int i = k + 1 + lane; i < n; i += 32) zmax = fmax(zmax, col[i - k]);
     }
   }
-  gmax = block_max<NT>(gmax, red);
-  zmax = block_max<NT>(zmax, red);
+  gmax = block_max<NTH>(gmax, red);
+  zmax = block_max<NTH>(zmax, red);
   double nu = sqrt((double)n * n - 1.0);
   if (nu < 1.0) nu = 1.0;
   const double beta2 = fmax(fmax(gmax, zmax / nu), 1e-15);
@@ -1500,7 +1501,7 @@ __device__ __noinline__ void mchol_left(int n, int np, double eps, const double*
       W[(size_t)i * np + j] = c;
       if (i > j) th = fmax(th, fabs(c));
     }
-    th = block_max<NT>(th, red);   // :2264-2276
+    th = block_max<NTH>(th, red);   // :2264-2276
     const double cjj = W[(size_t)j * np + j];
     const double d = fmax(fmax(eps, fabs(cjj)), th * th / beta2);  // :2279-2285
     if (d != cjj) flags |= (d > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
@@ -1530,10 +1531,11 @@ __device__ __noinline__ void seq_rebuild_P(int n, int np, int ncolsU, double* Sb
   for (int k = threadIdx.x; k < n; k += blockDim.x) Pd[k] = Pc[tri_off(k, n)];
 }
 // the reference's literal step for one column (:2149-2152): Pc <- Pc - u u^T, S <- modifiedCholesky(Pc), Pc <- Pc + E
+template <int NTH>
 __device__ __noinline__ void seq_literal_column(int n, int np, double eps, const double* u, double* Pc, double* W, double* Sb,
                                                 double* Pd, double* vec, uint32_t& flags) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;   // NT threads (k_update_seq is built for 8 warps)
-  for (int k = warp; k < n; k += NT / 32) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int k = warp; k < n; k += NTH / 32) {
     double* col = Pc + tri_off(k, n);
     const double uk = u[k];
     for (int i = k + lane; i < n; i += 32) col[i - k] = fma(-uk, u[i], col[i - k]);
@@ -1542,9 +1544,9 @@ __device__ __noinline__ void seq_literal_column(int n, int np, double eps, const
   // vec (the free ring): Lj [n] | Dv [n] | red [40] | evec [n]
   double* red = vec + 2 * n;
   double* evec = red + 40;
-  mchol_left(n, np, eps, Pc, W, Sb, vec, red, flags, evec);
+  mchol_left<NTH>(n, np, eps, Pc, W, Sb, vec, red, flags, evec);
   __syncthreads();
-  for (int k = tid; k < n; k += NT) Pc[tri_off(k, n)] += evec[k];
+  for (int k = tid; k < n; k += NTH) Pc[tri_off(k, n)] += evec[k];
   __syncthreads();
   seq_unpack_P(n, np, Pc, Sb, Pd);
   __syncthreads();
@@ -1557,7 +1559,7 @@ template <int NW, int MQ, int NBT, int URW>
 __global__ void __launch_bounds__(NW * 32, SRUKF_SEQ_CTAS) k_update_seq(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
   constexpr int CPP = NBT + 1, WDP = NBT + 1;
-  static_assert(MQ <= MAXQ && NW * 32 == NT, "the bisection fallback is built for the 8-warp, 5-slot variant");
+  static_assert(MQ <= MAXQ, "the bisection fallback is built for the 5-slot variants (np <= 640)");
   extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.n, np = p.np, L = p.L;
@@ -1793,7 +1795,7 @@ __global__ void __launch_bounds__(NW * 32, SRUKF_SEQ_CTAS) k_update_seq(DevParam
         __syncthreads();
         if (m == 1) {
           // wcol | red2 | evec alias the (now free) ring
-          seq_literal_column(n, np, p.epsilon, Ut + (size_t)cols[lo] * np, Pc, Wsq, Sb, Pd, Xs, flags);
+          seq_literal_column<NTH>(n, np, p.epsilon, Ut + (size_t)cols[lo] * np, Pc, Wsq, Sb, Pd, Xs, flags);
         } else if (tid == 0) {
           const int mid = lo + m / 2;
           int dd = sc[1];
@@ -2698,7 +2700,9 @@ size_t update_smem_bytes(const DevParams& p) {
   return off + sizeof(double) * (ring > panel ? ring : panel);
 }
 size_t update_seq_smem_bytes(const DevParams& p) { return update_smem_bytes(p) + sizeof(int) * ((size_t)p.Lc + 72); }
-bool update_seq_available(const DevParams& p) { return tile_warps(p) == 8 && !getenv("SRUKF_FALLBACK_LITERAL"); }
+bool update_seq_available(const DevParams& p) {   // the 5-slot variants: 8 warps (np <= 320) or 16 warps (np <= 640)
+  return (tile_warps(p) == 8 || (tile_warps(p) == 16 && !update_wide(p))) && !getenv("SRUKF_FALLBACK_LITERAL");
+}
 size_t downdate_smem_bytes(const DevParams& p) { return sizeof(double) * (2 * (size_t)p.n + 40); }
 
 // The dynamic shared-memory limit is a per-function, per-device attribute shared by every handle of the process:
@@ -2720,7 +2724,7 @@ cudaError_t configure_kernels(const DevParams&) {
   SRUKF_SET((k_update<2, false>)) SRUKF_SET((k_update<4, false>)) SRUKF_SET((k_update<16, false, 10, 16, 8>))
   SRUKF_SET((k_update<8, false, 1>)) SRUKF_SET((k_update<8, false, 2>)) SRUKF_SET((k_update<8, false, 3>))
   SRUKF_SET(k_downdate) SRUKF_SET(k_init_features) SRUKF_SET(k_add_features) SRUKF_SET(k_delete_feature)
-  SRUKF_SET(k_chol_update) SRUKF_SET(k_mchol_batch) SRUKF_SET((k_update_seq<8, MAXQ, NB, SRUKF_UPD_ROWS>))
+  SRUKF_SET(k_chol_update) SRUKF_SET(k_mchol_batch) SRUKF_SET((k_update_seq<8, MAXQ, NB, SRUKF_UPD_ROWS>)) SRUKF_SET((k_update_seq<16, MAXQ, NB, SRUKF_UPD_ROWS>))
 #undef SRUKF_SET
   if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
@@ -2767,7 +2771,8 @@ void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStrea
   }
 }
 void launch_update_seq(const DevParams& p, const StepPtrs& q, int nblocks, cudaStream_t st) {
-  k_update_seq<8, MAXQ, NB, SRUKF_UPD_ROWS><<<nblocks, 256, update_seq_smem_bytes(p), st>>>(p, q);
+  if (tile_warps(p) == 8) k_update_seq<8, MAXQ, NB, SRUKF_UPD_ROWS><<<nblocks, 256, update_seq_smem_bytes(p), st>>>(p, q);
+  else k_update_seq<16, MAXQ, NB, SRUKF_UPD_ROWS><<<nblocks, 512, update_seq_smem_bytes(p), st>>>(p, q);
 }
 void launch_downdate(const DevParams& p, const StepPtrs& q, int nblocks, int mode, int use_worklist, cudaStream_t st) {
   k_downdate<<<nblocks, NT, downdate_smem_bytes(p), st>>>(p, q, mode, use_worklist);

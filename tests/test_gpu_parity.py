@@ -537,7 +537,7 @@ def test_adversarial_indefinite_downdate_falls_back_to_reference_order(gpu, orac
         g.close()
 
 
-@pytest.mark.parametrize("L,B,steps", [(8, 6, 3), (50, 2, 1)])
+@pytest.mark.parametrize("L,B,steps", [(8, 6, 3), (50, 2, 1), (60, 2, 1)])
 def test_forced_fallback_takes_the_bisection_path_and_matches_the_oracle(gpu, oracle, L, B, steps, monkeypatch):
     """SRUKF_FORCE_FALLBACK_PPM (the knob behind bench.py --adversarial-frac) sends every filter through the guard's
     fallback although nothing is wrong: column groups by bisection on the tensor pipe, one pseudo-random column as the

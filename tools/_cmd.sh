@@ -1,7 +1,3 @@
-N=${1:-2}
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r03i_bench_n$N.json 2> gpurun_out/r03i_bench_n$N.err; echo "n$N rc=$?"; python - gpurun_out/r03i_bench_n$N.json <<'PY'
-import json, sys
-d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print("n_gpus", d["n_gpus"], "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "ms/step", round(d["ms_per_step"],2), "stats", d["stats"])
-PY
-tail -3 gpurun_out/r03i_bench_n$N.err
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "adversarial or forced_fallback or wide_state" 2>&1 | tail -3
+SRUKF_FORCE_FALLBACK_PPM=1000000 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/quick_parity.py 56:2:1 > gpurun_out/r03j_memcheck_seq16.log 2>&1; echo "memcheck seq16 rc=$?"; tail -3 gpurun_out/r03j_memcheck_seq16.log
+timeout 300 python bench.py --sweep 66:8192 --steps 3 --warmup 3 --adversarial-frac 0.01 | cut -c1-700
