@@ -1581,8 +1581,8 @@ __global__ void __launch_bounds__(NW * 32, SRUKF_SEQ_CTAS) k_update_seq(DevParam
     off += sizeof(double) * (ring > panel ? ring : panel);
   }
   int* cols = reinterpret_cast<int*>(smraw + off); off += sizeof(int) * (size_t)p.Lc;   // U columns of the active features
-  int* stk = reinterpret_cast<int*>(smraw + off);                                       // [2][32] bisection stack + [8] scalars
-  int* sc = stk + 64;   // sc[0] = number of columns, sc[1] = stack depth, sc[2] = pass verdict
+  int* stk = reinterpret_cast<int*>(smraw + off);                                       // [3][32] bisection stack + [8] scalars
+  int* sc = stk + 96;   // sc[0] = number of columns, sc[1] = stack depth, sc[2] = pass verdict
   Ring ring;
   ring_init<NW, UNS>(ring, bars);
 
@@ -1612,8 +1612,11 @@ __global__ void __launch_bounds__(NW * 32, SRUKF_SEQ_CTAS) k_update_seq(DevParam
       // the full group has already failed in k_update (or is forced to count as failed): start with its halves
       const int mid = nc / 2;
       int d = 0;
-      if (nc - mid > 0) { stk[d] = mid; stk[32 + d] = nc; ++d; }
-      if (mid > 0) { stk[d] = 0; stk[32 + d] = mid; ++d; }
+      // third stack field: -1 nothing known, -2 known to fail, >= 0 "fails for sure if my left sibling [that lo, my lo)
+      // passes in one piece": parent = left + right failed and the guard depends only on the final matrix, which the
+      // right half reaches exactly when the left half went through unmodified
+      if (nc - mid > 0) { stk[d] = mid; stk[32 + d] = nc; stk[64 + d] = (mid > 0) ? 0 : -2; ++d; }
+      if (mid > 0) { stk[d] = 0; stk[32 + d] = mid; stk[64 + d] = -1; ++d; }
       sc[1] = d;
     }
     seq_rebuild_P(n, np, 2 * L, Sb, Pd, q.Ed + (size_t)b * np, Ut, Pc);
@@ -1626,9 +1629,23 @@ __global__ void __launch_bounds__(NW * 32, SRUKF_SEQ_CTAS) k_update_seq(DevParam
       __syncthreads();
       const int d = sc[1] - 1;
       const int lo = stk[d], hi = stk[32 + d];
+      const bool known_bad = stk[64 + d] == -2;
       __syncthreads();
       if (tid == 0) sc[1] = d;
       const int m = hi - lo;
+      if (known_bad) {   // no pass needed to learn that this group fails
+        if (m == 1) {
+          seq_literal_column<NTH>(n, np, p.epsilon, Ut + (size_t)cols[lo] * np, Pc, Wsq, Sb, Pd, Xs, flags);
+        } else if (tid == 0) {
+          const int mid = lo + m / 2;
+          int dd = sc[1];
+          stk[dd] = mid; stk[32 + dd] = hi; stk[64 + dd] = lo; ++dd;
+          stk[dd] = lo; stk[32 + dd] = mid; stk[64 + dd] = -1; ++dd;
+          sc[1] = dd;
+        }
+        __syncthreads();
+        continue;
+      }
       const int rowsB = (m + 7) & ~7;
       // gather the group's U columns (rows of Ut) into the scratch, zero rows up to a multiple of 8
       for (int i = tid; i < rowsB * np; i += NTH) {
@@ -1789,6 +1806,10 @@ __global__ void __launch_bounds__(NW * 32, SRUKF_SEQ_CTAS) k_update_seq(DevParam
       if (!bad) {
         flags |= pflags;                    // (only the EPSILON-floor flag can be in there)
         seq_pack_P(n, np, Sb, Pd, Pc);      // commit: the carried covariance after this group
+        if (tid == 0 && sc[1] > 0) {        // my right sibling is now known to fail (see above)
+          const int t = sc[1] - 1;
+          if (stk[t] == hi && stk[64 + t] == lo) stk[64 + t] = -2;
+        }
         __syncthreads();
       } else {
         seq_unpack_P(n, np, Pc, Sb, Pd);    // undo: the pass overwrote the covariance in place
@@ -1799,8 +1820,8 @@ __global__ void __launch_bounds__(NW * 32, SRUKF_SEQ_CTAS) k_update_seq(DevParam
         } else if (tid == 0) {
           const int mid = lo + m / 2;
           int dd = sc[1];
-          stk[dd] = mid; stk[32 + dd] = hi; ++dd;
-          stk[dd] = lo; stk[32 + dd] = mid; ++dd;
+          stk[dd] = mid; stk[32 + dd] = hi; stk[64 + dd] = lo; ++dd;
+          stk[dd] = lo; stk[32 + dd] = mid; stk[64 + dd] = -1; ++dd;
           sc[1] = dd;
         }
       }
@@ -2699,7 +2720,7 @@ size_t update_smem_bytes(const DevParams& p) {
   size_t panel = (size_t)p.np * (nbt + 1);
   return off + sizeof(double) * (ring > panel ? ring : panel);
 }
-size_t update_seq_smem_bytes(const DevParams& p) { return update_smem_bytes(p) + sizeof(int) * ((size_t)p.Lc + 72); }
+size_t update_seq_smem_bytes(const DevParams& p) { return update_smem_bytes(p) + sizeof(int) * ((size_t)p.Lc + 104); }
 bool update_seq_available(const DevParams& p) {   // the 5-slot variants: 8 warps (np <= 320) or 16 warps (np <= 640)
   return (tile_warps(p) == 8 || (tile_warps(p) == 16 && !update_wide(p))) && !getenv("SRUKF_FALLBACK_LITERAL");
 }
