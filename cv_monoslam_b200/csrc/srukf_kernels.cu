@@ -443,6 +443,9 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
 #ifndef SRUKF_CANON_WARP
 #define SRUKF_CANON_WARP 0
 #endif
+#ifndef SRUKF_INIT_FIRST
+#define SRUKF_INIT_FIRST 0   // 1: issue the P_old loads of a panel before its first tensor copies (measured, see profiles)
+#endif
 constexpr int NB = 32;      // panel width (columns per contraction pass)
 constexpr int KC = 8;       // K rows per pipeline stage at full width
 #ifndef SRUKF_NSTAGE
@@ -1137,6 +1140,7 @@ __global__ void __launch_bounds__(NW * 32, (NW < 8) ? 16 / NW : ((NW == 8) ? ((M
 #pragma unroll
         for (int t = 0; t < NBT / 8; ++t) { acc[qq][t][0] = -acc[qq][t][0]; acc[qq][t][1] = -acc[qq][t][1]; }
     };
+#if !SRUKF_INIT_FIRST
     for (int t = 0; t < UNS - 1 && t < nchunks; ++t) {
       if (ring_my_turn<NW>(ring)) {
         fence_proxy_async();  // the ring aliases the previous panel's Cp (generic-proxy stores)
@@ -1144,6 +1148,7 @@ __global__ void __launch_bounds__(NW * 32, (NW < 8) ? 16 / NW : ((NW == 8) ? ((M
       }
       ring_next(ring);
     }
+#endif
     // (the first chunk loads are in flight while the accumulators are initialised from global memory)
     // accumulators start at -P_old(i, J): tiles below the panel's diagonal come straight from the lower triangle
     // of the old buffer, diagonal tiles mix lower entries and Pd, tiles above the diagonal are never used
@@ -1170,6 +1175,15 @@ __global__ void __launch_bounds__(NW * 32, (NW < 8) ? 16 / NW : ((NW == 8) ? ((M
       }
     }
 
+#if SRUKF_INIT_FIRST
+    for (int t = 0; t < UNS - 1 && t < nchunks; ++t) {
+      if (ring_my_turn<NW>(ring)) {
+        fence_proxy_async();  // the ring aliases the previous panel's Cp (generic-proxy stores)
+        produce(t);
+      }
+      ring_next(ring);
+    }
+#endif
     consume(cA, cA + cB);    // acc = -(P - U U^T) = -G(i, J)
     // G(i, J) is visible now: store the carried covariance of the new factor, P_new = G (+ E on the diagonal,
     // added after the pivots are known), and track max diag / max off-diag of G for beta^2 (:2204-2205)
