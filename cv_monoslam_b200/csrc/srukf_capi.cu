@@ -363,14 +363,21 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   CUH(cudaMemsetAsync(h->x, 0, sizeof(double) * B * n, h->stream));
   CUH(cudaMemsetAsync(h->S, 0, sizeof(double) * (size_t)B * p.nbp, h->stream));
   CUH(cudaMemsetAsync(h->visible, 0, (size_t)B * L, h->stream));
-  // scratch: chunk sized so the pipeline scratch (dZ and Ut per filter) stays <= 6 GiB: few, long launches keep
+  // scratch: chunk sized so the pipeline scratch (dZ and Ut per filter) stays <= 12 GiB (SRUKF_SCRATCH_GIB): few, long launches keep
   // the idle tail of each kernel (the last wave of CTAs) small against its run time
   size_t per = sizeof(double) * 2 * (size_t)p.np * p.Lc;
-  size_t budget = (size_t)6 << 30;
+  size_t budget = (size_t)12 << 30;   // 65,536 x L = 50: 3 chunks of 21,904 (6 GiB / 6 chunks: +0.65 % per step)
+  if (const char* e_ = getenv("SRUKF_SCRATCH_GIB")) { const long g_ = atol(e_); if (g_ > 0) budget = (size_t)g_ << 30; }
   long chunk = (long)(budget / per);
   if (chunk < 1) chunk = 1;
   if (chunk > B) chunk = B;
   if (chunk >= 592) chunk -= chunk % 296;  // whole waves of two CTAs per SM
+  if (chunk >= 592 && chunk < B) {         // equal chunks (whole waves) instead of full ones and a short last one
+    const long nch = (B + chunk - 1) / chunk;
+    long even = (B + nch - 1) / nch;
+    even += (296 - even % 296) % 296;
+    if (even < chunk) chunk = even;
+  }
   h->chunk = (int)chunk;
   h->gslots = (int)(chunk < 148 ? chunk : 148);
   if (prm.downdate_mode == 0 && update_seq_available(p) && tile_warps(p) == 8 && chunk > 148) h->gslots = (int)(chunk < 296 ? chunk : 296);

@@ -109,8 +109,14 @@ __device__ void householder4(double* T, int rows, double* red) {
 //           QrAndCholeskyForMeasurement :1700-1748 / calculateOneFeatureCovariance :1759-1775, and the
 //           robot rows of calculateOneFeatureCrossCovariance :2020-2038.
 // -------------------------------------------------------------------------------------------------
+#ifndef SRUKF_PREDICT_MINB
+#define SRUKF_PREDICT_MINB 2     // CTAs per SM k_predict is compiled for (register budget)
+#endif
+#ifndef SRUKF_PREDICT_FREE_KB
+#define SRUKF_PREDICT_FREE_KB 110   // barrier-free measurement loop if the kernel's shared memory stays below this
+#endif
 template <bool MOTION, bool MEAS>
-__global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int save_rsig) {
+__global__ void __launch_bounds__(NT, SRUKF_PREDICT_MINB) k_predict(DevParams p, StepPtrs q, int save_rsig) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   const int b = q.chunk0 + blockIdx.x;
@@ -442,6 +448,9 @@ __global__ void __launch_bounds__(NT, 2) k_predict(DevParams p, StepPtrs q, int 
 // -------------------------------------------------------------------------------------------------
 #ifndef SRUKF_CANON_WARP
 #define SRUKF_CANON_WARP 0
+#endif
+#ifndef SRUKF_D_WIDE
+#define SRUKF_D_WIDE 0   // 1: pivot block of factor_panel with 4 lanes per row
 #endif
 #ifndef SRUKF_INIT_FIRST
 #define SRUKF_INIT_FIRST 0   // 1: issue the P_old loads of a panel before its first tensor copies (measured, see profiles)
@@ -833,33 +842,35 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 16 / NW : 1) k_gain(DevPa
     if (lane == 0 && flags) atomicOr(q.flags + b, flags);
     return;
   }
-  // robot rows: U_r = Pxy_r sii ; padding rows/columns of Ut are zero
-  for (int i = tid; i < 4 * (Lc / 2); i += NTH) {
-    int r = i / (Lc / 2), j = i - r * (Lc / 2);
-    double u0 = 0.0, u1 = 0.0;
-    if (j < L) {
-      const double* pr = q.pxyr + (size_t)b * 8 * L + (size_t)r * L2 + 2 * j;
-      u0 = pr[0] * sii[4 * j] + pr[1] * sii[4 * j + 2];
-      u1 = pr[0] * sii[4 * j + 1] + pr[1] * sii[4 * j + 3];
+  // robot rows: U_r = Pxy_r sii ; padding rows/columns of Ut are zero.  One warp per robot row; the row's state shift
+  // x_r += sum_j U_rj g_j is reduced in registers (the values are not read back from Ut)
+  for (int r = warp; r < 4; r += NW) {
+    double dx = 0.0;
+    for (int j = lane; j < Lc / 2; j += 32) {
+      double u0 = 0.0, u1 = 0.0;
+      if (j < L) {
+        const double* pr = q.pxyr + (size_t)b * 8 * L + (size_t)r * L2 + 2 * j;
+        u0 = pr[0] * sii[4 * j] + pr[1] * sii[4 * j + 2];
+        u1 = pr[0] * sii[4 * j + 1] + pr[1] * sii[4 * j + 3];
+      }
+      Ut[(size_t)(2 * j) * np + nf + r] = u0;
+      Ut[(size_t)(2 * j + 1) * np + nf + r] = u1;
+      dx += u0 * gv[2 * j] + u1 * gv[2 * j + 1];
     }
-    Ut[(size_t)(2 * j) * np + nf + r] = u0;
-    Ut[(size_t)(2 * j + 1) * np + nf + r] = u1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dx += __shfl_xor_sync(0xffffffffu, dx, o);
+    if (!seq_shift && lane == 0) {
+      const double xn = xg[nf + r] + dx;
+      xg[nf + r] = xn;
+      if (!isfinite(xn)) flags |= SRUKF_FLAG_NAN;
+    }
   }
   for (int i = tid; i < Lc * (np - n); i += NTH) {
     int c = i / (np - n), f = n + (i - c * (np - n));
     Ut[(size_t)c * np + f] = 0.0;
   }
-  __syncthreads();
-  if (!seq_shift) {
-    if (tid < 4) {
-      double dx = 0.0;
-      for (int j = 0; j < L; ++j)
-        dx += Ut[(size_t)(2 * j) * np + nf + tid] * gv[2 * j] + Ut[(size_t)(2 * j + 1) * np + nf + tid] * gv[2 * j + 1];
-      const double xn = xg[nf + tid] + dx;
-      xg[nf + tid] = xn;
-      if (!isfinite(xn)) flags |= SRUKF_FLAG_NAN;
-    }
-  } else {
+  if (seq_shift) {
+    __syncthreads();
     // weight type 1: feature-sequential pass, one state row per thread:
     //   U_j = U0_j - dx (c_j^T si_j^-1);  dx += U_j (si_j^-T (z_j - hbar_j))
     for (int r = tid; r < n; r += NTH) {
@@ -925,6 +936,49 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
       }
       __syncwarp();
     }
+#if SRUKF_D_WIDE
+    // ---- D: 8x8 diagonal block, warp 0: lane = 4 * row + column pair (2 columns of one row per lane), so a pivot
+    //      step is one multiply and two fused multiply-adds per lane whatever the pivot (the 8-lane version issued
+    //      7 - j of them); every FP64 instruction of this chain waits for the tensor pipe the other CTA keeps busy ----
+    if (warp == 0) {
+      const int ri = lane >> 2, cp = lane & 3;
+      const double* myrow = Cp + (size_t)(c0 + ri) * CPP + c0 + 2 * cp;
+      double r0 = myrow[0], r1 = myrow[1];
+      double w0 = r0, w1 = r1, dmine = 1.0, cmine = 1.0, rmine = 1.0;
+      const bool diag0 = (ri == 2 * cp), diag1 = (ri == 2 * cp + 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int jc = j >> 1;
+        const double rj = (j & 1) ? r1 : r0;                                // this lane's candidate for column j
+        const double cjj = __shfl_sync(0xffffffffu, rj, 4 * j + jc);       // C(j,j)
+        const double aij = __shfl_sync(0xffffffffu, rj, (lane & ~3) | jc); // C(i,j), unscaled
+        const double ck0 = __shfl_sync(0xffffffffu, rj, 8 * cp + jc);      // C(2cp,j)
+        const double ck1 = __shfl_sync(0xffffffffu, rj, 8 * cp + 4 + jc);  // C(2cp+1,j)
+        const double d = fmax(eps, fabs(cjj));
+        const double rinv = fast_rcp(d);
+        const double lij = aij * rinv;   // L(i,j) = C(i,j)/d_j (:2232), as a multiplication by 1/d_j
+        if (ri == j && cp == jc) { dmine = d; cmine = cjj; rmine = rinv; }   // the lane that holds C(j,j)
+        if (cp == jc) { if (j & 1) { w1 = r1; r1 = lij; } else { w0 = r0; r0 = lij; } }   // column j: keep unscaled C, store L
+        if (2 * cp > j) r0 = fma(-lij, ck0, r0);       // in-block update (:2253), columns right of the pivot only
+        if (2 * cp + 1 > j) r1 = fma(-lij, ck1, r1);
+      }
+      __syncwarp();
+      double* wrow = Wd + (size_t)(c0 + ri) * WDP + c0 + 2 * cp;
+      double* crow = Cp + (size_t)(c0 + ri) * CPP + c0 + 2 * cp;
+      wrow[0] = w0;                              // unscaled C(i,j) (only j <= i is used)
+      wrow[1] = w1;
+      if (2 * cp < ri) crow[0] = r0;             // L(i,j), j < i
+      if (2 * cp + 1 < ri) crow[1] = r1;
+      if (diag0 || diag1) {
+        const double sd = sqrt(dmine), emine = dmine - cmine;   // E_j = D_j - C_jj, :2288
+        dsm[c0 + ri] = rmine;   // 1/d_j for the solve of the rows below
+        sdsm[c0 + ri] = sd;
+        esm[c0 + ri] = emine;
+        if (dmine != cmine && J0 + c0 + ri < n) flags |= (dmine > 16.0 * eps) ? SRUKF_FLAG_GMW_MODIFIED : SRUKF_FLAG_GMW_FLOOR;
+        if (!isfinite(sd) || !isfinite(emine)) flags |= SRUKF_FLAG_NAN;   // fmax(eps, |NaN|) = eps hides a NaN pivot: E = d - c_jj does not
+      }
+    }
+#else
     // ---- D: 8x8 diagonal block, warp 0, lanes 0..7 own rows c0..c0+7 ----
     if (warp == 0) {
       const int li = lane & 7;
@@ -967,6 +1021,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
         }
       }
     }
+#endif
     __syncthreads();
     // ---- T: rows below the 8x8 block ----
     for (int i = c0 + 8 + tid; i < R; i += NTH) {
@@ -2695,7 +2750,7 @@ int gain_dz_box(const DevParams& p) {
 bool predict_free(const DevParams& p) {
   const size_t base = (size_t)p.n + (size_t)p.P * 8 + 40;
   const size_t need = (size_t)(NT / 32) * p.L * 13 + 2 * (size_t)p.L;
-  return sizeof(double) * (base + need) <= 110 * 1024;
+  return sizeof(double) * (base + need) <= (size_t)SRUKF_PREDICT_FREE_KB * 1024;
 }
 size_t predict_smem_bytes(const DevParams& p) {
   size_t work = (size_t)(p.n + 10) * 4 + 10 * (NT / 32);       // motion step: T + the scratch of one 10-value reduction

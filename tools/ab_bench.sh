@@ -8,7 +8,8 @@ for e in "$@"; do
   lib=""; [ "$var" != "-" ] && lib="SRUKF_LIB_PATH=$PWD/variants/lib_$var.so"
   out=gpurun_out/${tag}_${label}
   env $lib $envs python tools/quick_parity.py ${QP:-3:3:2 20:3:2 50:2:2} > $out.quick.log 2>&1; qrc=$?
-  env $lib $envs python bench.py --steps ${STEPS:-5} --warmup 3 --no-cpu-baseline ${BENCH_ARGS} > $out.bench.json 2> $out.bench.err; brc=$?
+  if [ $qrc -ne 0 ] && [ -z "$BENCH_ANYWAY" ]; then echo "$label parity FAILED (rc=$qrc): bench skipped"; tail -3 $out.quick.log; continue; fi
+  env $lib $envs timeout ${BENCH_TIMEOUT:-120} python bench.py --steps ${STEPS:-5} --warmup 3 --no-cpu-baseline ${BENCH_ARGS} > $out.bench.json 2> $out.bench.err; brc=$?
   python - "$label" "$qrc" "$brc" $out.bench.json <<'PY'
 import json, sys
 label, qrc, brc, path = sys.argv[1:5]
