@@ -369,6 +369,7 @@ int srukf_create(int device, int B, int L, const SrukfParams* params, srukf_t** 
   size_t budget = (size_t)12 << 30;   // 65,536 x L = 50: 3 chunks of 21,904 (6 GiB / 6 chunks: +0.65 % per step)
   if (const char* e_ = getenv("SRUKF_SCRATCH_GIB")) { const long g_ = atol(e_); if (g_ > 0) budget = (size_t)g_ << 30; }
   long chunk = (long)(budget / per);
+  if (const char* e_ = getenv("SRUKF_CHUNK")) { const long c_ = atol(e_); if (c_ > 0 && c_ < chunk) chunk = c_; }   // tests: several chunks on a small batch
   if (chunk < 1) chunk = 1;
   if (chunk > B) chunk = B;
   if (chunk >= 592) chunk -= chunk % 296;  // whole waves of two CTAs per SM

@@ -551,6 +551,33 @@ def test_forced_fallback_takes_the_bisection_path_and_matches_the_oracle(gpu, or
     assert ((flags2 & gpu.FLAG_FALLBACK) != 0).all()
 
 
+@pytest.mark.parametrize("L,B,chunk,forced", [(5, 40, 16, False), (20, 21, 8, False), (8, 20, 8, True)])
+def test_several_chunks_per_step_match_the_oracle(gpu, oracle, L, B, chunk, forced, monkeypatch):
+    """A step of a large batch runs predict -> gain -> update per chunk of filters (scratch for dZ / Ut is per chunk, two
+    Ut sets alternate so that a chunk's fallback overlaps the next chunk).  SRUKF_CHUNK forces that structure on a
+    small batch (last chunk shorter): every filter must still match the oracle, also when every filter falls back."""
+    monkeypatch.setenv("SRUKF_CHUNK", str(chunk))
+    if forced:
+        monkeypatch.setenv("SRUKF_FORCE_FALLBACK_PPM", "1000000")
+    worst, flags, sc = run_against_oracle(gpu, oracle, L, B, 3, unique=B)
+    assert not (flags & gpu.FLAG_NAN).any()
+    if forced:
+        assert ((flags & gpu.FLAG_FALLBACK) != 0).all()
+    # and the chunked run is bit-identical to the unchunked one (filters are independent)
+    from cv_monoslam_b200 import CSLAMBatch
+    outs = []
+    for c in (str(chunk), None):
+        if c is None:
+            monkeypatch.delenv("SRUKF_CHUNK")
+        g = CSLAMBatch(B, L)
+        g.set_state(sc.x0, sc.S0)
+        for s in range(3):
+            g.SLAM(sc.u[s], sc.z[s], sc.matched[s])
+        outs.append(g.get_state())
+        g.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def test_unblocked_one_shot_mode_matches_fused_mode(gpu, oracle):
     """downdate_mode 2 (one unblocked GMW of S^T S - U U^T) is the plain-DFMA cross-check of the DMMA path."""
     run_against_oracle(gpu, oracle, 6, 4, 4, mode_gpu=2)
