@@ -2723,6 +2723,13 @@ int update_mq(const DevParams& p) {   // accumulator slots of the 8-warp variant
   const int strips = p.np / 8;
   return strips <= 8 ? 1 : (strips <= 16 ? 2 : (strips <= 24 ? 3 : MAXQ));
 }
+// accumulator slots of the 16-warp variant: 3 for np <= 384 (L = 54..63; 126 registers, no spills: L = 60 77.7 -> 74.4 ms per
+// step of 32,768 filters).  (4 slots for np <= 512 put the accumulators into a 912-byte stack frame -- the K-loop lambda
+// is no longer inlined -- and ran 3.7x slower; <16,4,5> for k_gain lost against <16,4,6>: profiles/r02_gain_tuning.md)
+int update_mq16(const DevParams& p) {
+  if (getenv("SRUKF_UPDATE_MQ5")) return MAXQ;
+  return p.np / 8 <= 48 ? 3 : MAXQ;
+}
 bool update_wide(const DevParams& p) { return p.np > 8 * 16 * MAXQ; }   // the <16, 10, 16, 8> variant
 // k_gain variant: 0 = <8,5,4> (np <= 320, 2 CTAs/SM), 1 = <16,3,7> (np <= 384, 1 CTA/SM, half the passes),
 // 2 = <16,5,4> (np <= 640), 3 = <2,5,4> (np <= 80, 8 CTAs/SM), 4 = <4,5,4> (np <= 160, 4 CTAs/SM), 5 = <16,4,6> (np <= 512)
@@ -2812,7 +2819,7 @@ cudaError_t configure_kernels(const DevParams&) {
   SRUKF_SET((k_gain<2, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<4, 5, 4, 8, NSTAGE>)) SRUKF_SET((k_gain<16, 4, 6, 16, 2>))
   SRUKF_SET((k_update<8, false>)) SRUKF_SET((k_update<16, false>)) SRUKF_SET((k_update<8, true>)) SRUKF_SET((k_update<16, true>))
   SRUKF_SET((k_update<2, false>)) SRUKF_SET((k_update<4, false>)) SRUKF_SET((k_update<16, false, 10, 16, 8>))
-  SRUKF_SET((k_update<8, false, 1>)) SRUKF_SET((k_update<8, false, 2>)) SRUKF_SET((k_update<8, false, 3>))
+  SRUKF_SET((k_update<16, false, 3>)) SRUKF_SET((k_update<8, false, 1>)) SRUKF_SET((k_update<8, false, 2>)) SRUKF_SET((k_update<8, false, 3>))
   SRUKF_SET(k_downdate) SRUKF_SET(k_init_features) SRUKF_SET(k_add_features) SRUKF_SET(k_delete_feature)
   SRUKF_SET(k_chol_update) SRUKF_SET(k_mchol_batch) SRUKF_SET((k_update_seq<8, MAXQ, NB, SRUKF_UPD_ROWS>)) SRUKF_SET((k_update_seq<16, MAXQ, NB, SRUKF_UPD_ROWS>))
 #undef SRUKF_SET
@@ -2856,6 +2863,7 @@ void launch_update(const DevParams& p, const StepPtrs& q, int nblocks, cudaStrea
     default:
       if (update_wide(p)) k_update<16, false, 10, 16, 8><<<nblocks, 512, smem, st>>>(p, q);
       else if (timing) k_update<16, true><<<nblocks, 512, smem, st>>>(p, q);
+      else if (update_mq16(p) == 3) k_update<16, false, 3><<<nblocks, 512, smem, st>>>(p, q);
       else k_update<16, false><<<nblocks, 512, smem, st>>>(p, q);
       break;
   }
