@@ -12,6 +12,7 @@
 //                the panel's modified-Cholesky pivots and a triangular solve.  Writes the other S buffer.
 //   k_downdate : reference-order fallback (unblocked GMW, optional per-column sequence) for flagged filters
 //                and for downdate_mode 1/2.
+#include <type_traits>
 #include <cuda.h>
 
 #include <cstdlib>
@@ -449,6 +450,9 @@ __global__ void __launch_bounds__(NT, SRUKF_PREDICT_MINB) k_predict(DevParams p,
 #ifndef SRUKF_CANON_WARP
 #define SRUKF_CANON_WARP 0
 #endif
+#ifndef SRUKF_U_HOIST
+#define SRUKF_U_HOIST 1   // factor_panel U step: the W fragments of a sub-panel stay in registers (loaded once, not once per strip): 73.3 -> 72.4 ms
+#endif
 #ifndef SRUKF_D_WIDE
 #define SRUKF_D_WIDE 0   // 1: pivot block of factor_panel with 4 lanes per row
 #endif
@@ -474,8 +478,12 @@ constexpr int TW = SRUKF_TW;   // payload columns per TMA box (64 or 128)
 // (4 doubles) apart: pitch == 4 (mod 8).  (pitch == 8 mod 16 put rows k and k+2 on the same banks: ncu counted
 // 48 % of the shared wavefronts of k_update / k_gain as conflicts.)
 constexpr int TP = TW + SRUKF_PAD;
-constexpr int CP_PITCH = NB + 1;  // odd pitch: one row per lane/thread is bank-conflict free
-constexpr int WD_PITCH = NB + 1;
+#ifndef SRUKF_PANEL_PAD
+#define SRUKF_PANEL_PAD 3   // panel pitch = width + pad.  Odd: one row per thread (T step) is conflict-free.  == 3 (mod 16): the DMMA fragment
+                            // loads of the U step (row = lane >> 2, k = lane & 3) hit bank 3g + t: 3 two-way conflicts per half-warp instead of
+                            // the 4-way ones of pitch 33 (28 % of the shared wavefronts of k_update were conflicts): 75.1 -> 72.8 ms per step
+#endif
+constexpr int PPAD = SRUKF_PANEL_PAD;
 
 // indices into the handle's tensor-map table (StepPtrs::tmaps)
 constexpr int TM_S0 = 0;    // +0..7: S buffer 0, boxes of 8/16/../64 rows x TP columns
@@ -911,7 +919,7 @@ template <int NW, int NBT>
 __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm, double* sdsm, double* esm, int R,
                                              int nbe, int J0, int n, double eps, uint32_t& flags) {
   constexpr int NTH = NW * 32;
-  constexpr int CPP = NBT + 1, WDP = NBT + 1;   // odd pitches: one row per lane / thread is bank-conflict free
+  constexpr int CPP = NBT + PPAD, WDP = NBT + PPAD;   // odd pitches: one row per lane / thread is bank-conflict free
   const int tid = threadIdx.x, lane = tid & 31;
 #if SRUKF_CANON_WARP
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: plain shuffles inside `if (warp == 0)`
@@ -924,6 +932,33 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
     if (sb > 0) {
       // ---- U: strips of 8 rows from c0 down, one 8x8 tile each, K = c0.  Warp 0 updates only the strip of the
       //      diagonal block and goes straight on to the pivot chain D, which the other warps' strips overlap ----
+#if SRUKF_U_HOIST
+      // the B fragments (W of the diagonal rows) are the same for every strip: loaded once per sub-panel, K = c0 known
+      // at compile time per case (a predicated-off DMMA would still be issued)
+      auto ustep = [&](auto ksc) {
+        constexpr int KS = decltype(ksc)::value;
+        const double* brow = Wd + (size_t)(c0 + (lane >> 2)) * WDP + (lane & 3);
+        double bf[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) bf[ks] = brow[4 * ks];
+        for (int rs = (warp == 0) ? sb : sb + warp; rs < R / 8; rs += (warp == 0) ? R : NW - 1) {
+          const int i = 8 * rs + (lane >> 2);
+          double* ctile = Cp + (size_t)i * CPP + c0 + 2 * (lane & 3);
+          double a0 = ctile[0], a1 = ctile[1];
+          const double* arow = Cp + (size_t)i * CPP + (lane & 3);
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) dmma(a0, a1, -arow[4 * ks], bf[ks]);
+          ctile[0] = a0;
+          ctile[1] = a1;
+        }
+      };
+      switch (sb) {
+        case 1: ustep(std::integral_constant<int, 2>{}); break;
+        case 2: if constexpr (NBT >= 24) ustep(std::integral_constant<int, 4>{}); break;
+        case 3: if constexpr (NBT >= 32) ustep(std::integral_constant<int, 6>{}); break;
+        default: break;
+      }
+#else
       for (int rs = (warp == 0) ? sb : sb + warp; rs < R / 8; rs += (warp == 0) ? R : NW - 1) {
         const int i = 8 * rs + (lane >> 2);
         double* ctile = Cp + (size_t)i * CPP + c0 + 2 * (lane & 3);
@@ -934,6 +969,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
         ctile[0] = a0;
         ctile[1] = a1;
       }
+#endif
       __syncwarp();
     }
 #if SRUKF_D_WIDE
@@ -1077,7 +1113,7 @@ template <int NW, bool TIMING, int MQ = MAXQ, int NBT = NB, int URW = SRUKF_UPD_
 __global__ void __launch_bounds__(NW * 32, (NW < 8) ? 16 / NW : ((NW == 8) ? ((MQ <= 2) ? 3 : 2) : 1))
     k_update(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
-  constexpr int CPP = NBT + 1, WDP = NBT + 1;
+  constexpr int CPP = NBT + PPAD, WDP = NBT + PPAD;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31;
 #if SRUKF_CANON_WARP
@@ -1627,7 +1663,7 @@ __device__ __noinline__ void seq_literal_column(int n, int np, double eps, const
 template <int NW, int MQ, int NBT, int URW>
 __global__ void __launch_bounds__(NW * 32, SRUKF_SEQ_CTAS) k_update_seq(DevParams p, StepPtrs q) {
   constexpr int NTH = NW * 32;
-  constexpr int CPP = NBT + 1, WDP = NBT + 1;
+  constexpr int CPP = NBT + PPAD, WDP = NBT + PPAD;
   static_assert(MQ <= MAXQ, "the bisection fallback is built for the 5-slot variants (np <= 640)");
   extern __shared__ __align__(128) unsigned char smraw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -2790,10 +2826,10 @@ size_t gain_smem_bytes(const DevParams& p) {
 size_t update_smem_bytes(const DevParams& p) {
   const int nbt = update_wide(p) ? 16 : NB, urw = update_wide(p) ? 8 : SRUKF_UPD_ROWS;
   size_t off = align16(2 * UNS * sizeof(uint64_t));
-  off += sizeof(double) * (nbt * (nbt + 1) + 4 * nbt);
+  off += sizeof(double) * (nbt * (nbt + PPAD) + 4 * nbt);
   off = (off + sizeof(double) * 40 + 127) & ~(size_t)127;
   size_t ring = (size_t)UNS * upd_stage_doubles(p.np, urw);  // stage size is fixed: urw rows at full width
-  size_t panel = (size_t)p.np * (nbt + 1);
+  size_t panel = (size_t)p.np * (nbt + PPAD);
   return off + sizeof(double) * (ring > panel ? ring : panel);
 }
 size_t update_seq_smem_bytes(const DevParams& p) { return update_smem_bytes(p) + sizeof(int) * ((size_t)p.Lc + 104); }
