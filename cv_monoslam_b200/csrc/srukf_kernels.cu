@@ -450,6 +450,9 @@ __global__ void __launch_bounds__(NT, SRUKF_PREDICT_MINB) k_predict(DevParams p,
 #ifndef SRUKF_CANON_WARP
 #define SRUKF_CANON_WARP 0
 #endif
+#ifndef SRUKF_STREAM_P
+#define SRUKF_STREAM_P 0   // 1: k_update reads P_old / writes G with streaming (evict-first) accesses
+#endif
 #ifndef SRUKF_U_HOIST
 #define SRUKF_U_HOIST 1   // factor_panel U step: the W fragments of a sub-panel stay in registers (loaded once, not once per strip): 73.3 -> 72.4 ms
 #endif
@@ -1254,7 +1257,11 @@ __global__ void __launch_bounds__(NW * 32, (NW < 8) ? 16 / NW : ((NW == 8) ? ((M
         if (rs < nstrip && tt < nt) {
           const int j = J0 + 8 * tt + 2 * (lane & 3);
           if (rs > tt) {
+#if SRUKF_STREAM_P   // P_old is read once and G written once per step: streaming accesses leave L2 to the K chunks
+            const double2 v = __ldcs(reinterpret_cast<const double2*>(prow + j));
+#else
             const double2 v = *reinterpret_cast<const double2*>(prow + j);
+#endif
             v0 = v.x; v1 = v.y;
           } else if (rs == tt) {
             v0 = (i > j) ? prow[j] : ((i == j) ? PdOld[i] : 0.0);
@@ -1290,7 +1297,11 @@ __global__ void __launch_bounds__(NW * 32, (NW < 8) ? 16 / NW : ((NW == 8) ? ((M
             const int j = J0 + 8 * tt + 2 * (lane & 3);
             const double g0 = -acc[qq][tt][0], g1 = -acc[qq][tt][1];
             if (rs > tt) {   // strictly below the diagonal; padding entries are exact zeros and zmax starts at 0
+#if SRUKF_STREAM_P
+              __stcs(reinterpret_cast<double2*>(prow + j), make_double2(g0, g1));
+#else
               *reinterpret_cast<double2*>(prow + j) = make_double2(g0, g1);
+#endif
               zmax = fmax(zmax, fmax(g0, g1));
             } else if (rs == tt) {
               if (i > j) prow[j] = g0; else if (i == j) gdiag[i - J0] = g0;
