@@ -450,6 +450,9 @@ __global__ void __launch_bounds__(NT, SRUKF_PREDICT_MINB) k_predict(DevParams p,
 #ifndef SRUKF_CANON_WARP
 #define SRUKF_CANON_WARP 0
 #endif
+#ifndef SRUKF_T_PAIR
+#define SRUKF_T_PAIR 0   // 1: factor_panel's T step takes two rows per thread in one pass
+#endif
 #ifndef SRUKF_STREAM_P
 #define SRUKF_STREAM_P 0   // 1: k_update reads P_old / writes G with streaming (evict-first) accesses
 #endif
@@ -1063,6 +1066,44 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
 #endif
     __syncthreads();
     // ---- T: rows below the 8x8 block ----
+#if SRUKF_T_PAIR
+    // Warps whose rows have a partner NTH further down (R > NTH + 8: the first panels) take both rows in ONE pass -- two
+    // independent substitution chains interleave -- instead of a second, nearly empty pass that costs a full chain latency
+    auto tstep = [&](auto pairc) {
+      constexpr bool PAIR = decltype(pairc)::value;
+      for (int i = c0 + 8 + tid; i < R; i += (PAIR ? 2 : 1) * NTH) {
+        const bool two = PAIR && (i + NTH < R);
+        double* crow = Cp + (size_t)i * CPP + c0;
+        double* crow2 = Cp + (size_t)(two ? i + NTH : i) * CPP + c0;
+        double cf[8], l[8], l2[PAIR ? 8 : 1];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          double a = crow[j], a2 = PAIR ? crow2[j] : 0.0;
+          const double* wj = Wd + (size_t)(c0 + j) * WDP + c0;
+#pragma unroll
+          for (int k = 0; k < j; ++k) {
+            a = fma(-l[k], wj[k], a);
+            if (PAIR) a2 = fma(-l2[PAIR ? k : 0], wj[k], a2);
+          }
+          cf[j] = a;
+          l[j] = a * dsm[c0 + j];
+          if (PAIR) l2[PAIR ? j : 0] = a2 * dsm[c0 + j];
+        }
+        if (i < nbe) {   // rows of the panel's own diagonal block feed later sub-panels as W (i + NTH is never one)
+          double* wrow = Wd + (size_t)i * WDP + c0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) wrow[j] = cf[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) crow[j] = l[j];
+        if (two) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) crow2[j] = l2[PAIR ? j : 0];
+        }
+      }
+    };
+    if (c0 + 8 + (tid & ~31) + NTH < R) tstep(std::true_type{}); else tstep(std::false_type{});
+#else
     for (int i = c0 + 8 + tid; i < R; i += NTH) {
       double* crow = Cp + (size_t)i * CPP + c0;
       double cf[8], l[8];
@@ -1083,6 +1124,7 @@ __device__ __forceinline__ void factor_panel(double* Cp, double* Wd, double* dsm
 #pragma unroll
       for (int j = 0; j < 8; ++j) crow[j] = l[j];
     }
+#endif
     __syncthreads();
   }
 }
